@@ -215,8 +215,8 @@ struct Edge {
     uint32_t n1; uint8_t o1; uint32_t n2; uint8_t o2; uint32_t ov;
     bool operator<(const Edge& b) const {
         if (n1 != b.n1) return n1 < b.n1;
-        if (o1 != b.o1) return o1 < b.o1;
         if (n2 != b.n2) return n2 < b.n2;
+        if (o1 != b.o1) return o1 < b.o1;
         if (o2 != b.o2) return o2 < b.o2;
         return ov < b.ov;
     }

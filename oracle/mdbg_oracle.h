@@ -104,7 +104,7 @@ void orc_graph_stats(const orc_graph* g, orc_stats* out);
 /* Nodes, sorted by index ascending (n_nodes entries).  tuple: n_nodes*k u64.        */
 void orc_graph_nodes(const orc_graph* g, uint32_t* index, uint16_t* abundance, uint32_t* seqlen,
                      uint16_t* shift /* 2 per node */, uint64_t* tuple);
-/* Edges, sorted by (n1,o1,n2,o2,overlap); o = 0 for '+', 1 for '-'.                 */
+/* Edges, sorted by (n1,n2,o1,o2,overlap); o = 0 for '+', 1 for '-'.                 */
 void orc_graph_edges(const orc_graph* g, uint32_t* n1, uint8_t* o1, uint32_t* n2, uint8_t* o2,
                      uint32_t* overlap);
 /* .sequences data lines in emission order: node index, read, [start,end) raw slice,

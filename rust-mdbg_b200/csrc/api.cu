@@ -1,0 +1,405 @@
+// api.cu -- context lifecycle, Entry 1 (Read::extract) and the push half of Entry 3 of the
+// C ABI declared in include/mdbg.h.  Host side only orchestrates: every byte of the hot
+// path is processed by the kernels in ka_*.cu .. ke_*.cu.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "ctx.h"
+
+using namespace mdbg;
+
+static std::string g_create_err;
+
+// ---- Pool -----------------------------------------------------------------------------------
+cudaError_t Pool::alloc(size_t bytes, void** out, size_t* cap_out) {
+    bytes = (bytes + 511) & ~(size_t)511;
+    auto it = free_.lower_bound(bytes);
+    if (it != free_.end() && it->first <= bytes * 2 + (1u << 20)) {
+        *out = it->second;
+        *cap_out = it->first;
+        free_.erase(it);
+        return cudaSuccess;
+    }
+    cudaError_t e = cudaMalloc(out, bytes);
+    if (e != cudaSuccess) {  // release the cache and retry once
+        cudaGetLastError();
+        trim();
+        e = cudaMalloc(out, bytes);
+    }
+    *cap_out = bytes;
+    return e;
+}
+void Pool::release(void* p, size_t cap) { free_.emplace(cap, p); }
+void Pool::trim() {
+    for (auto& kv : free_) cudaFree(kv.second);
+    free_.clear();
+}
+
+// ---- small kernels ---------------------------------------------------------------------------
+__global__ void widen_pos_kernel(const uint32_t* __restrict__ in, uint64_t* __restrict__ out, uint64_t n) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i];
+}
+__global__ void flush_kernel(uint4* p, uint64_t n, uint32_t v) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) p[i] = make_uint4(v, v, v, v);
+}
+
+extern "C" {
+
+const char* mdbg_version(void) { return "mdbg-b200 0.1 (sm_100a)"; }
+
+int mdbg_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+uint64_t mdbg_hash_bound(double density) { return hash_bound(density); }
+
+const char* mdbg_last_error(const mdbg_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int mdbg_ctx_create(const mdbg_params* p, mdbg_ctx** out) {
+    if (!p || !out) { g_create_err = "null argument"; return MDBG_ERR_BAD_ARG; }
+    *out = nullptr;
+    if (p->k < 2 || p->l < 2 || p->l > 64 || p->min_abundance < 1 || p->min_abundance > 65535 ||
+        !(p->density > 0.0)) {
+        g_create_err = "bad parameters: need k >= 2, 2 <= l <= 64, 1 <= min_abundance <= 65535, density > 0";
+        return MDBG_ERR_BAD_ARG;
+    }
+    int n = mdbg_device_count();
+    if (n <= 0) {
+        g_create_err = "no CUDA device: libmdbg_b200 has no CPU fallback";
+        return MDBG_ERR_NO_DEVICE;
+    }
+    if (p->device < 0 || p->device >= n) { g_create_err = "bad device ordinal"; return MDBG_ERR_BAD_ARG; }
+    mdbg_ctx* c = new mdbg_ctx();
+    c->p = *p;
+    c->device = p->device;
+    c->bound = hash_bound(p->density);
+    c->fc = make_filter(p->l, c->bound);
+    cudaError_t e = cudaSetDevice(c->device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking);
+    cudaDeviceProp prop;
+    if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, c->device);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_sc, sizeof(Scalars));
+    if (e == cudaSuccess) e = cudaMallocHost(&c->h_sc, sizeof(Scalars));
+    for (int i = 0; i < 16 && e == cudaSuccess; i++) e = cudaEventCreate(&c->ev[i]);
+    if (e != cudaSuccess) {
+        g_create_err = std::string("CUDA init failed: ") + cudaGetErrorString(e);
+        delete c;
+        return MDBG_ERR_CUDA;
+    }
+    c->num_sms = prop.multiProcessorCount;
+    int per_sm = ka_max_blocks_per_sm(p->hpc);
+    if (per_sm < 1) per_sm = 1;
+    c->ka_grid = c->num_sms * per_sm;
+    memset(&c->tm, 0, sizeof(c->tm));
+    *out = c;
+    return MDBG_OK;
+}
+
+void mdbg_graph_device_free(mdbg_ctx* ctx);  // graph.cu
+
+void mdbg_ctx_destroy(mdbg_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->st);
+    mdbg_graph_device_free(c);
+    if (c->m_hash) cudaFree(c->m_hash);
+    if (c->m_pos) cudaFree(c->m_pos);
+    if (c->m_off) cudaFree(c->m_off);
+    if (c->l2_flush) cudaFree(c->l2_flush);
+    if (c->d_sc) cudaFree(c->d_sc);
+    if (c->h_sc) cudaFreeHost(c->h_sc);
+    for (int i = 0; i < 16; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    c->pool.trim();
+    if (c->st) cudaStreamDestroy(c->st);
+    delete c;
+}
+
+int mdbg_ctx_set_k(mdbg_ctx* c, uint32_t k, uint32_t min_abundance, float presimp) {
+    if (!c || k < 2 || min_abundance < 1 || min_abundance > 65535) {
+        if (c) c->err = "bad k / min_abundance";
+        return MDBG_ERR_BAD_ARG;
+    }
+    c->p.k = k;
+    c->p.min_abundance = min_abundance;
+    c->p.presimp = presimp;
+    return MDBG_OK;
+}
+
+void* mdbg_stream(mdbg_ctx* c) { return c ? (void*)c->st : nullptr; }
+
+int mdbg_reset(mdbg_ctx* c) {
+    if (!c) return MDBG_ERR_BAD_ARG;
+    MDBG_CK(c, cudaSetDevice(c->device));
+    c->M = c->R = c->n_bases = 0;
+    c->tm.ka_launches = 0;
+    c->tm.ka_ms_sum = 0;
+    mdbg_graph_device_free(c);
+    return MDBG_OK;
+}
+
+}  // extern "C"
+
+// grow a persistent arena array, preserving `keep` bytes
+static int grow(mdbg_ctx* c, void** p, size_t* cap, size_t need, size_t keep) {
+    if (*cap >= need) return MDBG_OK;
+    size_t ncap = std::max(need, *cap + *cap / 2);
+    ncap = (ncap + 4095) & ~(size_t)4095;
+    void* q = nullptr;
+    MDBG_CK(c, cudaMalloc(&q, ncap));
+    if (*p) {
+        if (keep) MDBG_CK(c, cudaMemcpyAsync(q, *p, keep, cudaMemcpyDeviceToDevice, c->st));
+        MDBG_CK(c, cudaStreamSynchronize(c->st));
+        MDBG_CK(c, cudaFree(*p));
+    }
+    *p = q;
+    *cap = ncap;
+    return MDBG_OK;
+}
+
+static int ensure_arena(mdbg_ctx* c, uint64_t m_items, uint64_t r_items) {
+    int rc;
+    if ((rc = grow(c, (void**)&c->m_hash, &c->m_hash_cap, m_items * 8, c->M * 8))) return rc;
+    if ((rc = grow(c, (void**)&c->m_pos, &c->m_pos_cap, m_items * 4, c->M * 4))) return rc;
+    if ((rc = grow(c, (void**)&c->m_off, &c->m_off_cap, (r_items + 1) * 8, (c->R + 1) * 8))) return rc;
+    c->m_cap_items = std::min(c->m_hash_cap / 8, c->m_pos_cap / 4);
+    return MDBG_OK;
+}
+
+// Run K-A on a device-resident batch, appending to the arena.
+static int run_ka(mdbg_ctx* c, const uint8_t* d_bases, const uint64_t* d_read_off, uint64_t R, uint64_t B) {
+    if (((uintptr_t)d_bases & 15) != 0) { c->err = "bases must be 16-byte aligned"; return MDBG_ERR_BAD_ARG; }
+    // expected minimizers: ~2.2*density of the HPC positions; start with a generous estimate and
+    // re-run the batch once with the exact size if it did not fit.
+    double rho = std::min(1.0, 2.6 * c->p.density + 1e-4);
+    uint64_t est = (uint64_t)((double)B * rho) + 4096;
+    int rc;
+    if (c->M == 0 && c->R == 0 && c->m_off == nullptr) {
+        if ((rc = ensure_arena(c, est, R))) return rc;
+        MDBG_CK(c, cudaMemsetAsync(c->m_off, 0, 8, c->st));
+    } else if ((rc = ensure_arena(c, c->M + est, c->R + R))) return rc;
+
+    uint64_t n_tiles = std::max<uint64_t>(1, (B + KA_TILE - 1) / KA_TILE);
+    Tmp<uint64_t> tile_state, tile_lb;
+    MDBG_CK(c, tile_state.get(c->pool, n_tiles));
+    MDBG_CK(c, tile_lb.get(c->pool, n_tiles + 1));
+
+    for (int attempt = 0; attempt < 2; attempt++) {
+        Scalars init{};
+        init.err_pos = ~0ull;
+        *c->h_sc = init;
+        MDBG_CK(c, cudaMemcpyAsync(c->d_sc, c->h_sc, sizeof(Scalars), cudaMemcpyHostToDevice, c->st));
+        KAArgs A{};
+        A.bases = d_bases; A.read_off = d_read_off; A.n_reads = R; A.n_bases = B;
+        A.l = c->p.l; A.bound = c->bound; A.fc = c->fc; A.force_dense = 0;
+        A.out_hash = c->m_hash; A.out_pos = c->m_pos; A.out_read_off = c->m_off;
+        A.out_base = c->M; A.out_cap = c->m_cap_items; A.read_base = c->R;
+        A.total_out = &c->d_sc->total_out; A.err_pos = &c->d_sc->err_pos;
+        A.dense_tiles = &c->d_sc->dense_tiles; A.tile_counter = &c->d_sc->tile_counter;
+        A.tile_state = tile_state; A.tile_lb = tile_lb; A.n_tiles = n_tiles;
+        MDBG_CK(c, cudaEventRecord(c->ev[0], c->st));
+        MDBG_CK(c, ka_launch(A, c->p.hpc, c->ka_grid, c->st, &c->tm.launches_push));
+        MDBG_CK(c, cudaEventRecord(c->ev[1], c->st));
+        MDBG_CK(c, cudaMemcpyAsync(c->h_sc, c->d_sc, sizeof(Scalars), cudaMemcpyDeviceToHost, c->st));
+        MDBG_CK(c, cudaStreamSynchronize(c->st));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+        c->tm.ms_ka = ms;
+        c->tm.ka_ms_sum += ms;
+        c->tm.ka_launches += 1;
+        c->tm.ka_dense_tiles = c->h_sc->dense_tiles;
+        if (c->h_sc->err_pos != ~0ull) {
+            char buf[160];
+            snprintf(buf, sizeof buf, "Non-ACGTN nucleotide encountered! (batch byte offset %llu)", c->h_sc->err_pos);
+            c->err = buf;
+            return MDBG_ERR_ALPHABET;
+        }
+        uint64_t total = c->h_sc->total_out;
+        if (total <= c->m_cap_items) {
+            c->M = total;
+            c->R += R;
+            c->n_bases += B;
+            return MDBG_OK;
+        }
+        if ((rc = ensure_arena(c, total + 1024, c->R + R))) return rc;  // exact size, run again
+    }
+    c->err = "minimizer arena overflow after resize";
+    return MDBG_ERR_CAPACITY;
+}
+
+extern "C" {
+
+int mdbg_push_reads_device(mdbg_ctx* c, const uint8_t* d_bases, const uint64_t* d_read_off,
+                           uint64_t n_reads, uint64_t n_bases) {
+    if (!c) return MDBG_ERR_BAD_ARG;
+    MDBG_CK(c, cudaSetDevice(c->device));
+    c->tm.launches_push = 0;
+    c->tm.ms_h2d = 0;
+    MDBG_CK(c, cudaEventRecord(c->ev[2], c->st));
+    int rc = run_ka(c, d_bases, d_read_off, n_reads, n_bases);
+    if (rc) return rc;
+    MDBG_CK(c, cudaEventRecord(c->ev[3], c->st));
+    MDBG_CK(c, cudaEventSynchronize(c->ev[3]));
+    cudaEventElapsedTime(&c->tm.ms_total_push, c->ev[2], c->ev[3]);
+    return MDBG_OK;
+}
+
+int mdbg_push_reads(mdbg_ctx* c, const uint8_t* bases, const uint64_t* read_off, uint64_t n_reads) {
+    if (!c || !read_off || (n_reads && !bases && read_off[n_reads] != 0)) {
+        if (c) c->err = "null argument";
+        return MDBG_ERR_BAD_ARG;
+    }
+    MDBG_CK(c, cudaSetDevice(c->device));
+    uint64_t B = read_off[n_reads];
+    c->tm.launches_push = 0;
+    Tmp<uint8_t> d_bases;
+    Tmp<uint64_t> d_off;
+    MDBG_CK(c, d_bases.get(c->pool, B + 16));
+    MDBG_CK(c, d_off.get(c->pool, n_reads + 1));
+    MDBG_CK(c, cudaEventRecord(c->ev[2], c->st));
+    if (B) MDBG_CK(c, cudaMemcpyAsync(d_bases, bases, B, cudaMemcpyHostToDevice, c->st));
+    MDBG_CK(c, cudaMemcpyAsync(d_off, read_off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, c->st));
+    MDBG_CK(c, cudaEventRecord(c->ev[4], c->st));
+    int rc = run_ka(c, d_bases, d_off, n_reads, B);
+    if (rc == MDBG_ERR_ALPHABET) {  // turn the batch offset into (read, offset) like SURVEY 5 asks
+        uint64_t pos = c->h_sc->err_pos;
+        uint64_t r = std::upper_bound(read_off, read_off + n_reads + 1, pos) - read_off - 1;
+        char buf[200];
+        snprintf(buf, sizeof buf, "Non-ACGTN nucleotide encountered! (read %llu, offset %llu, byte 0x%02x)",
+                 (unsigned long long)(c->R + r), (unsigned long long)(pos - read_off[r]), bases[pos]);
+        c->err = buf;
+    }
+    if (rc) return rc;
+    MDBG_CK(c, cudaEventRecord(c->ev[3], c->st));
+    MDBG_CK(c, cudaEventSynchronize(c->ev[3]));
+    cudaEventElapsedTime(&c->tm.ms_h2d, c->ev[2], c->ev[4]);
+    cudaEventElapsedTime(&c->tm.ms_total_push, c->ev[2], c->ev[3]);
+    return MDBG_OK;
+}
+
+int mdbg_get_minimizers(mdbg_ctx* c, uint64_t* hash, uint64_t* pos, uint64_t* read_off, uint64_t cap,
+                        uint64_t* n_out) {
+    if (!c) return MDBG_ERR_BAD_ARG;
+    MDBG_CK(c, cudaSetDevice(c->device));
+    if (n_out) *n_out = c->M;
+    if (read_off) {
+        if (c->m_off) MDBG_CK(c, cudaMemcpyAsync(read_off, c->m_off, (c->R + 1) * 8, cudaMemcpyDeviceToHost, c->st));
+        else read_off[0] = 0;
+    }
+    if (c->M > cap && (hash || pos)) {
+        MDBG_CK(c, cudaStreamSynchronize(c->st));
+        c->err = "output capacity too small";
+        return MDBG_ERR_CAPACITY;
+    }
+    if (hash && c->M) MDBG_CK(c, cudaMemcpyAsync(hash, c->m_hash, c->M * 8, cudaMemcpyDeviceToHost, c->st));
+    if (pos && c->M) {
+        Tmp<uint64_t> wide;
+        MDBG_CK(c, wide.get(c->pool, c->M));
+        widen_pos_kernel<<<(unsigned)((c->M + 255) / 256), 256, 0, c->st>>>(c->m_pos, wide, c->M);
+        MDBG_CK(c, cudaGetLastError());
+        MDBG_CK(c, cudaMemcpyAsync(pos, wide, c->M * 8, cudaMemcpyDeviceToHost, c->st));
+        MDBG_CK(c, cudaStreamSynchronize(c->st));
+    }
+    MDBG_CK(c, cudaStreamSynchronize(c->st));
+    return MDBG_OK;
+}
+
+int mdbg_extract_minimizers(mdbg_ctx* c, const uint8_t* bases, const uint64_t* read_off, uint64_t n_reads,
+                            uint64_t* out_hash, uint64_t* out_pos, uint64_t* out_read_off, uint64_t cap,
+                            uint64_t* n_out) {
+    if (!c) return MDBG_ERR_BAD_ARG;
+    // Stateless with respect to the pushed reads: run on a scratch arena.
+    uint64_t sM = c->M, sR = c->R, sB = c->n_bases;
+    uint64_t* sh = c->m_hash; uint32_t* sp = c->m_pos; uint64_t* so = c->m_off;
+    size_t shc = c->m_hash_cap, spc = c->m_pos_cap, soc = c->m_off_cap;
+    uint64_t smc = c->m_cap_items;
+    c->M = c->R = c->n_bases = 0;
+    c->m_hash = nullptr; c->m_pos = nullptr; c->m_off = nullptr;
+    c->m_hash_cap = c->m_pos_cap = c->m_off_cap = 0; c->m_cap_items = 0;
+    int rc = mdbg_push_reads(c, bases, read_off, n_reads);
+    if (rc == MDBG_OK) rc = mdbg_get_minimizers(c, out_hash, out_pos, out_read_off, cap, n_out);
+    else if (n_out) *n_out = 0;
+    cudaSetDevice(c->device);
+    if (c->m_hash) cudaFree(c->m_hash);
+    if (c->m_pos) cudaFree(c->m_pos);
+    if (c->m_off) cudaFree(c->m_off);
+    c->M = sM; c->R = sR; c->n_bases = sB;
+    c->m_hash = sh; c->m_pos = sp; c->m_off = so;
+    c->m_hash_cap = shc; c->m_pos_cap = spc; c->m_off_cap = soc; c->m_cap_items = smc;
+    return rc;
+}
+
+int mdbg_read_extract(mdbg_ctx* c, const uint8_t* seq, uint64_t len, uint64_t* out_hash, uint64_t* out_pos,
+                      uint64_t cap, uint64_t* n_out) {
+    uint64_t off[2] = {0, len};
+    uint64_t ro[2];
+    return mdbg_extract_minimizers(c, seq, off, 1, out_hash, out_pos, ro, cap, n_out);
+}
+
+int mdbg_get_timings(mdbg_ctx* c, mdbg_timings* out) {
+    if (!c || !out) return MDBG_ERR_BAD_ARG;
+    *out = c->tm;
+    return MDBG_OK;
+}
+
+// ---- memory helpers ---------------------------------------------------------------------------
+int mdbg_device_malloc(mdbg_ctx* c, uint64_t bytes, void** out) {
+    if (!c || !out) return MDBG_ERR_BAD_ARG;
+    MDBG_CK(c, cudaSetDevice(c->device));
+    MDBG_CK(c, cudaMalloc(out, bytes ? bytes : 16));
+    return MDBG_OK;
+}
+int mdbg_device_free(mdbg_ctx* c, void* p) {
+    if (!c) return MDBG_ERR_BAD_ARG;
+    MDBG_CK(c, cudaSetDevice(c->device));
+    MDBG_CK(c, cudaFree(p));
+    return MDBG_OK;
+}
+int mdbg_host_alloc_pinned(uint64_t bytes, void** out) {
+    if (!out) return MDBG_ERR_BAD_ARG;
+    if (cudaMallocHost(out, bytes ? bytes : 16) != cudaSuccess) { cudaGetLastError(); return MDBG_ERR_CUDA; }
+    return MDBG_OK;
+}
+int mdbg_host_free_pinned(void* p) { return cudaFreeHost(p) == cudaSuccess ? MDBG_OK : MDBG_ERR_CUDA; }
+int mdbg_memcpy_h2d(mdbg_ctx* c, void* dst, const void* src, uint64_t bytes) {
+    if (!c) return MDBG_ERR_BAD_ARG;
+    MDBG_CK(c, cudaSetDevice(c->device));
+    MDBG_CK(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->st));
+    MDBG_CK(c, cudaStreamSynchronize(c->st));
+    return MDBG_OK;
+}
+int mdbg_memcpy_d2h(mdbg_ctx* c, void* dst, const void* src, uint64_t bytes) {
+    if (!c) return MDBG_ERR_BAD_ARG;
+    MDBG_CK(c, cudaSetDevice(c->device));
+    MDBG_CK(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->st));
+    MDBG_CK(c, cudaStreamSynchronize(c->st));
+    return MDBG_OK;
+}
+int mdbg_sync(mdbg_ctx* c) {
+    if (!c) return MDBG_ERR_BAD_ARG;
+    MDBG_CK(c, cudaSetDevice(c->device));
+    MDBG_CK(c, cudaStreamSynchronize(c->st));
+    return MDBG_OK;
+}
+int mdbg_flush_l2(mdbg_ctx* c) {
+    if (!c) return MDBG_ERR_BAD_ARG;
+    MDBG_CK(c, cudaSetDevice(c->device));
+    if (!c->l2_flush) {
+        c->l2_flush_bytes = 256u << 20;  // 2x the 126 MB L2
+        MDBG_CK(c, cudaMalloc(&c->l2_flush, c->l2_flush_bytes));
+    }
+    static uint32_t v = 0;
+    flush_kernel<<<c->num_sms * 8, 256, 0, c->st>>>((uint4*)c->l2_flush, c->l2_flush_bytes / 16, ++v);
+    MDBG_CK(c, cudaGetLastError());
+    return MDBG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,44 @@
+// comm.cu -- NCCL plumbing for the multi-GPU path (one process per GPU).  The unique id is
+// created on rank 0 by mdbg_nccl_unique_id and shipped by the host (torch.distributed
+// broadcast in bench.py / tests); the exchange itself is in graph_mgpu.cu.
+#include <cstring>
+#include <string>
+
+#include "ctx.h"
+#include "nccl_dl.h"
+
+using namespace mdbg;
+
+extern "C" {
+
+int mdbg_nccl_unique_id(uint8_t id[MDBG_NCCL_ID_BYTES]) {
+    static_assert(sizeof(ncclUniqueId) <= MDBG_NCCL_ID_BYTES, "ncclUniqueId larger than MDBG_NCCL_ID_BYTES");
+    NcclApi& N = nccl();
+    if (!N.ok) return MDBG_ERR_NCCL;
+    ncclUniqueId u;
+    if (N.GetUniqueId(&u) != ncclSuccess) return MDBG_ERR_NCCL;
+    memset(id, 0, MDBG_NCCL_ID_BYTES);
+    memcpy(id, &u, sizeof(u));
+    return MDBG_OK;
+}
+
+int mdbg_comm_init(mdbg_ctx* c, const uint8_t id[MDBG_NCCL_ID_BYTES], int rank, int world) {
+    if (!c || !id || world < 1 || rank < 0 || rank >= world) return MDBG_ERR_BAD_ARG;
+    NcclApi& N = nccl();
+    if (!N.ok) { c->err = "libnccl.so.2 could not be loaded"; return MDBG_ERR_NCCL; }
+    MDBG_CK(c, cudaSetDevice(c->device));
+    ncclUniqueId u;
+    memcpy(&u, id, sizeof(u));
+    ncclComm_t comm;
+    ncclResult_t r = N.CommInitRank(&comm, world, u, rank);
+    if (r != ncclSuccess) {
+        c->err = std::string("ncclCommInitRank: ") + N.GetErrorString(r);
+        return MDBG_ERR_NCCL;
+    }
+    c->comm = (void*)comm;
+    c->rank = rank;
+    c->world = world;
+    return MDBG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,100 @@
+// ctx.h -- the per-GPU context behind the C ABI (include/mdbg.h): stream, caching device
+// allocator, the resident minimizer arena, scalar mailboxes, timing events.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/mdbg.h"
+#include "mdbg_kernels.h"
+
+namespace mdbg {
+
+// Caching allocator: after warm-up a push/finish cycle performs no cudaMalloc/cudaFree.
+class Pool {
+public:
+    ~Pool() { trim(); }
+    cudaError_t alloc(size_t bytes, void** out, size_t* cap_out);
+    void release(void* p, size_t cap);
+    void trim();
+private:
+    std::multimap<size_t, void*> free_;
+};
+
+// RAII scratch buffer from the pool.
+template <class T>
+struct Tmp {
+    Pool* pool = nullptr;
+    T* p = nullptr;
+    size_t cap = 0, n = 0;
+    Tmp() {}
+    Tmp(const Tmp&) = delete;
+    Tmp& operator=(const Tmp&) = delete;
+    Tmp(Tmp&& o) noexcept { *this = std::move(o); }
+    Tmp& operator=(Tmp&& o) noexcept {
+        if (this != &o) { reset(); pool = o.pool; p = o.p; cap = o.cap; n = o.n; o.p = nullptr; o.cap = 0; o.n = 0; }
+        return *this;
+    }
+    ~Tmp() { reset(); }
+    cudaError_t get(Pool& pl, size_t count) {
+        reset();
+        pool = &pl;
+        n = count;
+        void* q = nullptr;
+        cudaError_t e = pl.alloc((count ? count : 1) * sizeof(T), &q, &cap);
+        p = (T*)q;
+        return e;
+    }
+    void reset() {
+        if (p && pool) pool->release(p, cap);
+        p = nullptr; cap = 0; n = 0;
+    }
+    operator T*() const { return p; }
+};
+
+struct Scalars {  // device mailbox mirrored into pinned host memory
+    unsigned long long total_out;
+    unsigned long long err_pos;
+    unsigned int dense_tiles;
+    unsigned int tile_counter;
+    unsigned long long v[12];   // stage-specific counters (see api.cu)
+};
+
+}  // namespace mdbg
+
+struct mdbg_ctx {
+    mdbg_params p{};
+    uint64_t bound = 0;
+    mdbg::FilterConsts fc{};
+    int device = 0, num_sms = 0, ka_grid = 0;
+    cudaStream_t st = nullptr;
+    std::string err;
+    mdbg::Pool pool;
+    // resident minimizer arena (global read order)
+    uint64_t* m_hash = nullptr; size_t m_hash_cap = 0;   // bytes
+    uint32_t* m_pos = nullptr;  size_t m_pos_cap = 0;
+    uint64_t* m_off = nullptr;  size_t m_off_cap = 0;
+    uint64_t M = 0, R = 0, n_bases = 0;
+    uint64_t m_cap_items = 0, r_cap_items = 0;
+    mdbg::Scalars* d_sc = nullptr;
+    mdbg::Scalars* h_sc = nullptr;   // pinned
+    void* l2_flush = nullptr; size_t l2_flush_bytes = 0;
+    cudaEvent_t ev[16]{};
+    mdbg_timings tm{};
+    // NCCL (multi-GPU)
+    void* comm = nullptr; int rank = 0, world = 1;
+    // device-resident result of the last finish (kept until the next finish/reset)
+    struct DeviceGraph* dg = nullptr;
+};
+
+#define MDBG_CK(ctx, call)                                                                   \
+    do {                                                                                     \
+        cudaError_t _e = (call);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(_e);                 \
+            return MDBG_ERR_CUDA;                                                            \
+        }                                                                                    \
+    } while (0)

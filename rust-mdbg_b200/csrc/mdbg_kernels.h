@@ -1,0 +1,40 @@
+// mdbg_kernels.h -- internal launch interfaces between the context (api.cu) and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mdbg_common.cuh"
+
+namespace mdbg {
+
+// ---- K-A (ka_minimizers.cu) ----------------------------------------------------------------
+constexpr int KA_THREADS = 128;
+constexpr int KA_SEG = 128;                    // bytes walked by one thread
+constexpr int KA_TILE = KA_THREADS * KA_SEG;   // 16 KiB of bases per CTA iteration
+
+struct KAArgs {
+    const uint8_t* bases;        // concatenated ASCII reads (16-byte aligned)
+    const uint64_t* read_off;    // [n_reads + 1], offsets into bases
+    uint64_t n_reads, n_bases;
+    uint32_t l;
+    uint64_t bound;              // hash_bound(density), computed on the host in f64
+    FilterConsts fc;
+    int force_dense;
+    // outputs (global, (read, position)-ordered)
+    uint64_t* out_hash;
+    uint32_t* out_pos;           // raw position inside the read
+    uint64_t* out_read_off;      // [read_base + r] = index of read r's first minimizer
+    uint64_t out_base, out_cap, read_base;
+    unsigned long long* total_out;   // out_base + minimizers of this batch
+    unsigned long long* err_pos;     // min byte offset of an illegal base that was hashed
+    unsigned int* dense_tiles;
+    // scratch
+    uint64_t* tile_state;        // [n_tiles]
+    uint64_t* tile_lb;           // [n_tiles + 1]
+    unsigned int* tile_counter;
+    uint64_t n_tiles;
+};
+cudaError_t ka_launch(const KAArgs& A, int hpc, int grid, cudaStream_t st, uint64_t* launches);
+int ka_max_blocks_per_sm(int hpc);
+
+}  // namespace mdbg
