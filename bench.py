@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py -- reads -> mdBG throughput on B200 (BASELINE.json metric), one JSON line on stdout.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+  (N > 1: launched by `python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N`)
+
+A "step" is one pass of the hot path over one batch of synthetic HiFi-shape reads: minimizer
+extraction (K-A) + windowing/canonicalisation (K-B) + node table (K-C/K-D) + edges (K-E).
+`value` is timed with the reads already resident in HBM (CUDA events on the launching stream);
+`e2e` is the same metric through the host-facing C ABI with pinned HOST buffers: H2D of the
+reads and D2H of the graph are inside the timed region.  The default workload is BASELINE
+config 2 (synthetic E. coli 5 Mbp, HiFi 50x, k=21 l=12 d=0.003); per-GPU work is fixed as N
+grows (weak scaling): rank r builds reads [r*R, (r+1)*R) of the same job.
+`--impl reference` times the CPU restatement of the reference algorithm (oracle/, the Rust
+reference cannot be built in this image) in the reference's thread structure on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[1] / configs[2] (configs[0] is the CPU-runnable example, a parity case)
+    "ecoli50x": dict(genome_len=5_000_000, coverage=50.0, k=21, l=12, density=0.003,
+                     desc="synthetic E. coli 5 Mbp HiFi 50x, k=21 l=12 d=0.003"),
+    "dmel50x": dict(genome_len=140_000_000, coverage=50.0, k=35, l=12, density=0.002,
+                    desc="synthetic D. melanogaster 140 Mbp HiFi 50x, k=35 l=12 d=0.002"),
+    "tiny": dict(genome_len=200_000, coverage=20.0, k=21, l=12, density=0.003, desc="smoke-size"),
+}
+MIN_ABUNDANCE, PRESIMP = 2, 0.01
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.proc, self.path = device, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return None
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if not sm:
+            return None
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_reference_run(wl, n_reads, steps, warmup):
+    """The reference algorithm on the host cores (oracle/ in the reference's thread structure)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py
+    import rust_mdbg_b200 as m
+    cores = host_threads()
+    s = m.Synth(genome_len=wl["genome_len"])
+    ro, total = s.plan(0, n_reads)
+    host = s.fill_host(0, n_reads, ro, threads=cores)
+    times = []
+    stats = None
+    for i in range(warmup + steps):
+        t = time.perf_counter()
+        g = oracle_py.build_graph(host, ro, wl["k"], wl["l"], wl["density"], MIN_ABUNDANCE, PRESIMP, threads=cores)
+        dt = time.perf_counter() - t
+        stats = g.stats
+        g.close()
+        if i >= warmup:
+            times.append(dt)
+    sec = sum(times) / max(1, len(times))
+    return total / sec / 1e9, cores, total, sec, stats
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="ecoli50x", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+
+    import rust_mdbg_b200 as m
+    synth = m.Synth(genome_len=wl["genome_len"])
+    reads_per_rank = synth.num_reads(wl["coverage"])
+    config = {"workload": wl["desc"], "reads_per_gpu": reads_per_rank, "min_abundance": MIN_ABUNDANCE,
+              "presimp": PRESIMP, "hpc": True, "input": "ASCII bases, 1 B/base",
+              "l2": "inputs (>= 250 MB per GPU) larger than the 126 MB L2; no explicit flush",
+              "sharding": "reads by record, contiguous ranges per rank" if world > 1 else "single GPU"}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        n = max(64, reads_per_rank // 4)          # bounded sample of the same workload per step
+        v, cores, total, sec, st = cpu_reference_run(wl, n, steps, warmup)
+        sample = "first %d reads (%d bases) of the workload per step" % (n, total)
+        out = {"impl": "reference", "metric": "Gbases/sec reads->mdBG", "value": v, "unit": "Gbases/s",
+               "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3,
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+               "data": "synthetic", "config": config,
+               "cpu_baseline": {"value": v, "unit": "Gbases/s", "cores": cores, "kind": "port", "sample": sample},
+               "e2e": {"value": v, "unit": "Gbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+               "note": "CPU restatement of the reference algorithm in its thread structure (oracle/); the Rust "
+                       "binary cannot be built in this image (no cargo/rustc)"}
+        print(json.dumps(out))
+        return 0
+
+    # ------------------------------------------------------------------ our arm (GPU)
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    P = m.Params(k=wl["k"], l=wl["l"], density=wl["density"], min_abundance=MIN_ABUNDANCE, presimp=PRESIMP,
+                 device=local_rank)
+    ctx = m.Context(P)
+    if world > 1:
+        ids = [m.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        ctx.comm_init(ids[0], rank, world)
+
+    first = rank * reads_per_rank
+    ro, total = synth.plan(first, reads_per_rank)
+    d_bases = ctx.device_malloc(total + 64)
+    d_off = ctx.device_malloc((reads_per_rank + 1) * 8)
+    synth.fill_device(ctx, first, reads_per_rank, ro, d_bases, d_off)
+
+    def step_device():
+        ctx.reset()
+        ctx.push_reads_device(d_bases, d_off, reads_per_rank, total)
+        return ctx.finish_device()
+
+    for _ in range(warmup):
+        step_device()
+    sampler = ClockSampler(local_rank)
+    ctx.sync(); barrier()
+    sampler.start()
+    ctx.timer_start()
+    t0 = time.perf_counter()
+    ka_ms, launches, stats = 0.0, 0, None
+    stage = {"ka": 0.0, "kb": 0.0, "kc": 0.0, "kd": 0.0, "ke": 0.0}
+    for _ in range(steps):
+        stats = step_device()
+        tm = ctx.timings()
+        ka_ms += tm["ms_ka"]
+        launches += tm["launches_push"] + tm["launches_finish"]
+        for s_ in stage:
+            stage[s_] += tm["ms_" + s_]
+    ctx.sync()
+    dev_ms = ctx.timer_stop()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    barrier()
+    clocks = sampler.stop()
+    dev_ms = max_over_ranks(dev_ms)
+    wall_ms = max_over_ranks(wall_ms)
+    bases_all = sum_over_ranks(float(total))
+    value = bases_all * steps / (dev_ms * 1e-3) / 1e9
+
+    # roofline of the dominant kernel (K-A), algorithmic bytes per launch
+    M = stats["n_minimizers"]
+    alg_bytes = total + 12 * M + 16 * (reads_per_rank + 1)
+    ka_avg_ms = ka_ms / steps
+    achieved = alg_bytes / (ka_avg_ms * 1e-3) / 1e9
+    peak, peak_src = measured_peak()
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "ka_traffic.json")
+    if os.path.exists(tp):
+        try:
+            tj = json.load(open(tp))
+            if tj.get("workload") == args.workload:
+                traffic = tj.get("dram_bytes_per_launch")
+        except Exception:
+            pass
+    roofline = {"kernel": "ka_minimizers_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": ka_avg_ms,
+                "share_of_step": ka_avg_ms / (dev_ms / steps)}
+
+    # ------------------------------------------------------------------ e2e through the host ABI
+    e2e = None
+    if not args.no_e2e:
+        import ctypes
+        import numpy as np
+        hb = ctx.host_alloc_pinned(total + 64)
+        ho = ctx.host_alloc_pinned((reads_per_rank + 1) * 8)
+        hb_arr = np.ctypeslib.as_array(ctypes.cast(hb, ctypes.POINTER(ctypes.c_uint8)), shape=(total,))
+        ho_arr = np.ctypeslib.as_array(ctypes.cast(ho, ctypes.POINTER(ctypes.c_uint64)), shape=(reads_per_rank + 1,))
+        ho_arr[:] = ro
+        ctx.d2h(hb_arr, d_bases)     # same bytes as the device copy (generated on the device)
+        d2h_bytes = 0
+
+        def step_e2e():
+            ctx.reset()
+            ctx.push_reads_ptr(hb, ho, reads_per_rank)
+            cg = ctx.finish_raw(want_seqlines=False)
+            nb = cg.n_nodes * (4 + 2 + 4 + 4 + 8 * cg.k) + cg.n_edges * (4 + 1 + 4 + 1 + 4)
+            ctx.graph_free(cg)
+            return nb
+
+        for _ in range(max(1, warmup)):
+            step_e2e()
+        ctx.sync(); barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            d2h_bytes = step_e2e()
+        ctx.sync()
+        e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        barrier()
+        e2e = {"value": bases_all * steps / (e2e_ms * 1e-3) / 1e9, "unit": "Gbases/s",
+               "h2d_bytes_per_step": int(total + 8 * (reads_per_rank + 1)), "d2h_bytes_per_step": int(d2h_bytes),
+               "ms_per_step": e2e_ms / steps, "timing": "host wall clock around K steps, max over ranks"}
+        ctx.host_free_pinned(hb); ctx.host_free_pinned(ho)
+
+    # ------------------------------------------------------------------ CPU baseline (rank 0, N=1)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        n = max(64, reads_per_rank // 2)
+        v, cores, tot, sec, _ = cpu_reference_run(wl, n, 1, 0)
+        cpu = {"value": v, "unit": "Gbases/s", "cores": cores, "kind": "port",
+               "sample": "first %d reads (%d bases) of the workload, %.1f s" % (n, tot, sec)}
+
+    if rank == 0:
+        out = {"metric": "Gbases/sec reads->mdBG", "value": value, "unit": "Gbases/s", "n_gpus": world,
+               "steps": steps, "warmup": warmup, "ms_per_step": dev_ms / steps, "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": config,
+               "timing": "CUDA events on the launching stream around K steps, max over ranks",
+               "wall_ms_per_step": wall_ms / steps, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+               "roofline": roofline, "cpu_baseline": cpu,
+               "stage_ms_per_step": {k_: v_ / steps for k_, v_ in stage.items()},
+               "counts": {k_: int(v_) for k_, v_ in stats.items()}}
+        print(json.dumps(out))
+    ctx.device_free(d_bases); ctx.device_free(d_off)
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

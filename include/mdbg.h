@@ -156,6 +156,10 @@ typedef struct {
 } mdbg_timings;
 int mdbg_get_timings(mdbg_ctx* ctx, mdbg_timings* out);
 void* mdbg_stream(mdbg_ctx* ctx);              /* the cudaStream_t all kernels run on        */
+/* CUDA-event stopwatch on that stream (the launching stream): start records an event, stop
+ * records a second one, synchronises and returns the elapsed device time.                 */
+int mdbg_timer_start(mdbg_ctx* ctx);
+int mdbg_timer_stop(mdbg_ctx* ctx, float* ms);
 
 /* ---- synthetic HiFi-shape reads (bench workload) ----------------------------
  * Counter-based (splitmix64) so any rank/device/CPU reproduces the same bytes.  plan: fills

@@ -350,6 +350,25 @@ int mdbg_get_timings(mdbg_ctx* c, mdbg_timings* out) {
     return MDBG_OK;
 }
 
+int mdbg_timer_start(mdbg_ctx* c) {
+    if (!c) return MDBG_ERR_BAD_ARG;
+    MDBG_CK(c, cudaSetDevice(c->device));
+    MDBG_CK(c, cudaStreamSynchronize(c->st));
+    MDBG_CK(c, cudaEventRecord(c->ev[15], c->st));
+    return MDBG_OK;
+}
+int mdbg_timer_stop(mdbg_ctx* c, float* ms) {
+    if (!c || !ms) return MDBG_ERR_BAD_ARG;
+    MDBG_CK(c, cudaSetDevice(c->device));
+    cudaEvent_t e;
+    MDBG_CK(c, cudaEventCreate(&e));
+    MDBG_CK(c, cudaEventRecord(e, c->st));
+    MDBG_CK(c, cudaEventSynchronize(e));
+    MDBG_CK(c, cudaEventElapsedTime(ms, c->ev[15], e));
+    cudaEventDestroy(e);
+    return MDBG_OK;
+}
+
 // ---- memory helpers ---------------------------------------------------------------------------
 int mdbg_device_malloc(mdbg_ctx* c, uint64_t bytes, void** out) {
     if (!c || !out) return MDBG_ERR_BAD_ARG;

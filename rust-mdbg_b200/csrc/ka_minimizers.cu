@@ -51,16 +51,23 @@ constexpr int WIN = ROWS * 128;
 constexpr int QCAP = 1024;
 constexpr int WORDS = TILE / 32;  // 512
 
+constexpr uint32_t Q_DROP = 0xFFFFFFFFu;
+constexpr uint32_t Q_VERIFIED = 0x80000000u;
+constexpr uint64_t VALID_BY_CLASS = 0x4E00000047544341ull;  // "ACTG\0\0\0N": the byte a class must equal
+
 constexpr uint64_t ST_AGG = 1ull << 62;
 constexpr uint64_t ST_PREFIX = 2ull << 62;
 constexpr uint64_t ST_VAL = (1ull << 62) - 1;
 
 struct __align__(16) Smem {
     uint8_t raw[ROWS * RSTRIDE];
-    uint32_t queue[QCAP];
+    uint64_t hq[QCAP];        // exact hash of a verified queue entry
+    uint32_t queue[QCAP];     // candidates: window-relative position of the LAST run; after phase B:
+                              // tile-relative start position of a verified minimizer, or Q_DROP
     uint32_t bitmap[WORDS];
     uint32_t prefix[WORDS];
-    uint2 tab[16];
+    __align__(128) uint2 tab[16];
+    uint64_t hfw[8], hrc[8];  // ntHash seeds by base class (c>>1)&7: A0 C1 T2 G3 N7
     uint32_t warp_sum[NT / 32];
     uint32_t qn;
     uint32_t total;
@@ -72,6 +79,8 @@ struct Win {  // byte access through the staged window, falling back to global m
     const uint8_t* raw;
     const uint8_t* g;
     int64_t w0;
+    const uint64_t* hfw;
+    const uint64_t* hrc;
     __device__ __forceinline__ uint32_t byte(int64_t p) const {
         int64_t x = p - w0;
         if (x >= 0 && x < WIN) return raw[(x >> 7) * RSTRIDE + (x & 127)];
@@ -85,6 +94,8 @@ __device__ __forceinline__ bool collapsible(uint32_t c) {  // "ACTGactgNn", read
 }
 
 // Exact canonical hash of the l-mer whose first run starts at p0 (read ends at re).
+// fh is rolled left, rh right (one fixed rotate per run); rh gets its l-1 rotation at the end:
+//   XOR_j rol(H_j, l-1-j)  and  rol(XOR_j ror(RC_j, l-1-j), l-1) = XOR_j rol(RC_j, j).
 // 0: fewer than l runs remain; 1: ok; 2: ok but an illegal byte was hashed (inv = its position).
 template <bool HPC>
 __device__ int lmer_hash(const Win& W, int64_t p0, int64_t re, uint32_t l, uint64_t& h, int64_t& inv) {
@@ -94,17 +105,18 @@ __device__ int lmer_hash(const Win& W, int64_t p0, int64_t re, uint32_t l, uint6
     for (uint32_t j = 0; j < l; j++) {
         if (p >= re) return 0;
         uint32_t c = W.byte(p);
-        bool ok;
-        uint64_t hv = nt_fwd(c, ok);
-        uint64_t rv = nt_rc(c);
-        if (!ok && res == 1) { res = 2; inv = p; }
-        fh ^= rol64(hv, l - 1 - j);
-        rh ^= rol64(rv, j);
+        uint32_t cls = (c >> 1) & 7u;
+        bool valid = (uint32_t)((VALID_BY_CLASS >> (8 * cls)) & 0xFFu) == c;
+        if (!valid && res == 1) { res = 2; inv = p; }
+        uint64_t hv = valid ? W.hfw[cls] : 0, rv = valid ? W.hrc[cls] : 0;
+        fh = ((fh << 1) | (fh >> 63)) ^ hv;
+        rh = ((rh >> 1) | (rh << 63)) ^ rv;
         int64_t q = p + 1;
-        if (HPC && collapsible(c))
+        if (HPC && (valid || collapsible(c)))
             while (q < re && W.byte(q) == c) q++;
         p = q;
     }
+    rh = rol64(rh, l - 1);
     h = fh < rh ? fh : rh;
     return res;
 }
@@ -167,15 +179,19 @@ __global__ void ka_tile_lb_kernel(const uint64_t* __restrict__ read_off, uint64_
 }
 
 template <bool HPC>
-__global__ void __launch_bounds__(NT, 6) ka_minimizers_kernel(const KAArgs A) {
+__global__ void __launch_bounds__(NT, 5) ka_minimizers_kernel(const KAArgs A) {
     __shared__ Smem sm;
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const uint32_t l = A.l;
     const uint64_t bound = A.bound;
     if (tid < 16) sm.tab[tid] = make_uint2(A.fc.tab[tid][0], A.fc.tab[tid][1]);
+    if (tid < 8) {
+        sm.hfw[tid] = tid < 4 ? nt_fwd_code(tid) : 0;   // classes 4..7 (illegal bytes and N) hash as 0
+        sm.hrc[tid] = tid < 4 ? nt_rc_code(tid) : 0;
+    }
     const bool use_filter = A.fc.usable && !A.force_dense;
-    const uint32_t SH = A.fc.hist_shift, fth = A.fc.f_thresh, gm = A.fc.g_mask, gth = A.fc.g_thresh;
+    const uint32_t SH = A.fc.hist_shift, fth = A.fc.f_thresh, gz = A.fc.g_zero;
     const uint8_t* __restrict__ gb = A.bases;
     const int64_t B = (int64_t)A.n_bases;
 
@@ -217,13 +233,16 @@ __global__ void __launch_bounds__(NT, 6) ka_minimizers_kernel(const KAArgs A) {
             *reinterpret_cast<uint4*>(sm.raw + (q >> 3) * RSTRIDE + (q & 7) * 16) = v;
         }
         __syncthreads();
-        Win W{sm.raw, gb, w0};
+        Win W{sm.raw, gb, w0, sm.hfw, sm.hrc};
+        const uint32_t tab_s = (uint32_t)__cvta_generic_to_shared(sm.tab);
+        const uint32_t raw_s = (uint32_t)__cvta_generic_to_shared(sm.raw);
 
         const int64_t a = t0 + (int64_t)tid * SEG;
         const int64_t seg_end = (a + SEG < t1) ? a + SEG : t1;
 
-        // Exact evaluation of every run start of [pb, plim) (slow path).
-        auto exact_portion = [&](int64_t rs, int64_t re, int64_t pb, int64_t plim) {
+        // Exact evaluation of every run start of [pb, plim) (slow path).  QUEUE: also leave a
+        // verified queue entry so that the emit phase need not recompute the hash.
+        auto exact_portion_impl = [&](int64_t rs, int64_t re, int64_t pb, int64_t plim, bool to_queue) {
             uint32_t prev = (pb > rs) ? W.byte(pb - 1) : 0x100u;
             for (int64_t p = pb; p < plim; p++) {
                 uint32_t c = W.byte(p);
@@ -235,49 +254,149 @@ __global__ void __launch_bounds__(NT, 6) ka_minimizers_kernel(const KAArgs A) {
                 int res = lmer_hash<HPC>(W, p, re, l, h, inv);
                 if (res == 0) break;  // no later start of this read can complete either
                 if (res == 2) atomicMin(A.err_pos, (unsigned long long)inv);
-                if (h <= bound) atomicOr(&sm.bitmap[(p - t0) >> 5], 1u << ((p - t0) & 31));
+                if (h <= bound) {
+                    uint32_t rel = (uint32_t)(p - t0), bit = 1u << (rel & 31);
+                    uint32_t old = atomicOr(&sm.bitmap[rel >> 5], bit);
+                    if (to_queue && !(old & bit)) {
+                        uint32_t qi = atomicAdd(&sm.qn, 1u);
+                        if (qi < QCAP) { sm.queue[qi] = rel | Q_VERIFIED; sm.hq[qi] = h; }
+                    }
+                }
             }
+        };
+        auto exact_portion = [&](int64_t rs, int64_t re, int64_t pb, int64_t plim) {
+            exact_portion_impl(rs, re, pb, plim, false);
         };
 
         // Filtered scan of one portion; falls back to exact_portion if a non-ACGT byte shows up.
         auto fast_portion = [&](int64_t rs, int64_t re, int64_t pb, int64_t plim) {
             uint32_t F = A.fc.f_init, G = A.fc.g_init, hist = 0, bad = 0;
-#define MDBG_RUN_STEP(code, pos)                                                 \
-    {                                                                            \
-        hist = (hist << 2) | (code);                                             \
-        uint2 tt = sm.tab[((hist >> SH) & 0xCu) | (code)];                       \
-        F = (F << 1) ^ tt.x;                                                     \
-        G = (G >> 1) ^ tt.y;                                                     \
-        if (F <= fth || (G & gm) <= gth) {                                       \
-            uint32_t qi = atomicAdd(&sm.qn, 1u);                                 \
-            if (qi < QCAP) sm.queue[qi] = (uint32_t)((pos) - w0);                \
-        }                                                                        \
-    }
+            auto push = [&](int64_t pos) {
+                uint32_t qi = atomicAdd(&sm.qn, 1u);
+                if (qi < QCAP) sm.queue[qi] = (uint32_t)(pos - w0);
+            };
+            // one run (C++ form, used on ragged portions): roll the 2-bit history and the two filter
+            // words; true if the window ending here may be a minimizer
+            auto run_step = [&](uint32_t code) -> bool {
+                hist = (hist << 2) | code;
+                uint2 tt = sm.tab[((hist >> SH) & 0xCu) | code];
+                F = (F << 1) ^ tt.x;
+                G = (G >> 1) ^ tt.y;
+                return F <= fth || (G & gz) == 0;
+            };
+            // The same step for byte J of a word, hand-scheduled in PTX: every instruction is
+            // predicated on "byte J starts a run" (p) -- no branch per byte, no select chains.
+            //   x: word ^ (word shifted by one byte)  cw: 2-bit codes, one per byte
+            // TAIL adds the data-dependent halo conditions (runs left to consume, bytes left in
+            // the read) and only then looks at the per-byte "not ACGT" flags in bw.
+#define MDBG_STEP(J, BITN)                                                                                  \
+    asm("{\n\t.reg .pred p, q;\n\t.reg .b32 t, c, a, b, tx, ty;\n\t"                                        \
+        "and.b32 t, %4, %10;\n\tsetp.ne.u32 p, t, 0;\n\t"                                                   \
+        "prmt.b32 c, %5, 0, %11;\n\t"                                                                       \
+        "@p mad.lo.u32 %0, %0, 4, c;\n\t"                                                                   \
+        "shr.u32 t, %0, %6;\n\t"                                                                            \
+        "lop3.b32 t, t, 12, c, 0xEA;\n\t"                                                                   \
+        "mad.lo.u32 t, t, 8, %7;\n\t"                                                                       \
+        "ld.shared.v2.u32 {tx, ty}, [t];\n\t"                                                               \
+        "shl.b32 a, %1, 1;\n\t@p xor.b32 %1, a, tx;\n\t"                                                    \
+        "shr.u32 b, %2, 1;\n\t@p xor.b32 %2, b, ty;\n\t"                                                    \
+        "and.b32 a, %2, %9;\n\tsetp.eq.u32 q, a, 0;\n\t"                                                    \
+        "setp.le.or.u32 q, %1, %8, q;\n\tand.pred q, q, p;\n\t"                                             \
+        "@q or.b32 %3, %3, %12;\n\t}"                                                                       \
+        : "+r"(hist), "+r"(F), "+r"(G), "+r"(cand)                                                          \
+        : "r"(x), "r"(cw), "r"(SHr), "r"(tab_r), "r"(fthr), "r"(gzr), "n"(0xFFu << (8 * (J))),              \
+          "n"(0x4440 | (J)), "n"(1u << (BITN)))
+#define MDBG_TSTEP(J, BITN)                                                                                 \
+    asm("{\n\t.reg .pred p, q, e;\n\t.reg .b32 t, c, a, b, tx, ty;\n\t"                                     \
+        "setp.gt.u32 e, %4, 0;\n\tsetp.gt.and.u32 e, %15, %16, e;\n\t"                                      \
+        "and.b32 t, %6, %12;\n\tsetp.ne.and.u32 p, t, 0, e;\n\t"                                            \
+        "and.b32 t, %17, %12;\n\t@e or.b32 %5, %5, t;\n\t"                                                  \
+        "prmt.b32 c, %7, 0, %13;\n\t"                                                                       \
+        "@p mad.lo.u32 %0, %0, 4, c;\n\t"                                                                   \
+        "@p add.u32 %4, %4, -1;\n\t"                                                                        \
+        "shr.u32 t, %0, %8;\n\t"                                                                            \
+        "lop3.b32 t, t, 12, c, 0xEA;\n\t"                                                                   \
+        "mad.lo.u32 t, t, 8, %9;\n\t"                                                                       \
+        "ld.shared.v2.u32 {tx, ty}, [t];\n\t"                                                               \
+        "shl.b32 a, %1, 1;\n\t@p xor.b32 %1, a, tx;\n\t"                                                    \
+        "shr.u32 b, %2, 1;\n\t@p xor.b32 %2, b, ty;\n\t"                                                    \
+        "and.b32 a, %2, %11;\n\tsetp.eq.u32 q, a, 0;\n\t"                                                   \
+        "setp.le.or.u32 q, %1, %10, q;\n\tand.pred q, q, p;\n\t"                                            \
+        "@q or.b32 %3, %3, %14;\n\t}"                                                                       \
+        : "+r"(hist), "+r"(F), "+r"(G), "+r"(cand), "+r"(rem), "+r"(bad)                                    \
+        : "r"(x), "r"(cw), "r"(SHr), "r"(tab_r), "r"(fthr), "r"(gzr), "n"(0xFFu << (8 * (J))),              \
+          "n"(0x4440 | (J)), "n"(1u << (BITN)), "r"(left), "n"(BITN), "r"(bw))
             uint32_t prevb;
+            uint32_t rem = l - 1;
+            int64_t tail_from = plim;
             if (pb == a && plim == a + SEG) {
-                // full, 16-byte aligned segment: 8 x LDS.128, everything else in registers
-                const uint8_t* row = sm.raw + (tid + 1) * RSTRIDE;
-                uint32_t first = row[0];
-                uint32_t pw = ((pb > rs) ? W.byte(pb - 1) : (first ^ 0xFFu)) << 24;
-#pragma unroll 2
+                // full, 16-byte aligned segment: 8 x LDS.128, everything else in registers.
+                // The loop constants are pinned in ordinary registers (a volatile move cannot be
+                // re-materialised) so that nothing is re-derived per step.
+                uint32_t tab_r, SHr, fthr, gzr, row_r;
+                asm volatile("mov.b32 %0, %1;" : "=r"(tab_r) : "r"(tab_s));
+                asm volatile("mov.b32 %0, %1;" : "=r"(SHr) : "r"(SH));
+                asm volatile("mov.b32 %0, %1;" : "=r"(fthr) : "r"(fth));
+                asm volatile("mov.b32 %0, %1;" : "=r"(gzr) : "r"(gz));
+                asm volatile("mov.b32 %0, %1;" : "=r"(row_r) : "r"(raw_s + (tid + 1) * RSTRIDE));
+                uint32_t pw;
+                {
+                    uint32_t first = sm.raw[(tid + 1) * RSTRIDE];
+                    pw = ((pb > rs) ? (uint32_t)sm.raw[tid * RSTRIDE + 127] : (first ^ 0xFFu)) << 24;
+                }
+#pragma unroll 1
                 for (int c16 = 0; c16 < 8; c16++) {
-                    // the 8 chunks of thread t sit at chunk index (t+1)*9 + c16 of the padded rows
-                    uint4 v = *reinterpret_cast<const uint4*>(row + c16 * 16);
-                    uint32_t ws[4] = {v.x, v.y, v.z, v.w};
+                    uint32_t ws[4];
+                    asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(ws[0]), "=r"(ws[1]), "=r"(ws[2]), "=r"(ws[3])
+                        : "r"(row_r + c16 * 16));
+                    uint32_t cand = 0;
 #pragma unroll
                     for (int wi = 0; wi < 4; wi++) {
                         uint32_t w = ws[wi];
-                        uint32_t x = w ^ __funnelshift_l(pw, w, 8);
+                        uint32_t x = HPC ? (w ^ __funnelshift_l(pw, w, 8)) : 0xFFFFFFFFu;
                         uint32_t cw = (w >> 1) & 0x03030303u;
                         bad |= badword(w);
-#pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            bool nr = !HPC || ((x >> (8 * j)) & 0xFFu) != 0;
-                            uint32_t code = (cw >> (8 * j)) & 3u;
-                            if (nr) MDBG_RUN_STEP(code, a + c16 * 16 + wi * 4 + j)
-                        }
+                        if (wi == 0) { MDBG_STEP(0, 0); MDBG_STEP(1, 1); MDBG_STEP(2, 2); MDBG_STEP(3, 3); }
+                        if (wi == 1) { MDBG_STEP(0, 4); MDBG_STEP(1, 5); MDBG_STEP(2, 6); MDBG_STEP(3, 7); }
+                        if (wi == 2) { MDBG_STEP(0, 8); MDBG_STEP(1, 9); MDBG_STEP(2, 10); MDBG_STEP(3, 11); }
+                        if (wi == 3) { MDBG_STEP(0, 12); MDBG_STEP(1, 13); MDBG_STEP(2, 14); MDBG_STEP(3, 15); }
                         pw = w;
                     }
+                    while (cand) {
+                        int b = __ffs(cand) - 1;
+                        cand &= cand - 1;
+                        push(a + c16 * 16 + b);
+                    }
+                }
+                // data-dependent halo, same code chunk by chunk: the rows after this thread's row
+                // (up to 256 more bytes) are in shared memory for every thread of the tile
+#pragma unroll 1
+                for (int tc = 0; tc < 16 && rem > 0; tc++) {
+                    int64_t cpos = a + SEG + tc * 16;
+                    if (cpos >= re) break;
+                    uint32_t left = (re - cpos) > 16 ? 16u : (uint32_t)(re - cpos);
+                    uint32_t ws[4];
+                    asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(ws[0]), "=r"(ws[1]), "=r"(ws[2]), "=r"(ws[3])
+                        : "r"(row_r + (1 + (tc >> 3)) * RSTRIDE + (tc & 7) * 16));
+                    uint32_t cand = 0;
+#pragma unroll
+                    for (int wi = 0; wi < 4; wi++) {
+                        uint32_t w = ws[wi];
+                        uint32_t x = HPC ? (w ^ __funnelshift_l(pw, w, 8)) : 0xFFFFFFFFu;
+                        uint32_t cw = (w >> 1) & 0x03030303u;
+                        uint32_t bw = badword(w);
+                        if (wi == 0) { MDBG_TSTEP(0, 0); MDBG_TSTEP(1, 1); MDBG_TSTEP(2, 2); MDBG_TSTEP(3, 3); }
+                        if (wi == 1) { MDBG_TSTEP(0, 4); MDBG_TSTEP(1, 5); MDBG_TSTEP(2, 6); MDBG_TSTEP(3, 7); }
+                        if (wi == 2) { MDBG_TSTEP(0, 8); MDBG_TSTEP(1, 9); MDBG_TSTEP(2, 10); MDBG_TSTEP(3, 11); }
+                        if (wi == 3) { MDBG_TSTEP(0, 12); MDBG_TSTEP(1, 13); MDBG_TSTEP(2, 14); MDBG_TSTEP(3, 15); }
+                        pw = w;
+                    }
+                    while (cand) {
+                        int b = __ffs(cand) - 1;
+                        cand &= cand - 1;
+                        push(cpos + b);
+                    }
+                    tail_from = cpos + 16;
                 }
                 prevb = pw >> 24;
             } else {
@@ -285,20 +404,20 @@ __global__ void __launch_bounds__(NT, 6) ka_minimizers_kernel(const KAArgs A) {
                 for (int64_t p = pb; p < plim; p++) {
                     uint32_t c = W.byte(p);
                     bad |= !(c == 'A' || c == 'C' || c == 'G' || c == 'T');
-                    if (!HPC || c != prevb) MDBG_RUN_STEP((c >> 1) & 3u, p)
+                    if (!HPC || c != prevb) { if (run_step((c >> 1) & 3u)) push(p); }
                     prevb = c;
                 }
             }
-            // data-dependent halo: l-1 more runs complete the l-mers that start in the portion
-            uint32_t rem = l - 1;
-            for (int64_t p = plim; p < re && rem > 0; p++) {
+#undef MDBG_STEP
+#undef MDBG_TSTEP
+            // ragged portions, and halos longer than 256 bytes: byte-wise
+            for (int64_t p = tail_from; p < re && rem > 0; p++) {
                 uint32_t c = W.byte(p);
                 bad |= !(c == 'A' || c == 'C' || c == 'G' || c == 'T');
-                if (!HPC || c != prevb) { MDBG_RUN_STEP((c >> 1) & 3u, p) rem--; }
+                if (!HPC || c != prevb) { if (run_step((c >> 1) & 3u)) push(p); rem--; }
                 prevb = c;
             }
-#undef MDBG_RUN_STEP
-            if (bad) exact_portion(rs, re, pb, plim);
+            if (bad) exact_portion_impl(rs, re, pb, plim, true);
         };
 
         auto for_each_portion = [&](auto&& fn) {
@@ -316,18 +435,25 @@ __global__ void __launch_bounds__(NT, 6) ka_minimizers_kernel(const KAArgs A) {
         };
 
         // ---- phase A: scan --------------------------------------------------------------
+        bool queue_mode = use_filter;
         if (use_filter) for_each_portion(fast_portion);
         else for_each_portion(exact_portion);
         __syncthreads();
         if (use_filter) {
             const uint32_t qn = sm.qn;
             if (qn > QCAP) {  // low-complexity sequence flooded the queue: exact path for the tile
+                queue_mode = false;
+                for (int i = tid; i < WORDS; i += NT) sm.bitmap[i] = 0;
+                __syncthreads();
                 if (tid == 0) atomicAdd(A.dense_tiles, 1u);
                 for_each_portion(exact_portion);
             } else {
                 // ---- phase B: exact re-evaluation of the survivors -------------------------
                 for (uint32_t qi = tid; qi < qn; qi += NT) {
-                    int64_t pe = w0 + (int64_t)sm.queue[qi];
+                    uint32_t ent = sm.queue[qi];
+                    if (ent & Q_VERIFIED) { sm.queue[qi] = ent & ~Q_VERIFIED; continue; }
+                    sm.queue[qi] = Q_DROP;
+                    int64_t pe = w0 + (int64_t)ent;
                     // the read containing pe (pe may lie past this tile: widen the range)
                     uint64_t hi2 = rhi;
                     if (pe >= t1) hi2 = A.n_reads;
@@ -341,7 +467,11 @@ __global__ void __launch_bounds__(NT, 6) ka_minimizers_kernel(const KAArgs A) {
                     int res = lmer_hash<HPC>(W, p0, re, l, h, inv);
                     if (res == 0) continue;
                     if (res == 2) atomicMin(A.err_pos, (unsigned long long)inv);
-                    if (h <= bound) atomicOr(&sm.bitmap[(p0 - t0) >> 5], 1u << ((p0 - t0) & 31));
+                    if (h <= bound) {
+                        uint32_t rel = (uint32_t)(p0 - t0), bit = 1u << (rel & 31);
+                        uint32_t old = atomicOr(&sm.bitmap[rel >> 5], bit);
+                        if (!(old & bit)) { sm.queue[qi] = rel; sm.hq[qi] = h; }  // first finder emits it
+                    }
                 }
             }
         } else if (tid == 0) {
@@ -386,7 +516,7 @@ __global__ void __launch_bounds__(NT, 6) ka_minimizers_kernel(const KAArgs A) {
                     uint32_t pref = __ballot_sync(0xffffffffu, flag == 2);
                     int fp = pref ? __ffs(pref) - 1 : 32;
                     uint32_t need = fp >= 31 ? 0xffffffffu : ((2u << fp) - 1u);
-                    if (inval & need) continue;  // a predecessor has not published yet
+                    if (inval & need) { __nanosleep(200); continue; }  // a predecessor has not published yet
                     uint64_t v = (lane <= fp) ? (s & ST_VAL) : 0;
 #pragma unroll
                     for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
@@ -413,25 +543,42 @@ __global__ void __launch_bounds__(NT, 6) ka_minimizers_kernel(const KAArgs A) {
             else rank = sm.prefix[x >> 5] + __popc(sm.bitmap[x >> 5] & ((1u << (x & 31)) - 1u));
             A.out_read_off[A.read_base + r] = obase + rank;
         }
-#pragma unroll 1
-        for (int i = 0; i < 4; i++) {
-            uint32_t word = wv[i];
-            uint32_t rank = sm.prefix[tid * 4 + i];
-            while (word) {
-                int b = __ffs(word) - 1;
-                word &= word - 1;
-                int64_t p0 = t0 + (tid * 4 + i) * 32 + b;
+        if (queue_mode) {
+            // every verified queue entry knows its hash; its rank is a popcount prefix of the bitmap
+            const uint32_t qn = sm.qn;
+            for (uint32_t qi = tid; qi < qn; qi += NT) {
+                uint32_t rel = sm.queue[qi];
+                if (rel == Q_DROP) continue;
+                uint32_t rank = sm.prefix[rel >> 5] + __popc(sm.bitmap[rel >> 5] & ((1u << (rel & 31)) - 1u));
+                int64_t p0 = t0 + rel;
                 uint64_t r = find_read(A.read_off, rlo, rhi, p0);
-                int64_t rs = (int64_t)__ldg(A.read_off + r), re = (int64_t)__ldg(A.read_off + r + 1);
-                uint64_t h = 0;
-                int64_t inv;
-                lmer_hash<HPC>(W, p0, re, l, h, inv);
                 uint64_t o = obase + rank;
                 if (o < A.out_cap) {
-                    A.out_hash[o] = h;
-                    A.out_pos[o] = (uint32_t)(p0 - rs);
+                    A.out_hash[o] = sm.hq[qi];
+                    A.out_pos[o] = (uint32_t)(p0 - (int64_t)__ldg(A.read_off + r));
                 }
-                rank++;
+            }
+        } else {
+#pragma unroll 1
+            for (int i = 0; i < 4; i++) {
+                uint32_t word = wv[i];
+                uint32_t rank = sm.prefix[tid * 4 + i];
+                while (word) {
+                    int b = __ffs(word) - 1;
+                    word &= word - 1;
+                    int64_t p0 = t0 + (tid * 4 + i) * 32 + b;
+                    uint64_t r = find_read(A.read_off, rlo, rhi, p0);
+                    int64_t rs = (int64_t)__ldg(A.read_off + r), re = (int64_t)__ldg(A.read_off + r + 1);
+                    uint64_t h = 0;
+                    int64_t inv;
+                    lmer_hash<HPC>(W, p0, re, l, h, inv);
+                    uint64_t o = obase + rank;
+                    if (o < A.out_cap) {
+                        A.out_hash[o] = h;
+                        A.out_pos[o] = (uint32_t)(p0 - rs);
+                    }
+                    rank++;
+                }
             }
         }
     }

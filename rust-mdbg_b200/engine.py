@@ -209,6 +209,24 @@ class Context:
     def sync(self):
         self._ck(self.L.mdbg_sync(self.h))
 
+    def timer_start(self):
+        self._ck(self.L.mdbg_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = ctypes.c_float(0)
+        self._ck(self.L.mdbg_timer_stop(self.h, ctypes.byref(ms)))
+        return ms.value
+
+    def host_alloc_pinned(self, nbytes):
+        p = ffi.vp()
+        rc = self.L.mdbg_host_alloc_pinned(nbytes, ctypes.byref(p))
+        if rc != 0:
+            raise MdbgError(rc, "cudaMallocHost failed")
+        return p.value
+
+    def host_free_pinned(self, p):
+        self.L.mdbg_host_free_pinned(p)
+
     def flush_l2(self):
         self._ck(self.L.mdbg_flush_l2(self.h))
 

@@ -81,6 +81,8 @@ SYMBOLS = {
     "mdbg_get_minimizers": (ctypes.c_int, [vp, vp, vp, vp, u64, ctypes.POINTER(u64)]),
     "mdbg_get_timings": (ctypes.c_int, [vp, ctypes.POINTER(CTimings)]),
     "mdbg_stream": (vp, [vp]),
+    "mdbg_timer_start": (ctypes.c_int, [vp]),
+    "mdbg_timer_stop": (ctypes.c_int, [vp, ctypes.POINTER(ctypes.c_float)]),
     "mdbg_synth_num_reads": (u64, [ctypes.POINTER(CSynth), ctypes.c_double]),
     "mdbg_synth_plan": (u64, [ctypes.POINTER(CSynth), u64, u64, vp, vp, vp]),
     "mdbg_synth_fill_device": (ctypes.c_int, [vp, ctypes.POINTER(CSynth), u64, u64, vp, vp, vp]),
