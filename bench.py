@@ -226,7 +226,7 @@ def main():
     for _ in range(steps):
         stats = step_device()
         tm = ctx.timings()
-        ka_ms += tm["ms_ka"]
+        ka_ms += tm["ms_ka_kernel"]
         launches += tm["launches_push"] + tm["launches_finish"]
         for s_ in stage:
             stage[s_] += tm["ms_" + s_]

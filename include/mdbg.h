@@ -153,6 +153,7 @@ typedef struct {
     uint64_t ka_launches; float ka_ms_sum;     /* accumulated over pushes since reset        */
     uint32_t table_attempts;                   /* fingerprint seeds tried by the last finish */
     uint32_t ka_dense_tiles;                   /* tiles that took the exact (dense) path     */
+    float ms_ka_kernel;                        /* ka_minimizers_kernel alone (last push)     */
 } mdbg_timings;
 int mdbg_get_timings(mdbg_ctx* ctx, mdbg_timings* out);
 void* mdbg_stream(mdbg_ctx* ctx);              /* the cudaStream_t all kernels run on        */

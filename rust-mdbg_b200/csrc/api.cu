@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <cub/cub.cuh>
 #include <string>
 
 #include "ctx.h"
@@ -89,7 +90,7 @@ int mdbg_ctx_create(const mdbg_params* p, mdbg_ctx** out) {
     if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, c->device);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_sc, sizeof(Scalars));
     if (e == cudaSuccess) e = cudaMallocHost(&c->h_sc, sizeof(Scalars));
-    for (int i = 0; i < 16 && e == cudaSuccess; i++) e = cudaEventCreate(&c->ev[i]);
+    for (int i = 0; i < 24 && e == cudaSuccess; i++) e = cudaEventCreate(&c->ev[i]);
     if (e != cudaSuccess) {
         g_create_err = std::string("CUDA init failed: ") + cudaGetErrorString(e);
         delete c;
@@ -117,7 +118,7 @@ void mdbg_ctx_destroy(mdbg_ctx* c) {
     if (c->l2_flush) cudaFree(c->l2_flush);
     if (c->d_sc) cudaFree(c->d_sc);
     if (c->h_sc) cudaFreeHost(c->h_sc);
-    for (int i = 0; i < 16; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (int i = 0; i < 24; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     c->pool.trim();
     if (c->st) cudaStreamDestroy(c->st);
     delete c;
@@ -188,11 +189,21 @@ static int run_ka(mdbg_ctx* c, const uint8_t* d_bases, const uint64_t* d_read_of
     } else if ((rc = ensure_arena(c, c->M + est, c->R + R))) return rc;
 
     uint64_t n_tiles = std::max<uint64_t>(1, (B + KA_TILE - 1) / KA_TILE);
-    Tmp<uint64_t> tile_state, tile_lb;
-    MDBG_CK(c, tile_state.get(c->pool, n_tiles));
+    Tmp<uint64_t> tile_cnt, tile_soff, tile_excl, tile_lb, stage_hash;
+    Tmp<uint32_t> stage_pos;
+    Tmp<uint8_t> scan_tmp;
+    MDBG_CK(c, tile_cnt.get(c->pool, n_tiles));
+    MDBG_CK(c, tile_soff.get(c->pool, n_tiles));
+    MDBG_CK(c, tile_excl.get(c->pool, n_tiles));
     MDBG_CK(c, tile_lb.get(c->pool, n_tiles + 1));
+    size_t scan_bytes = 0;
+    MDBG_CK(c, cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, tile_cnt.p, tile_excl.p, n_tiles, c->st));
+    MDBG_CK(c, scan_tmp.get(c->pool, scan_bytes + 256));
 
     for (int attempt = 0; attempt < 2; attempt++) {
+        const uint64_t stage_cap = c->m_cap_items - c->M;
+        MDBG_CK(c, stage_hash.get(c->pool, stage_cap));
+        MDBG_CK(c, stage_pos.get(c->pool, stage_cap));
         Scalars init{};
         init.err_pos = ~0ull;
         *c->h_sc = init;
@@ -204,15 +215,22 @@ static int run_ka(mdbg_ctx* c, const uint8_t* d_bases, const uint64_t* d_read_of
         A.out_base = c->M; A.out_cap = c->m_cap_items; A.read_base = c->R;
         A.total_out = &c->d_sc->total_out; A.err_pos = &c->d_sc->err_pos;
         A.dense_tiles = &c->d_sc->dense_tiles; A.tile_counter = &c->d_sc->tile_counter;
-        A.tile_state = tile_state; A.tile_lb = tile_lb; A.n_tiles = n_tiles;
+        A.stage_hash = stage_hash; A.stage_pos = stage_pos; A.stage_cap = stage_cap;
+        A.stage_counter = &c->d_sc->stage_counter; A.tile_cnt = tile_cnt; A.tile_soff = tile_soff;
+        A.tile_lb = tile_lb; A.n_tiles = n_tiles;
         MDBG_CK(c, cudaEventRecord(c->ev[0], c->st));
         MDBG_CK(c, ka_launch(A, c->p.hpc, c->ka_grid, c->st, &c->tm.launches_push));
+        MDBG_CK(c, cudaEventRecord(c->ev[16], c->st));
+        MDBG_CK(c, cub::DeviceScan::ExclusiveSum(scan_tmp.p, scan_bytes, tile_cnt.p, tile_excl.p, n_tiles, c->st));
+        c->tm.launches_push += 2;
+        MDBG_CK(c, ka_finalize(A, tile_excl, c->st, &c->tm.launches_push));
         MDBG_CK(c, cudaEventRecord(c->ev[1], c->st));
         MDBG_CK(c, cudaMemcpyAsync(c->h_sc, c->d_sc, sizeof(Scalars), cudaMemcpyDeviceToHost, c->st));
         MDBG_CK(c, cudaStreamSynchronize(c->st));
         float ms = 0;
         cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
         c->tm.ms_ka = ms;
+        cudaEventElapsedTime(&c->tm.ms_ka_kernel, c->ev[0], c->ev[16]);
         c->tm.ka_ms_sum += ms;
         c->tm.ka_launches += 1;
         c->tm.ka_dense_tiles = c->h_sc->dense_tiles;

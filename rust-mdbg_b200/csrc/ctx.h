@@ -60,6 +60,7 @@ struct Scalars {  // device mailbox mirrored into pinned host memory
     unsigned long long err_pos;
     unsigned int dense_tiles;
     unsigned int tile_counter;
+    unsigned long long stage_counter;
     unsigned long long v[12];   // stage-specific counters (see api.cu)
 };
 
@@ -82,7 +83,7 @@ struct mdbg_ctx {
     mdbg::Scalars* d_sc = nullptr;
     mdbg::Scalars* h_sc = nullptr;   // pinned
     void* l2_flush = nullptr; size_t l2_flush_bytes = 0;
-    cudaEvent_t ev[16]{};
+    cudaEvent_t ev[24]{};
     mdbg_timings tm{};
     // NCCL (multi-GPU)
     void* comm = nullptr; int rank = 0, world = 1;

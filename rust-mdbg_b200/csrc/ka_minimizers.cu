@@ -20,9 +20,10 @@
 //     its end until l-1 more runs are consumed (data-dependent halo, no fixed bound);
 //   * survivors go to a shared queue and are re-evaluated exactly (64-bit, N-aware, walking
 //     the runs backwards/forwards) by the whole CTA afterwards; hits set a bit per tile byte.
-// A block-wide popcount scan of that bitmap plus a decoupled look-back across tiles (single
-// pass, tiles are claimed in order) gives every minimizer its final position in the global,
-// (read, position)-ordered output, and the per-read offsets fall out of the same prefix.
+// A block-wide popcount scan of that bitmap orders the tile's minimizers; the tile reserves a
+// slice of a staging array with one atomicAdd (tiles never wait for each other) and a small
+// finalize kernel scans the per-tile counts and moves every slice to its final position in the
+// global, (read, position)-ordered output; the per-read offsets fall out of the same prefix.
 // Anything the filter cannot represent (N or illegal bytes in the segment, l > 15, large
 // densities, queue overflow on low-complexity sequence) takes the exact per-position path in
 // the same kernel -- never the CPU.
@@ -54,10 +55,6 @@ constexpr int WORDS = TILE / 32;  // 512
 constexpr uint32_t Q_DROP = 0xFFFFFFFFu;
 constexpr uint32_t Q_VERIFIED = 0x80000000u;
 constexpr uint64_t VALID_BY_CLASS = 0x4E00000047544341ull;  // "ACTG\0\0\0N": the byte a class must equal
-
-constexpr uint64_t ST_AGG = 1ull << 62;
-constexpr uint64_t ST_PREFIX = 2ull << 62;
-constexpr uint64_t ST_VAL = (1ull << 62) - 1;
 
 struct __align__(16) Smem {
     uint8_t raw[ROWS * RSTRIDE];
@@ -137,18 +134,48 @@ __device__ bool walk_back(const Win& W, int64_t p_end, int64_t rs, uint32_t l, i
     return true;
 }
 
+// Fast exact evaluation of a filter survivor, entirely from the staged window: walk the runs
+// BACKWARDS from the last run (at window-relative byte `rel_end`) and fold both strands on the way:
+//   A <- ror(A,1) ^ H[c]   gives  fh = rol(A, l-1);      B <- rol(B,1) ^ RC[c]  gives  rh = B.
+// Returns false when the window is not plain ACGT inside the staged bytes (N, illegal byte, read
+// start or window edge within reach, homopolymer longer than the guard): the caller then takes the
+// general path.
+template <bool HPC>
+__device__ __forceinline__ bool verify_fast(const uint8_t* raw, const uint64_t* hfw, const uint64_t* hrc,
+                                            int rel_end, int64_t rel_rs, uint32_t l, int& rel_p0, uint64_t& h) {
+    constexpr int GUARD = 96;
+    if (rel_end < GUARD || (int64_t)rel_end - rel_rs < GUARD || rel_end >= WIN) return false;
+    uint64_t A = 0, B = 0;
+    int r = rel_end;
+    uint32_t c = raw[r + (r >> 7) * 16];
+    for (uint32_t need = l;;) {
+        uint32_t cls = (c >> 1) & 7u;
+        if (cls > 3u || (uint32_t)((VALID_BY_CLASS >> (8 * cls)) & 0xFFu) != c) return false;
+        A = ((A >> 1) | (A << 63)) ^ hfw[cls];
+        B = ((B << 1) | (B >> 63)) ^ hrc[cls];
+        if (--need == 0) break;
+        r--;
+        c = raw[r + (r >> 7) * 16];
+        if (HPC) {
+            for (;;) {
+                int q = r - 1;
+                if (raw[q + (q >> 7) * 16] != c) break;
+                r = q;
+            }
+        }
+        if (rel_end - r > GUARD - 2) return false;
+    }
+    rel_p0 = r;
+    uint64_t fh = rol64(A, l - 1);
+    h = fh < B ? fh : B;
+    return true;
+}
+
 __device__ __forceinline__ uint32_t badword(uint32_t w) {  // nonzero iff some byte is not A/C/G/T
     uint32_t t = (w >> 2) & ~(w >> 1);
     uint32_t d = w >> 4;
     uint32_t b2 = (d & (~t | w)) | (~d & (~w | t));
     return ((w & 0xE8E8E8E8u) ^ 0x40404040u) | (b2 & 0x01010101u);
-}
-
-__device__ __forceinline__ uint64_t ld_state(const uint64_t* p) {
-    return *reinterpret_cast<const volatile uint64_t*>(p);
-}
-__device__ __forceinline__ void st_state(uint64_t* p, uint64_t v) {
-    *reinterpret_cast<volatile uint64_t*>(p) = v;
 }
 
 // last r in [lo, hi) with read_off[r] <= p   (read_off[lo] <= p guaranteed)
@@ -327,25 +354,67 @@ __global__ void __launch_bounds__(NT, 5) ka_minimizers_kernel(const KAArgs A) {
         : "r"(x), "r"(cw), "r"(SHr), "r"(tab_r), "r"(fthr), "r"(gzr), "n"(0xFFu << (8 * (J))),              \
           "n"(0x4440 | (J)), "n"(1u << (BITN)), "r"(left), "n"(BITN), "r"(bw))
             uint32_t prevb;
-            uint32_t rem = l - 1;
+            // A read that ends inside the NEXT thread's segment is walked to its end by this thread
+            // (the next thread skips that head portion, see for_each_portion): the whole warp is
+            // in its halo loop at that time, instead of one lane crawling through a ragged portion.
+            const bool extend = (plim == a + SEG) && (re < plim + SEG) && (tid + 1 < NT);
+            uint32_t rem = extend ? 0x7FFFFFFFu : l - 1;
             int64_t tail_from = plim;
-            if (pb == a && plim == a + SEG) {
-                // full, 16-byte aligned segment: 8 x LDS.128, everything else in registers.
-                // The loop constants are pinned in ordinary registers (a volatile move cannot be
-                // re-materialised) so that nothing is re-derived per step.
+            // chunked path: the portion ends with the segment and starts either with the segment or
+            // with a read that begins inside it
+            if (plim == a + SEG && (pb == a || pb == rs)) {
+                // 8 x LDS.128, everything else in registers.  The loop constants are pinned in
+                // ordinary registers (a volatile move cannot be re-materialised) so that nothing is
+                // re-derived per step.
                 uint32_t tab_r, SHr, fthr, gzr, row_r;
                 asm volatile("mov.b32 %0, %1;" : "=r"(tab_r) : "r"(tab_s));
                 asm volatile("mov.b32 %0, %1;" : "=r"(SHr) : "r"(SH));
                 asm volatile("mov.b32 %0, %1;" : "=r"(fthr) : "r"(fth));
                 asm volatile("mov.b32 %0, %1;" : "=r"(gzr) : "r"(gz));
                 asm volatile("mov.b32 %0, %1;" : "=r"(row_r) : "r"(raw_s + (tid + 1) * RSTRIDE));
-                uint32_t pw;
-                {
+                uint32_t pw = 0;
+                int c16 = 0;
+                if (pb == a) {
                     uint32_t first = sm.raw[(tid + 1) * RSTRIDE];
                     pw = ((pb > rs) ? (uint32_t)sm.raw[tid * RSTRIDE + 127] : (first ^ 0xFFu)) << 24;
+                } else {
+                    // the read starts at byte `off` of chunk c16: earlier bytes belong to the previous
+                    // read (no runs, not inspected), byte `off` is a run start whatever precedes it
+                    c16 = (int)(pb - a) >> 4;
+                    const int off = (int)(pb - a) & 15;
+                    uint32_t ws[4];
+                    asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(ws[0]), "=r"(ws[1]), "=r"(ws[2]), "=r"(ws[3])
+                        : "r"(row_r + c16 * 16));
+                    uint32_t cand = 0;
+#pragma unroll
+                    for (int wi = 0; wi < 4; wi++) {
+                        uint32_t w = ws[wi];
+                        uint32_t x = HPC ? (w ^ __funnelshift_l(pw, w, 8)) : 0xFFFFFFFFu;
+                        uint32_t cw = (w >> 1) & 0x03030303u;
+                        uint32_t bw = badword(w);
+                        const int wlo = off - 4 * wi;
+                        if (wlo >= 4) { x = 0; bw = 0; }
+                        else if (wlo >= 0) {
+                            uint32_t mk = 0xFFFFFFFFu << (8 * wlo);
+                            x = (x & mk) | (0xFFu << (8 * wlo));
+                            bw &= mk;
+                        }
+                        bad |= bw;
+                        if (wi == 0) { MDBG_STEP(0, 0); MDBG_STEP(1, 1); MDBG_STEP(2, 2); MDBG_STEP(3, 3); }
+                        if (wi == 1) { MDBG_STEP(0, 4); MDBG_STEP(1, 5); MDBG_STEP(2, 6); MDBG_STEP(3, 7); }
+                        if (wi == 2) { MDBG_STEP(0, 8); MDBG_STEP(1, 9); MDBG_STEP(2, 10); MDBG_STEP(3, 11); }
+                        if (wi == 3) { MDBG_STEP(0, 12); MDBG_STEP(1, 13); MDBG_STEP(2, 14); MDBG_STEP(3, 15); }
+                        pw = w;
+                    }
+                    while (cand) {
+                        int b = __ffs(cand) - 1;
+                        cand &= cand - 1;
+                        push(a + c16 * 16 + b);
+                    }
+                    c16++;
                 }
 #pragma unroll 1
-                for (int c16 = 0; c16 < 8; c16++) {
+                for (; c16 < 8; c16++) {
                     uint32_t ws[4];
                     asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(ws[0]), "=r"(ws[1]), "=r"(ws[2]), "=r"(ws[3])
                         : "r"(row_r + c16 * 16));
@@ -417,10 +486,10 @@ __global__ void __launch_bounds__(NT, 5) ka_minimizers_kernel(const KAArgs A) {
                 if (!HPC || c != prevb) { if (run_step((c >> 1) & 3u)) push(p); rem--; }
                 prevb = c;
             }
-            if (bad) exact_portion_impl(rs, re, pb, plim, true);
+            if (bad) exact_portion_impl(rs, re, pb, extend ? re : plim, true);
         };
 
-        auto for_each_portion = [&](auto&& fn) {
+        auto for_each_portion = [&](auto&& fn, bool delegate) {
             if (a >= t1) return;
             uint64_t r = find_read(A.read_off, rlo, rhi, a);
             int64_t p = a;
@@ -428,7 +497,9 @@ __global__ void __launch_bounds__(NT, 5) ka_minimizers_kernel(const KAArgs A) {
                 int64_t rs = (int64_t)__ldg(A.read_off + r), re = (int64_t)__ldg(A.read_off + r + 1);
                 if (re <= p) { r++; continue; }
                 int64_t plim = seg_end < re ? seg_end : re;
-                fn(rs, re, p, plim);
+                // the tail of a read that began before this segment and ends inside it was already
+                // walked by the previous thread of the tile (`extend` in fast_portion)
+                if (!(delegate && p == a && tid > 0 && rs < a && re < a + SEG)) fn(rs, re, p, plim);
                 p = plim;
                 if (p == re) r++;
             }
@@ -436,8 +507,8 @@ __global__ void __launch_bounds__(NT, 5) ka_minimizers_kernel(const KAArgs A) {
 
         // ---- phase A: scan --------------------------------------------------------------
         bool queue_mode = use_filter;
-        if (use_filter) for_each_portion(fast_portion);
-        else for_each_portion(exact_portion);
+        if (use_filter) for_each_portion(fast_portion, true);
+        else for_each_portion(exact_portion, false);
         __syncthreads();
         if (use_filter) {
             const uint32_t qn = sm.qn;
@@ -446,7 +517,7 @@ __global__ void __launch_bounds__(NT, 5) ka_minimizers_kernel(const KAArgs A) {
                 for (int i = tid; i < WORDS; i += NT) sm.bitmap[i] = 0;
                 __syncthreads();
                 if (tid == 0) atomicAdd(A.dense_tiles, 1u);
-                for_each_portion(exact_portion);
+                for_each_portion(exact_portion, false);
             } else {
                 // ---- phase B: exact re-evaluation of the survivors -------------------------
                 for (uint32_t qi = tid; qi < qn; qi += NT) {
@@ -458,15 +529,22 @@ __global__ void __launch_bounds__(NT, 5) ka_minimizers_kernel(const KAArgs A) {
                     uint64_t hi2 = rhi;
                     if (pe >= t1) hi2 = A.n_reads;
                     uint64_t r = find_read(A.read_off, rlo, hi2, pe);
-                    int64_t rs = (int64_t)__ldg(A.read_off + r), re = (int64_t)__ldg(A.read_off + r + 1);
+                    int64_t rs = (int64_t)__ldg(A.read_off + r);
                     int64_t p0;
-                    if (!walk_back<HPC>(W, pe, rs, l, p0)) continue;
-                    if (p0 < t0 || p0 >= t1) continue;  // owned by another tile
                     uint64_t h;
-                    int64_t inv = 0;
-                    int res = lmer_hash<HPC>(W, p0, re, l, h, inv);
-                    if (res == 0) continue;
-                    if (res == 2) atomicMin(A.err_pos, (unsigned long long)inv);
+                    int rel_p0;
+                    if (verify_fast<HPC>(sm.raw, sm.hfw, sm.hrc, (int)ent, rs - w0, l, rel_p0, h)) {
+                        p0 = w0 + rel_p0;
+                        if (p0 < t0 || p0 >= t1) continue;  // owned by another tile
+                    } else {
+                        int64_t re = (int64_t)__ldg(A.read_off + r + 1);
+                        if (!walk_back<HPC>(W, pe, rs, l, p0)) continue;
+                        if (p0 < t0 || p0 >= t1) continue;
+                        int64_t inv = 0;
+                        int res = lmer_hash<HPC>(W, p0, re, l, h, inv);
+                        if (res == 0) continue;
+                        if (res == 2) atomicMin(A.err_pos, (unsigned long long)inv);
+                    }
                     if (h <= bound) {
                         uint32_t rel = (uint32_t)(p0 - t0), bit = 1u << (rel & 31);
                         uint32_t old = atomicOr(&sm.bitmap[rel >> 5], bit);
@@ -502,38 +580,17 @@ __global__ void __launch_bounds__(NT, 5) ka_minimizers_kernel(const KAArgs A) {
 #pragma unroll
         for (int i = 0; i < 4; i++) { sm.prefix[tid * 4 + i] = ex; ex += __popc(wv[i]); }
 
-        // ---- decoupled look-back across tiles (warp 0) ------------------------------------
-        if (warp == 0) {
-            if (lane == 0) st_state(A.tile_state + tile, (tile == 0 ? ST_PREFIX : ST_AGG) | total);
-            uint64_t excl = 0;
-            if (tile > 0) {
-                int64_t look = (int64_t)tile - 1;
-                for (;;) {
-                    int64_t idx = look - lane;
-                    uint64_t s = idx >= 0 ? ld_state(A.tile_state + idx) : ST_PREFIX;
-                    uint32_t flag = (uint32_t)(s >> 62);
-                    uint32_t inval = __ballot_sync(0xffffffffu, flag == 0);
-                    uint32_t pref = __ballot_sync(0xffffffffu, flag == 2);
-                    int fp = pref ? __ffs(pref) - 1 : 32;
-                    uint32_t need = fp >= 31 ? 0xffffffffu : ((2u << fp) - 1u);
-                    if (inval & need) { __nanosleep(200); continue; }  // a predecessor has not published yet
-                    uint64_t v = (lane <= fp) ? (s & ST_VAL) : 0;
-#pragma unroll
-                    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-                    excl += v;
-                    if (fp < 32) break;
-                    look -= 32;
-                }
-                if (lane == 0) st_state(A.tile_state + tile, ST_PREFIX | (excl + total));
-            }
-            if (lane == 0) {
-                sm.base = excl;
-                sm.total = total;
-                if (tile + 1 == A.n_tiles) *A.total_out = A.out_base + excl + total;
-            }
+        // ---- reserve this tile's slice of the staging arrays (no ordering between tiles here: the
+        //      finalize kernel scans the per-tile counts and moves the slices to their final place)
+        if (tid == 0) {
+            unsigned long long sb = atomicAdd(A.stage_counter, (unsigned long long)total);
+            sm.base = sb;
+            sm.total = total;
+            A.tile_cnt[tile] = total;
+            A.tile_soff[tile] = sb;
         }
         __syncthreads();
-        const uint64_t obase = A.out_base + sm.base;
+        const uint64_t obase = sm.base;
 
         // ---- emit: per-read offsets, then (hash, pos) at the final positions ---------------
         for (uint64_t r = lb + tid; r < lbn; r += NT) {
@@ -541,7 +598,7 @@ __global__ void __launch_bounds__(NT, 5) ka_minimizers_kernel(const KAArgs A) {
             uint32_t rank;
             if (x >= TILE) rank = sm.total;
             else rank = sm.prefix[x >> 5] + __popc(sm.bitmap[x >> 5] & ((1u << (x & 31)) - 1u));
-            A.out_read_off[A.read_base + r] = obase + rank;
+            A.out_read_off[A.read_base + r] = (tile << 32) | rank;   // fixed up by ka_finalize_kernel
         }
         if (queue_mode) {
             // every verified queue entry knows its hash; its rank is a popcount prefix of the bitmap
@@ -553,9 +610,9 @@ __global__ void __launch_bounds__(NT, 5) ka_minimizers_kernel(const KAArgs A) {
                 int64_t p0 = t0 + rel;
                 uint64_t r = find_read(A.read_off, rlo, rhi, p0);
                 uint64_t o = obase + rank;
-                if (o < A.out_cap) {
-                    A.out_hash[o] = sm.hq[qi];
-                    A.out_pos[o] = (uint32_t)(p0 - (int64_t)__ldg(A.read_off + r));
+                if (o < A.stage_cap) {
+                    A.stage_hash[o] = sm.hq[qi];
+                    A.stage_pos[o] = (uint32_t)(p0 - (int64_t)__ldg(A.read_off + r));
                 }
             }
         } else {
@@ -573,9 +630,9 @@ __global__ void __launch_bounds__(NT, 5) ka_minimizers_kernel(const KAArgs A) {
                     int64_t inv;
                     lmer_hash<HPC>(W, p0, re, l, h, inv);
                     uint64_t o = obase + rank;
-                    if (o < A.out_cap) {
-                        A.out_hash[o] = h;
-                        A.out_pos[o] = (uint32_t)(p0 - rs);
+                    if (o < A.stage_cap) {
+                        A.stage_hash[o] = h;
+                        A.stage_pos[o] = (uint32_t)(p0 - rs);
                     }
                     rank++;
                 }
@@ -584,18 +641,47 @@ __global__ void __launch_bounds__(NT, 5) ka_minimizers_kernel(const KAArgs A) {
     }
 }
 
+// One warp per tile: move the tile's staged slice to its final, globally ordered position; then fix
+// up the per-read offsets (tile-relative rank -> global index).
+__global__ void ka_finalize_kernel(const KAArgs A, const uint64_t* __restrict__ tile_excl) {
+    const uint64_t gtid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    const uint64_t warp = gtid >> 5, lane = gtid & 31;
+    if (warp < A.n_tiles) {
+        const uint64_t cnt = A.tile_cnt[warp], src = A.tile_soff[warp], dst = A.out_base + tile_excl[warp];
+        for (uint64_t i = lane; i < cnt; i += 32) {
+            if (src + i < A.stage_cap && dst + i < A.out_cap) {
+                A.out_hash[dst + i] = A.stage_hash[src + i];
+                A.out_pos[dst + i] = A.stage_pos[src + i];
+            }
+        }
+        if (warp + 1 == A.n_tiles && lane == 0) *A.total_out = A.out_base + tile_excl[warp] + cnt;
+    }
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t r = gtid; r <= A.n_reads; r += stride) {
+        uint64_t v = A.out_read_off[A.read_base + r];
+        A.out_read_off[A.read_base + r] = A.out_base + tile_excl[v >> 32] + (v & 0xFFFFFFFFull);
+    }
+}
+
 // ---- host launchers ------------------------------------------------------------------------
 cudaError_t ka_launch(const KAArgs& A, int hpc, int grid, cudaStream_t st, uint64_t* launches) {
     uint64_t nt = A.n_tiles;
-    cudaError_t e = cudaMemsetAsync(A.tile_state, 0, sizeof(uint64_t) * nt, st);
+    cudaError_t e = cudaMemsetAsync(A.tile_counter, 0, sizeof(uint32_t), st);
     if (e != cudaSuccess) return e;
-    e = cudaMemsetAsync(A.tile_counter, 0, sizeof(uint32_t), st);
+    e = cudaMemsetAsync(A.stage_counter, 0, sizeof(unsigned long long), st);
     if (e != cudaSuccess) return e;
     unsigned nb = (unsigned)((nt + 1 + 255) / 256);
     ka_tile_lb_kernel<<<nb, 256, 0, st>>>(A.read_off, A.n_reads, nt, A.tile_lb);
     if (hpc) ka_minimizers_kernel<true><<<grid, NT, 0, st>>>(A);
     else ka_minimizers_kernel<false><<<grid, NT, 0, st>>>(A);
     if (launches) *launches += 2;
+    return cudaGetLastError();
+}
+
+cudaError_t ka_finalize(const KAArgs& A, const uint64_t* tile_excl, cudaStream_t st, uint64_t* launches) {
+    uint64_t threads = A.n_tiles * 32;
+    ka_finalize_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(A, tile_excl);
+    if (launches) *launches += 1;
     return cudaGetLastError();
 }
 

@@ -28,13 +28,20 @@ struct KAArgs {
     unsigned long long* total_out;   // out_base + minimizers of this batch
     unsigned long long* err_pos;     // min byte offset of an illegal base that was hashed
     unsigned int* dense_tiles;
+    // staging (tile order is restored by ka_finalize_kernel)
+    uint64_t* stage_hash;
+    uint32_t* stage_pos;
+    uint64_t stage_cap;
+    unsigned long long* stage_counter;
+    uint64_t* tile_cnt;          // [n_tiles] minimizers found in the tile
+    uint64_t* tile_soff;         // [n_tiles] offset of the tile's slice in the staging arrays
     // scratch
-    uint64_t* tile_state;        // [n_tiles]
     uint64_t* tile_lb;           // [n_tiles + 1]
     unsigned int* tile_counter;
     uint64_t n_tiles;
 };
 cudaError_t ka_launch(const KAArgs& A, int hpc, int grid, cudaStream_t st, uint64_t* launches);
+cudaError_t ka_finalize(const KAArgs& A, const uint64_t* tile_excl, cudaStream_t st, uint64_t* launches);
 int ka_max_blocks_per_sm(int hpc);
 
 }  // namespace mdbg

@@ -46,7 +46,8 @@ class CTimings(ctypes.Structure):
     _fields_ = [(n, ctypes.c_float) for n in ("ms_h2d", "ms_ka", "ms_kb", "ms_kc", "ms_kd", "ms_ke",
                                               "ms_d2h", "ms_total_push", "ms_total_finish")] + \
                [("launches_push", u64), ("launches_finish", u64), ("ka_launches", u64),
-                ("ka_ms_sum", ctypes.c_float), ("table_attempts", u32), ("ka_dense_tiles", u32)]
+                ("ka_ms_sum", ctypes.c_float), ("table_attempts", u32), ("ka_dense_tiles", u32),
+                ("ms_ka_kernel", ctypes.c_float)]
 
 
 class CSynth(ctypes.Structure):
