@@ -63,7 +63,7 @@ struct __align__(16) Smem {
                               // tile-relative start position of a verified minimizer, or Q_DROP
     uint32_t bitmap[WORDS];
     uint32_t prefix[WORDS];
-    __align__(128) uint2 tab[16];
+    __align__(128) uint32_t tab[32];   // [0,16): TF, [16,32): bit-reversed TG
     uint64_t hfw[8], hrc[8];  // ntHash seeds by base class (c>>1)&7: A0 C1 T2 G3 N7
     uint32_t warp_sum[NT / 32];
     uint32_t qn;
@@ -171,11 +171,25 @@ __device__ __forceinline__ bool verify_fast(const uint8_t* raw, const uint64_t* 
     return true;
 }
 
-__device__ __forceinline__ uint32_t badword(uint32_t w) {  // nonzero iff some byte is not A/C/G/T
-    uint32_t t = (w >> 2) & ~(w >> 1);
-    uint32_t d = w >> 4;
-    uint32_t b2 = (d & (~t | w)) | (~d & (~w | t));
-    return ((w & 0xE8E8E8E8u) ^ 0x40404040u) | (b2 & 0x01010101u);
+// Alphabet check, word-parallel.  A byte is one of A C G T  iff  bits 7,5,3 are 0, bit 6 is 1,
+// b0 != b4 and b4 == (b2 & ~b1).  The three terms are evaluated at bit 4 of every byte from LEFT
+// shifted copies of the word (left shifts issue on the FMA pipe as IMAD.SHL; the ALU pipe is the
+// bottleneck of this kernel) and OR-accumulated over a chunk; bad_of() folds them once at the end.
+struct BadAcc { uint32_t k, y, x; };
+__device__ __forceinline__ void bad_accumulate(BadAcc& b, uint32_t w) {
+    uint32_t s4 = w << 4, s3 = w << 3, s2 = w << 2;
+    b.k |= w ^ 0x40404040u;            // bits 7,5,3 (and 6) of any byte off the pattern
+    b.y |= ~(s4 ^ w);                  // at bit 4: b0 == b4
+    b.x |= (w ^ (s2 & ~s3));           // at bit 4: b4 != (b2 & ~b1)
+}
+__device__ __forceinline__ uint32_t bad_of(const BadAcc& b) {
+    return (b.k & 0xE8E8E8E8u) | ((b.y | b.x) & 0x10101010u);
+}
+// per-byte form: byte j of the result is non-zero iff byte j of w is not A/C/G/T
+__device__ __forceinline__ uint32_t badword(uint32_t w) {
+    BadAcc b{0, 0, 0};
+    bad_accumulate(b, w);
+    return bad_of(b);
 }
 
 // last r in [lo, hi) with read_off[r] <= p   (read_off[lo] <= p guaranteed)
@@ -212,7 +226,7 @@ __global__ void __launch_bounds__(NT, 5) ka_minimizers_kernel(const KAArgs A) {
     const int lane = tid & 31, warp = tid >> 5;
     const uint32_t l = A.l;
     const uint64_t bound = A.bound;
-    if (tid < 16) sm.tab[tid] = make_uint2(A.fc.tab[tid][0], A.fc.tab[tid][1]);
+    if (tid < 16) { sm.tab[tid] = A.fc.tab_f[tid]; sm.tab[16 + tid] = A.fc.tab_g[tid]; }
     if (tid < 8) {
         sm.hfw[tid] = tid < 4 ? nt_fwd_code(tid) : 0;   // classes 4..7 (illegal bytes and N) hash as 0
         sm.hrc[tid] = tid < 4 ? nt_rc_code(tid) : 0;
@@ -304,11 +318,11 @@ __global__ void __launch_bounds__(NT, 5) ka_minimizers_kernel(const KAArgs A) {
             };
             // one run (C++ form, used on ragged portions): roll the 2-bit history and the two filter
             // words; true if the window ending here may be a minimizer
-            auto run_step = [&](uint32_t code) -> bool {
-                hist = (hist << 2) | code;
-                uint2 tt = sm.tab[((hist >> SH) & 0xCu) | code];
-                F = (F << 1) ^ tt.x;
-                G = (G >> 1) ^ tt.y;
+            auto run_step = [&](uint32_t code) -> bool {   // hist pre-scaled by 4, G bit-reversed
+                hist = (hist << 2) | (code << 2);
+                uint32_t idx = ((hist >> SH) & 0x30u) | (code << 2);
+                F = (F << 1) ^ sm.tab[idx >> 2];
+                G = (G << 1) ^ sm.tab[16 + (idx >> 2)];
                 return F <= fth || (G & gz) == 0;
             };
             // The same step for byte J of a word, hand-scheduled in PTX: every instruction is
@@ -316,19 +330,24 @@ __global__ void __launch_bounds__(NT, 5) ka_minimizers_kernel(const KAArgs A) {
             //   x: word ^ (word shifted by one byte)  cw: 2-bit codes, one per byte
             // TAIL adds the data-dependent halo conditions (runs left to consume, bytes left in
             // the read) and only then looks at the per-byte "not ACGT" flags in bw.
+            // ALU-pipe budget: the kernel is bound by the 16-lane ALU pipe (LOP3/SHF/PRMT/ISETP), so
+            // whatever can run on the FMA pipe does: history update (IMAD), both rolls (IMAD.SHL, G is
+            // kept bit-reversed for that).  A survivor is flagged whenever the CURRENT state passes,
+            // also on the non-run bytes that follow a passing run: phase B drops those (one byte
+            // compare) -- cheaper than and-ing the run predicate into every step.
 #define MDBG_STEP(J, BITN)                                                                                  \
     asm("{\n\t.reg .pred p, q;\n\t.reg .b32 t, c, a, b, tx, ty;\n\t"                                        \
         "and.b32 t, %4, %10;\n\tsetp.ne.u32 p, t, 0;\n\t"                                                   \
         "prmt.b32 c, %5, 0, %11;\n\t"                                                                       \
         "@p mad.lo.u32 %0, %0, 4, c;\n\t"                                                                   \
         "shr.u32 t, %0, %6;\n\t"                                                                            \
-        "lop3.b32 t, t, 12, c, 0xEA;\n\t"                                                                   \
-        "mad.lo.u32 t, t, 8, %7;\n\t"                                                                       \
-        "ld.shared.v2.u32 {tx, ty}, [t];\n\t"                                                               \
+        "lop3.b32 t, t, 48, c, 0xEA;\n\t"                                                                   \
+        "add.u32 t, t, %7;\n\t"                                                                             \
+        "ld.shared.u32 tx, [t];\n\tld.shared.u32 ty, [t+64];\n\t"                                           \
         "shl.b32 a, %1, 1;\n\t@p xor.b32 %1, a, tx;\n\t"                                                    \
-        "shr.u32 b, %2, 1;\n\t@p xor.b32 %2, b, ty;\n\t"                                                    \
+        "shl.b32 b, %2, 1;\n\t@p xor.b32 %2, b, ty;\n\t"                                                    \
         "and.b32 a, %2, %9;\n\tsetp.eq.u32 q, a, 0;\n\t"                                                    \
-        "setp.le.or.u32 q, %1, %8, q;\n\tand.pred q, q, p;\n\t"                                             \
+        "setp.le.or.u32 q, %1, %8, q;\n\t"                                                                  \
         "@q or.b32 %3, %3, %12;\n\t}"                                                                       \
         : "+r"(hist), "+r"(F), "+r"(G), "+r"(cand)                                                          \
         : "r"(x), "r"(cw), "r"(SHr), "r"(tab_r), "r"(fthr), "r"(gzr), "n"(0xFFu << (8 * (J))),              \
@@ -342,11 +361,11 @@ __global__ void __launch_bounds__(NT, 5) ka_minimizers_kernel(const KAArgs A) {
         "@p mad.lo.u32 %0, %0, 4, c;\n\t"                                                                   \
         "@p add.u32 %4, %4, -1;\n\t"                                                                        \
         "shr.u32 t, %0, %8;\n\t"                                                                            \
-        "lop3.b32 t, t, 12, c, 0xEA;\n\t"                                                                   \
-        "mad.lo.u32 t, t, 8, %9;\n\t"                                                                       \
-        "ld.shared.v2.u32 {tx, ty}, [t];\n\t"                                                               \
+        "lop3.b32 t, t, 48, c, 0xEA;\n\t"                                                                   \
+        "add.u32 t, t, %9;\n\t"                                                                             \
+        "ld.shared.u32 tx, [t];\n\tld.shared.u32 ty, [t+64];\n\t"                                           \
         "shl.b32 a, %1, 1;\n\t@p xor.b32 %1, a, tx;\n\t"                                                    \
-        "shr.u32 b, %2, 1;\n\t@p xor.b32 %2, b, ty;\n\t"                                                    \
+        "shl.b32 b, %2, 1;\n\t@p xor.b32 %2, b, ty;\n\t"                                                    \
         "and.b32 a, %2, %11;\n\tsetp.eq.u32 q, a, 0;\n\t"                                                   \
         "setp.le.or.u32 q, %1, %10, q;\n\tand.pred q, q, p;\n\t"                                            \
         "@q or.b32 %3, %3, %14;\n\t}"                                                                       \
@@ -374,6 +393,7 @@ __global__ void __launch_bounds__(NT, 5) ka_minimizers_kernel(const KAArgs A) {
                 asm volatile("mov.b32 %0, %1;" : "=r"(row_r) : "r"(raw_s + (tid + 1) * RSTRIDE));
                 uint32_t pw = 0;
                 int c16 = 0;
+                BadAcc bacc{0, 0, 0};
                 if (pb == a) {
                     uint32_t first = sm.raw[(tid + 1) * RSTRIDE];
                     pw = ((pb > rs) ? (uint32_t)sm.raw[tid * RSTRIDE + 127] : (first ^ 0xFFu)) << 24;
@@ -390,7 +410,7 @@ __global__ void __launch_bounds__(NT, 5) ka_minimizers_kernel(const KAArgs A) {
                     for (int wi = 0; wi < 4; wi++) {
                         uint32_t w = ws[wi];
                         uint32_t x = HPC ? (w ^ __funnelshift_l(pw, w, 8)) : 0xFFFFFFFFu;
-                        uint32_t cw = (w >> 1) & 0x03030303u;
+                        uint32_t cw = (w << 1) & 0x0C0C0C0Cu;   // 2-bit codes, pre-scaled by 4
                         uint32_t bw = badword(w);
                         const int wlo = off - 4 * wi;
                         if (wlo >= 4) { x = 0; bw = 0; }
@@ -423,8 +443,8 @@ __global__ void __launch_bounds__(NT, 5) ka_minimizers_kernel(const KAArgs A) {
                     for (int wi = 0; wi < 4; wi++) {
                         uint32_t w = ws[wi];
                         uint32_t x = HPC ? (w ^ __funnelshift_l(pw, w, 8)) : 0xFFFFFFFFu;
-                        uint32_t cw = (w >> 1) & 0x03030303u;
-                        bad |= badword(w);
+                        uint32_t cw = (w << 1) & 0x0C0C0C0Cu;   // 2-bit codes, pre-scaled by 4
+                        bad_accumulate(bacc, w);
                         if (wi == 0) { MDBG_STEP(0, 0); MDBG_STEP(1, 1); MDBG_STEP(2, 2); MDBG_STEP(3, 3); }
                         if (wi == 1) { MDBG_STEP(0, 4); MDBG_STEP(1, 5); MDBG_STEP(2, 6); MDBG_STEP(3, 7); }
                         if (wi == 2) { MDBG_STEP(0, 8); MDBG_STEP(1, 9); MDBG_STEP(2, 10); MDBG_STEP(3, 11); }
@@ -437,6 +457,7 @@ __global__ void __launch_bounds__(NT, 5) ka_minimizers_kernel(const KAArgs A) {
                         push(a + c16 * 16 + b);
                     }
                 }
+                bad |= bad_of(bacc);
                 // data-dependent halo, same code chunk by chunk: the rows after this thread's row
                 // (up to 256 more bytes) are in shared memory for every thread of the tile
 #pragma unroll 1
@@ -452,7 +473,7 @@ __global__ void __launch_bounds__(NT, 5) ka_minimizers_kernel(const KAArgs A) {
                     for (int wi = 0; wi < 4; wi++) {
                         uint32_t w = ws[wi];
                         uint32_t x = HPC ? (w ^ __funnelshift_l(pw, w, 8)) : 0xFFFFFFFFu;
-                        uint32_t cw = (w >> 1) & 0x03030303u;
+                        uint32_t cw = (w << 1) & 0x0C0C0C0Cu;   // 2-bit codes, pre-scaled by 4
                         uint32_t bw = badword(w);
                         if (wi == 0) { MDBG_TSTEP(0, 0); MDBG_TSTEP(1, 1); MDBG_TSTEP(2, 2); MDBG_TSTEP(3, 3); }
                         if (wi == 1) { MDBG_TSTEP(0, 4); MDBG_TSTEP(1, 5); MDBG_TSTEP(2, 6); MDBG_TSTEP(3, 7); }
@@ -530,6 +551,9 @@ __global__ void __launch_bounds__(NT, 5) ka_minimizers_kernel(const KAArgs A) {
                     if (pe >= t1) hi2 = A.n_reads;
                     uint64_t r = find_read(A.read_off, rlo, hi2, pe);
                     int64_t rs = (int64_t)__ldg(A.read_off + r);
+                    // the scan flags every byte at which the filter state passes, also the non-run
+                    // bytes after a passing run: only run starts are windows
+                    if (HPC && pe > rs && W.byte(pe - 1) == W.byte(pe)) continue;
                     int64_t p0;
                     uint64_t h;
                     int rel_p0;

@@ -94,20 +94,30 @@ MDBG_HD uint64_t fp_init(uint64_t seed, uint32_t k) { return seed ^ (0x9e3779b97
 //     (F <= f_thresh) || ((G & g_zero) == 0)
 // (g_zero = the exact bits of G above the bit length of top_E(bound): one LOP3 with a predicate
 // result instead of mask + compare) is a superset test passing ~0.7 % of the windows at
-// d = 0.003; survivors are re-evaluated exactly in 64 bits.  Valid for 4 <= l <= 15 (the 2-bit
-// history register holds l+1 codes).
+// d = 0.003; survivors are re-evaluated exactly in 64 bits.  Valid for 4 <= l <= 14 (the 2-bit
+// history register holds l+1 codes, pre-scaled by 4).
+// The kernel keeps G BIT-REVERSED (so that it, too, rolls with a left shift, which the compiler
+// issues on the otherwise idle FMA pipe as IMAD.SHL) and the 2-bit history pre-scaled by 4 (the
+// table index (out<<2|in) then needs no scaling: tables are two arrays of 16 32-bit words).
 struct FilterConsts {
-    uint32_t tab[16][2];   // [out<<2 | in] -> {TF, TG}
-    uint32_t f_init, g_init;
-    uint32_t f_thresh, g_mask, g_thresh, g_zero;
+    uint32_t tab_f[16];    // [out<<2 | in] -> TF
+    uint32_t tab_g[16];    // [out<<2 | in] -> bitrev(TG)
+    uint32_t f_init, g_init;            // g_init bit-reversed
+    uint32_t f_thresh, g_mask, g_thresh, g_zero;   // g_zero bit-reversed; g_mask/g_thresh plain (tests)
     uint32_t hist_shift;   // 2l-2
     uint32_t usable;       // 0 => use the exact (dense) path
 };
 
+inline uint32_t brev32(uint32_t x) {
+    uint32_t r = 0;
+    for (int i = 0; i < 32; i++) r |= ((x >> i) & 1u) << (31 - i);
+    return r;
+}
+
 inline FilterConsts make_filter(uint32_t l, uint64_t bound) {
     FilterConsts fc{};
     fc.usable = 0;
-    if (l < 4 || l > 15) return fc;
+    if (l < 4 || l > 14) return fc;   // history = l+1 codes, pre-scaled by 4: 2l+4 <= 32
     uint32_t bh = (uint32_t)(bound >> 32);
     // the filter only pays when few windows pass: require >= 5 leading zero bits (d < 1/32)
     if (bh >= (1u << 27)) return fc;
@@ -115,8 +125,8 @@ inline FilterConsts make_filter(uint32_t l, uint64_t bound) {
         for (uint32_t i = 0; i < 4; i++) {
             uint32_t ho = (uint32_t)(nt_fwd_code(o) >> 32), hi = (uint32_t)(nt_fwd_code(i) >> 32);
             uint32_t ro = (uint32_t)(nt_rc_code(o) >> 32), ri = (uint32_t)(nt_rc_code(i) >> 32);
-            fc.tab[(o << 2) | i][0] = (ho << l) ^ hi;
-            fc.tab[(o << 2) | i][1] = (ro >> l) ^ ri;
+            fc.tab_f[(o << 2) | i] = (ho << l) ^ hi;
+            fc.tab_g[(o << 2) | i] = brev32((ro >> l) ^ ri);
         }
     uint32_t ha = (uint32_t)(nt_fwd_code(0) >> 32), ra = (uint32_t)(nt_rc_code(0) >> 32);
     fc.f_init = fc.g_init = 0;
@@ -130,7 +140,8 @@ inline FilterConsts make_filter(uint32_t l, uint64_t bound) {
     fc.g_thresh = bh >> (l - 1);
     uint32_t bl = 0;                         // bit length of top_E(bound)
     while (bl < 32 && (fc.g_thresh >> bl) != 0) bl++;
-    fc.g_zero = fc.g_mask & ~((bl >= 32) ? 0xffffffffu : ((1u << bl) - 1u));
+    fc.g_zero = brev32(fc.g_mask & ~((bl >= 32) ? 0xffffffffu : ((1u << bl) - 1u)));
+    fc.g_init = brev32(fc.g_init);
     fc.hist_shift = 2 * l - 2;
     fc.usable = 1;
     return fc;

@@ -129,3 +129,24 @@ def test_filter_is_superset(oracle):
                     assert passed, (l, d, i)
         true = int((hashes <= np.uint64(bound)).sum())
         assert true <= npass <= true * 2.2 + 20, (l, d, true, npass)
+
+
+def test_alphabet_predicate_model():
+    """Word-parallel A/C/G/T check of the K-A kernel (bad_accumulate in ka_minimizers.cu), modelled
+    bit for bit: byte j of the result is non-zero iff byte j of the word is not one of ACGT."""
+    M = 0xFFFFFFFF
+
+    def badword(w):
+        s4, s3, s2 = (w << 4) & M, (w << 3) & M, (w << 2) & M
+        k, y, x = w ^ 0x40404040, (~(s4 ^ w)) & M, (w ^ (s2 & ~s3)) & M
+        return (k & 0xE8E8E8E8) | ((y | x) & 0x10101010)
+
+    for lane in range(4):
+        for c in range(256):
+            for fill in b"ACGT":
+                w = 0
+                for j in range(4):
+                    w |= (c if j == lane else fill) << (8 * j)
+                bw = badword(w)
+                for j in range(4):
+                    assert (((bw >> (8 * j)) & 0xFF) != 0) == (j == lane and chr(c) not in "ACGT")
