@@ -197,6 +197,8 @@ int mdbg_flush_l2(mdbg_ctx* ctx);
 #define MDBG_NCCL_ID_BYTES 128
 int mdbg_nccl_unique_id(uint8_t id[MDBG_NCCL_ID_BYTES]);             /* rank 0, then broadcast */
 int mdbg_comm_init(mdbg_ctx* ctx, const uint8_t id[MDBG_NCCL_ID_BYTES], int rank, int world);
+/* global index of the first read this rank pushes (default: ranks are numbered in rank order) */
+int mdbg_comm_set_read_base(mdbg_ctx* ctx, uint64_t first_read);
 /* host-only planning helpers (pure functions, testable without a GPU) */
 void     mdbg_shard_reads(uint64_t n_reads_total, int world, int rank, uint64_t* lo, uint64_t* hi);
 uint32_t mdbg_owner_of_fingerprint(uint64_t fp, int world);

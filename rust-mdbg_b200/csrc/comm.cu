@@ -41,4 +41,13 @@ int mdbg_comm_init(mdbg_ctx* c, const uint8_t id[MDBG_NCCL_ID_BYTES], int rank, 
     return MDBG_OK;
 }
 
+// Global index of the first read this rank pushes (reads are sharded by record in contiguous
+// ranges).  Without it the ranks number their reads in rank order of what they pushed.
+int mdbg_comm_set_read_base(mdbg_ctx* c, uint64_t first_read) {
+    if (!c) return MDBG_ERR_BAD_ARG;
+    c->read_base = first_read;
+    c->read_base_set = true;
+    return MDBG_OK;
+}
+
 }  // extern "C"

@@ -87,6 +87,7 @@ struct mdbg_ctx {
     mdbg_timings tm{};
     // NCCL (multi-GPU)
     void* comm = nullptr; int rank = 0, world = 1;
+    uint64_t read_base = 0; bool read_base_set = false;   // global index of this rank's first read
     // device-resident result of the last finish (kept until the next finish/reset)
     struct DeviceGraph* dg = nullptr;
 };

@@ -1,7 +1,21 @@
 // graph.cu -- mdbg_finish / mdbg_finish_device / mdbg_window: host orchestration of K-B .. K-E
 // (kernels in graph_kernels.cuh; radix sort / scan / select are CUB device-wide primitives).
+//
 // Serial-order semantics: index = rank of a tuple's first sighting, abundance =
 // sightings (u16), seqlen/shift/sequence from the minabund-th sighting.
+//
+// One code path for 1 and N GPUs (one process per GPU, NCCL over NVLink):
+//   1. every k-min-mer sighting becomes a RECORD {canonical tuple, global ordinal, RecInfo}
+//   2. N > 1: records are range-partitioned by tuple fingerprint and exchanged with ONE
+//      all-to-all (grouped ncclSend/ncclRecv), so every copy of a tuple meets on one owner;
+//      records arrive grouped by source rank = ascending global ordinal
+//   3. owner: open-address table (fingerprint placed, tuple verified), stable radix sort by slot,
+//      segmented reduce -> abundance / first sighting / representative sighting
+//   4. node index = number of distinct tuples first seen earlier anywhere: the owners all-gather
+//      their sorted first-sighting ordinals and sum W lower_bounds
+//   5. solid nodes are all-gathered (small: ~2d nodes per genome base); every GPU builds the
+//      (k-1)-mer entry index and emits the edges of its slice of the nodes; presimp removals are
+//      all-gathered before the final filter
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -13,16 +27,18 @@
 
 #include "ctx.h"
 #include "graph_kernels.cuh"
+#include "nccl_dl.h"
 
 using namespace mdbg;
 
 // Device-resident result of the last finish.
 struct DeviceGraph {
     uint64_t n_kminmers = 0, n_distinct = 0, n_nodes = 0, n_edges = 0, presimp_removed = 0, n_seqlines = 0;
+    uint64_t n_edges_local = 0, n_seq_local = 0;
     uint32_t k = 0;
     Tmp<uint32_t> index; Tmp<uint16_t> abundance; Tmp<uint32_t> seqlen; Tmp<uint16_t> shift; Tmp<uint64_t> tuple;
-    Tmp<uint32_t> e_n1, e_n2, e_ov; Tmp<uint8_t> e_o1, e_o2;
-    Tmp<uint32_t> q_index; Tmp<uint64_t> q_read, q_start, q_end, q_shift; Tmp<uint8_t> q_rev;
+    Tmp<uint32_t> e_n1, e_n2, e_ov; Tmp<uint8_t> e_o1, e_o2;   // this GPU's slice (sorted)
+    Tmp<SeqRec> seq;                                           // this GPU's lines (ordinal order)
 };
 
 extern "C" void mdbg_graph_device_free(mdbg_ctx* c) {
@@ -36,7 +52,6 @@ inline unsigned nblk(uint64_t n, unsigned bs = 256) { return (unsigned)std::max<
 struct Runner {  // CUB call helper: size query, pooled temp storage, launch accounting
     mdbg_ctx* c;
     Tmp<uint8_t> temp;
-    int err = 0;
     template <class F>
     int cub(F&& f) {
         size_t bytes = 0;
@@ -56,6 +71,14 @@ struct Runner {  // CUB call helper: size query, pooled temp storage, launch acc
 
 #define RC(x) do { int _rc = (x); if (_rc) return _rc; } while (0)
 #define LAUNCHED(c) do { (c)->tm.launches_finish++; MDBG_CK(c, cudaGetLastError()); } while (0)
+#define NCK(c, call)                                                                        \
+    do {                                                                                    \
+        ncclResult_t _r = (call);                                                           \
+        if (_r != ncclSuccess) {                                                            \
+            (c)->err = std::string(#call) + ": " + nccl().GetErrorString(_r);               \
+            return MDBG_ERR_NCCL;                                                           \
+        }                                                                                   \
+    } while (0)
 
 int read_scalars(mdbg_ctx* c) {
     MDBG_CK(c, cudaMemcpyAsync(c->h_sc, c->d_sc, sizeof(Scalars), cudaMemcpyDeviceToHost, c->st));
@@ -65,6 +88,82 @@ int read_scalars(mdbg_ctx* c) {
 
 int log2_ceil(uint64_t x) { int b = 0; while ((1ull << b) < x) b++; return b; }
 
+// ---- NCCL helpers (world > 1) -----------------------------------------------------------------
+// all[s * n + i] = value i of rank s
+int allgather_u64(mdbg_ctx* c, const uint64_t* mine, int n, std::vector<uint64_t>& all) {
+    const int W = c->world;
+    all.assign((size_t)W * n, 0);
+    if (W == 1) { for (int i = 0; i < n; i++) all[i] = mine[i]; return MDBG_OK; }
+    Tmp<uint64_t> d_in, d_out;
+    MDBG_CK(c, d_in.get(c->pool, n));
+    MDBG_CK(c, d_out.get(c->pool, (size_t)W * n));
+    MDBG_CK(c, cudaMemcpyAsync(d_in, mine, n * 8, cudaMemcpyHostToDevice, c->st));
+    NCK(c, nccl().AllGather(d_in, d_out, n, ncclUint64, (ncclComm_t)c->comm, c->st));
+    MDBG_CK(c, cudaMemcpyAsync(all.data(), d_out, (size_t)W * n * 8, cudaMemcpyDeviceToHost, c->st));
+    MDBG_CK(c, cudaStreamSynchronize(c->st));
+    return MDBG_OK;
+}
+
+// variable all-to-all of `elem`-byte items: send_cnt[d] items to rank d (send buffer grouped by
+// destination), recv_cnt[s] items from rank s (receive buffer grouped by source)
+int alltoallv(mdbg_ctx* c, const void* send, const uint64_t* send_cnt, void* recv, const uint64_t* recv_cnt,
+              size_t elem) {
+    const int W = c->world;
+    NcclApi& N = nccl();
+    size_t so = 0, ro = 0;
+    NCK(c, N.GroupStart());
+    for (int p = 0; p < W; p++) {
+        if (send_cnt[p]) NCK(c, N.Send((const char*)send + so, send_cnt[p] * elem, ncclChar, p, (ncclComm_t)c->comm, c->st));
+        if (recv_cnt[p]) NCK(c, N.Recv((char*)recv + ro, recv_cnt[p] * elem, ncclChar, p, (ncclComm_t)c->comm, c->st));
+        so += send_cnt[p] * elem;
+        ro += recv_cnt[p] * elem;
+    }
+    NCK(c, N.GroupEnd());
+    return MDBG_OK;
+}
+
+// all-gather of variable-length arrays: every rank ends with the concatenation in rank order
+int allgatherv(mdbg_ctx* c, const void* mine, uint64_t my_cnt, const std::vector<uint64_t>& cnt, void* out,
+               size_t elem) {
+    const int W = c->world;
+    if (W == 1) {
+        if (my_cnt && out != mine) MDBG_CK(c, cudaMemcpyAsync(out, mine, my_cnt * elem, cudaMemcpyDeviceToDevice, c->st));
+        return MDBG_OK;
+    }
+    NcclApi& N = nccl();
+    size_t ro = 0;
+    NCK(c, N.GroupStart());
+    for (int p = 0; p < W; p++) {
+        if (my_cnt) NCK(c, N.Send(mine, my_cnt * elem, ncclChar, p, (ncclComm_t)c->comm, c->st));
+        if (cnt[p]) NCK(c, N.Recv((char*)out + ro, cnt[p] * elem, ncclChar, p, (ncclComm_t)c->comm, c->st));
+        ro += cnt[p] * elem;
+    }
+    NCK(c, N.GroupEnd());
+    return MDBG_OK;
+}
+
+// gather variable-length arrays on rank 0 (concatenated in rank order)
+int gatherv_root(mdbg_ctx* c, const void* mine, uint64_t my_cnt, const std::vector<uint64_t>& cnt, void* out,
+                 size_t elem) {
+    const int W = c->world;
+    if (W == 1) {
+        if (my_cnt && out != mine) MDBG_CK(c, cudaMemcpyAsync(out, mine, my_cnt * elem, cudaMemcpyDeviceToDevice, c->st));
+        return MDBG_OK;
+    }
+    NcclApi& N = nccl();
+    NCK(c, N.GroupStart());
+    if (my_cnt) NCK(c, N.Send(mine, my_cnt * elem, ncclChar, 0, (ncclComm_t)c->comm, c->st));
+    if (c->rank == 0) {
+        size_t ro = 0;
+        for (int p = 0; p < W; p++) {
+            if (cnt[p]) NCK(c, N.Recv((char*)out + ro, cnt[p] * elem, ncclChar, p, (ncclComm_t)c->comm, c->st));
+            ro += cnt[p] * elem;
+        }
+    }
+    NCK(c, N.GroupEnd());
+    return MDBG_OK;
+}
+
 // Everything from the resident minimizers to the device graph.
 int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
     mdbg_graph_device_free(c);
@@ -72,254 +171,340 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
     c->dg = G;
     const uint32_t k = c->p.k, l = c->p.l, minab = c->p.min_abundance;
     const float presimp = c->p.presimp;
+    const int W = c->world, rank = c->rank;
     G->k = k;
     c->tm.launches_finish = 0;
     c->tm.table_attempts = 0;
+    c->tm.ms_kb = c->tm.ms_kc = c->tm.ms_kd = c->tm.ms_ke = 0;
     cudaStream_t st = c->st;
     Runner R{c};
+    if (W > 1 && !c->comm) { c->err = "world > 1 but mdbg_comm_init was not called"; return MDBG_ERR_BAD_ARG; }
     if (c->M >= 0xFFFFFFF0ull) { c->err = "more than 2^32 minimizers on one GPU"; return MDBG_ERR_RANGE; }
     MDBG_CK(c, cudaEventRecord(c->ev[5], st));
     MinArena A{c->m_hash, c->m_pos, c->m_off, c->R};
     const uint64_t nR = c->R;
 
-    // ---- K-B: k-min-mer offsets per read ------------------------------------------------------
+    // ---- K-B: records -------------------------------------------------------------------------
     Tmp<uint64_t> cnt, kmer_off;
     MDBG_CK(c, cnt.get(c->pool, nR + 1));
     MDBG_CK(c, kmer_off.get(c->pool, nR + 1));
-    uint64_t K = 0;
+    uint64_t Kl = 0;  // local sightings
     if (nR > 0 && c->M > 0) {
         kb_count_kernel<<<nblk(nR + 1), 256, 0, st>>>(c->m_off, nR, k, cnt);
         LAUNCHED(c);
         RC(R.cub([&](void* t, size_t& b) { return cub::DeviceScan::ExclusiveSum(t, b, cnt.p, kmer_off.p, nR + 1, st); }));
         MDBG_CK(c, cudaMemcpyAsync(&c->h_sc->v[0], kmer_off.p + nR, 8, cudaMemcpyDeviceToHost, st));
         MDBG_CK(c, cudaStreamSynchronize(st));
-        K = c->h_sc->v[0];
+        Kl = c->h_sc->v[0];
     }
-    G->n_kminmers = K;
-    if (K >= 0x7FFFFFF0ull) { c->err = "more than 2^31 k-min-mers on one GPU"; return MDBG_ERR_RANGE; }
-    MDBG_CK(c, cudaEventRecord(c->ev[6], st));
-    if (K == 0) {
-        MDBG_CK(c, cudaEventRecord(c->ev[7], st));
-        MDBG_CK(c, cudaEventRecord(c->ev[8], st));
-        MDBG_CK(c, cudaEventRecord(c->ev[9], st));
-        return MDBG_OK;
-    }
+    if (Kl >= 0x7FFFFFF0ull) { c->err = "more than 2^31 k-min-mers on one GPU"; return MDBG_ERR_RANGE; }
+    // global ordinal / read bases
+    std::vector<uint64_t> allK;
+    { uint64_t mine[2] = {Kl, c->R}; RC(allgather_u64(c, mine, 2, allK)); }
+    uint64_t ord_base = 0, read_base = c->read_base, Ktot = 0;
+    for (int r = 0; r < W; r++) { if (r < rank) ord_base += allK[2 * r]; Ktot += allK[2 * r]; }
+    if (W > 1 && !c->read_base_set) { read_base = 0; for (int r = 0; r < rank; r++) read_base += allK[2 * r + 1]; }
+    G->n_kminmers = Ktot;
 
-    // ---- K-B window + K-C table (retry with a new seed on a fingerprint collision) --------------
-    Tmp<uint64_t> fp; Tmp<uint32_t> loc, iota, slot, first; Tmp<uint8_t> rev; Tmp<uint64_t> keys;
-    MDBG_CK(c, fp.get(c->pool, K));
-    MDBG_CK(c, loc.get(c->pool, K));
-    MDBG_CK(c, iota.get(c->pool, K));
-    MDBG_CK(c, slot.get(c->pool, K));
-    MDBG_CK(c, rev.get(c->pool, K));
-    const int cap_bits = std::max(12, log2_ceil(2 * K));
-    const uint64_t cap = 1ull << cap_bits;
-    MDBG_CK(c, keys.get(c->pool, cap));
-    MDBG_CK(c, first.get(c->pool, cap));
-    float ms_kb = 0, ms_kc = 0;
-    for (int attempt = 0;; attempt++) {
-        if (attempt >= 8) { c->err = "fingerprint collisions persisted over 8 seeds"; return MDBG_ERR_RANGE; }
-        c->tm.table_attempts = attempt + 1;
-        uint64_t seed = 0x6d64626700000000ull + 0x9e3779b97f4a7c15ull * (uint64_t)attempt;
-        uint64_t mask = ~0ull;
-        if (attempt == 0 && c->p.debug_fp_bits > 0 && c->p.debug_fp_bits < 64) mask = (1ull << c->p.debug_fp_bits) - 1;
-        MDBG_CK(c, cudaEventRecord(c->ev[10], st));
-        kb_window_kernel<<<nblk(K), 256, 0, st>>>(A, kmer_off, K, k, seed, mask, fp, loc, rev, iota);
+    Tmp<uint64_t> l_tuple, l_ord, l_fp;
+    Tmp<RecInfo> l_info;
+    MDBG_CK(c, l_tuple.get(c->pool, Kl * k));
+    MDBG_CK(c, l_ord.get(c->pool, Kl));
+    MDBG_CK(c, l_info.get(c->pool, Kl));
+    MDBG_CK(c, l_fp.get(c->pool, Kl));
+    if (Kl) {
+        kb_records_kernel<<<nblk(Kl), 256, 0, st>>>(A, kmer_off, Kl, k, 0x6d64626700000000ull, ord_base, read_base,
+                                                    l_tuple, l_ord, l_info, l_fp);
         LAUNCHED(c);
-        MDBG_CK(c, cudaEventRecord(c->ev[11], st));
-        MDBG_CK(c, cudaMemsetAsync(keys, 0xFF, cap * 8, st));
-        MDBG_CK(c, cudaMemsetAsync(first, 0xFF, cap * 4, st));
-        MDBG_CK(c, cudaMemsetAsync(&c->d_sc->v[1], 0, 8, st));
-        kc_insert_kernel<<<nblk(K * 4), 256, 0, st>>>(fp, K, keys, first, cap - 1, slot);
-        LAUNCHED(c);
-        kc_verify_kernel<<<nblk(K), 256, 0, st>>>(A, K, k, slot, first, loc, rev, &c->d_sc->v[1]);
-        LAUNCHED(c);
-        MDBG_CK(c, cudaEventRecord(c->ev[12], st));
-        RC(read_scalars(c));
-        float a = 0, b = 0;
-        cudaEventElapsedTime(&a, c->ev[10], c->ev[11]);
-        cudaEventElapsedTime(&b, c->ev[11], c->ev[12]);
-        ms_kb += a; ms_kc += b;
-        if (c->h_sc->v[1] == 0) break;  // every slot holds exactly one tuple
     }
-    keys.reset();
-    fp.reset();
+    cnt.reset();
+    kmer_off.reset();
+
+    // ---- exchange: all copies of a tuple meet on the owner of its fingerprint range -------------
+    uint64_t K = Kl;  // records this GPU owns
+    Tmp<uint64_t> x_tuple, x_ord;
+    Tmp<RecInfo> x_info;
+    uint64_t* r_tuple = l_tuple; uint64_t* r_ord = l_ord; RecInfo* r_info = l_info;
+    if (W > 1) {
+        Tmp<uint32_t> owner, owner_s, iota, perm;
+        Tmp<uint64_t> s_tuple, s_ord;
+        Tmp<RecInfo> s_info;
+        Tmp<unsigned long long> d_start;
+        MDBG_CK(c, owner.get(c->pool, Kl)); MDBG_CK(c, owner_s.get(c->pool, Kl));
+        MDBG_CK(c, iota.get(c->pool, Kl)); MDBG_CK(c, perm.get(c->pool, Kl));
+        MDBG_CK(c, s_tuple.get(c->pool, Kl * k)); MDBG_CK(c, s_ord.get(c->pool, Kl)); MDBG_CK(c, s_info.get(c->pool, Kl));
+        MDBG_CK(c, d_start.get(c->pool, W + 1));
+        std::vector<uint64_t> send_cnt(W, 0);
+        if (Kl) {
+            kb_owner_kernel<<<nblk(Kl), 256, 0, st>>>(l_fp, Kl, (uint32_t)W, owner, iota);
+            LAUNCHED(c);
+            RC(R.cub([&](void* t, size_t& b) {   // stable: ordinal order is kept inside every destination
+                return cub::DeviceRadixSort::SortPairs(t, b, owner.p, owner_s.p, iota.p, perm.p, (uint32_t)Kl, 0,
+                                                       std::max(1, log2_ceil(W)), st);
+            }));
+            kb_permute_kernel<<<nblk(Kl), 256, 0, st>>>(perm, Kl, k, l_tuple, l_ord, l_info, s_tuple, s_ord, s_info);
+            LAUNCHED(c);
+        }
+        kb_owner_counts_kernel<<<nblk(Kl + 1), 256, 0, st>>>(owner_s, Kl, (uint32_t)W, d_start);
+        LAUNCHED(c);
+        std::vector<unsigned long long> h_start(W + 1);
+        MDBG_CK(c, cudaMemcpyAsync(h_start.data(), d_start, (W + 1) * 8, cudaMemcpyDeviceToHost, st));
+        MDBG_CK(c, cudaStreamSynchronize(st));
+        for (int p = 0; p < W; p++) send_cnt[p] = h_start[p + 1] - h_start[p];
+        std::vector<uint64_t> mat;
+        RC(allgather_u64(c, send_cnt.data(), W, mat));
+        std::vector<uint64_t> recv_cnt(W);
+        K = 0;
+        for (int s = 0; s < W; s++) { recv_cnt[s] = mat[(size_t)s * W + rank]; K += recv_cnt[s]; }
+        if (K >= 0x7FFFFFF0ull) { c->err = "more than 2^31 k-min-mers owned by one GPU"; return MDBG_ERR_RANGE; }
+        MDBG_CK(c, x_tuple.get(c->pool, K * k)); MDBG_CK(c, x_ord.get(c->pool, K)); MDBG_CK(c, x_info.get(c->pool, K));
+        std::vector<uint64_t> sc_t(W), rc_t(W);
+        for (int p = 0; p < W; p++) { sc_t[p] = send_cnt[p] * k; rc_t[p] = recv_cnt[p] * k; }
+        RC(alltoallv(c, s_tuple, sc_t.data(), x_tuple, rc_t.data(), 8));
+        RC(alltoallv(c, s_ord, send_cnt.data(), x_ord, recv_cnt.data(), 8));
+        RC(alltoallv(c, s_info, send_cnt.data(), x_info, recv_cnt.data(), sizeof(RecInfo)));
+        MDBG_CK(c, cudaStreamSynchronize(st));   // send buffers are released below
+        r_tuple = x_tuple; r_ord = x_ord; r_info = x_info;
+        l_tuple.reset(); l_ord.reset(); l_info.reset();
+    }
+    l_fp.reset();
+    MDBG_CK(c, cudaEventRecord(c->ev[6], st));
+
+    // ---- K-C table (retry with a new seed on a fingerprint collision) ---------------------------
+    uint32_t D = 0, S_local = 0, Q_local = 0;
+    Tmp<uint32_t> slot, first, iota, sslot, sj, seg_start, seg_index, solid_seg, nseq, seq_off;
+    Tmp<uint64_t> first_ord;
+    Tmp<uint8_t> solid;
+    const int cap_bits = std::max(12, log2_ceil(2 * std::max<uint64_t>(K, 1)));
+    if (K > 0) {
+        Tmp<uint64_t> fp, keys;
+        const uint64_t cap = 1ull << cap_bits;
+        MDBG_CK(c, fp.get(c->pool, K)); MDBG_CK(c, iota.get(c->pool, K)); MDBG_CK(c, slot.get(c->pool, K));
+        MDBG_CK(c, keys.get(c->pool, cap)); MDBG_CK(c, first.get(c->pool, cap));
+        for (int attempt = 0;; attempt++) {
+            if (attempt >= 8) { c->err = "fingerprint collisions persisted over 8 seeds"; return MDBG_ERR_RANGE; }
+            c->tm.table_attempts = attempt + 1;
+            uint64_t seed = 0x7461626c65000000ull + 0x9e3779b97f4a7c15ull * (uint64_t)attempt;
+            uint64_t mask = ~0ull;
+            if (attempt == 0 && c->p.debug_fp_bits > 0 && c->p.debug_fp_bits < 64) mask = (1ull << c->p.debug_fp_bits) - 1;
+            kc_fp_kernel<<<nblk(K), 256, 0, st>>>(r_tuple, K, k, seed, mask, fp, iota);
+            LAUNCHED(c);
+            MDBG_CK(c, cudaMemsetAsync(keys, 0xFF, cap * 8, st));
+            MDBG_CK(c, cudaMemsetAsync(first, 0xFF, cap * 4, st));
+            MDBG_CK(c, cudaMemsetAsync(&c->d_sc->v[1], 0, 8, st));
+            kc_insert_kernel<<<nblk(K * 4), 256, 0, st>>>(fp, K, keys, first, cap - 1, slot);
+            LAUNCHED(c);
+            kc_verify_kernel<<<nblk(K), 256, 0, st>>>(r_tuple, K, k, slot, first, &c->d_sc->v[1]);
+            LAUNCHED(c);
+            RC(read_scalars(c));
+            if (c->h_sc->v[1] == 0) break;  // every slot holds exactly one tuple
+        }
+    }
     MDBG_CK(c, cudaEventRecord(c->ev[7], st));
 
-    // ---- K-D: sort ordinals by slot (stable => ascending ordinal inside a slot), segment -------
-    Tmp<uint32_t> sslot, sg;
-    MDBG_CK(c, sslot.get(c->pool, K));
-    MDBG_CK(c, sg.get(c->pool, K));
-    RC(R.cub([&](void* t, size_t& b) {
-        return cub::DeviceRadixSort::SortPairs(t, b, slot.p, sslot.p, iota.p, sg.p, (uint32_t)K, 0, cap_bits, st);
-    }));
-    iota.reset();
-    Tmp<uint8_t> head;
-    Tmp<uint32_t> seg_start;
-    MDBG_CK(c, head.get(c->pool, K));
-    MDBG_CK(c, seg_start.get(c->pool, K + 1));
-    kd_heads_kernel<<<nblk(K), 256, 0, st>>>(sslot, K, head);
-    LAUNCHED(c);
-    RC(R.cub([&](void* t, size_t& b) {
-        return cub::DeviceSelect::Flagged(t, b, cub::CountingInputIterator<uint32_t>(0), head.p, seg_start.p,
-                                          (uint32_t*)&c->d_sc->v[2], (uint32_t)K, st);
-    }));
-    RC(read_scalars(c));
-    const uint32_t D = (uint32_t)(c->h_sc->v[2] & 0xFFFFFFFFu);
-    G->n_distinct = D;
-    sslot.reset();
-    head.reset();
-    Tmp<uint8_t> flag_first, flag_seq, solid;
-    Tmp<uint32_t> seg_first, first_rank, solid_seg;
-    MDBG_CK(c, flag_first.get(c->pool, K));
-    MDBG_CK(c, flag_seq.get(c->pool, K));
-    MDBG_CK(c, solid.get(c->pool, D));
-    MDBG_CK(c, seg_first.get(c->pool, D));
-    MDBG_CK(c, first_rank.get(c->pool, K));
-    MDBG_CK(c, solid_seg.get(c->pool, D));
-    MDBG_CK(c, cudaMemsetAsync(flag_first, 0, K, st));
-    MDBG_CK(c, cudaMemsetAsync(flag_seq, 0, K, st));
-    kd_segments_kernel<<<nblk(D), 256, 0, st>>>(seg_start, D, K, sg, minab, flag_first, flag_seq, solid, seg_first);
-    LAUNCHED(c);
-    // node index = number of earlier first sightings (NODE_INDEX order, main.rs:662)
-    RC(R.cub([&](void* t, size_t& b) {
-        return cub::DeviceScan::ExclusiveSum(t, b, flag_first.p, first_rank.p, (uint32_t)K, st);
-    }));
-    RC(R.cub([&](void* t, size_t& b) {
-        return cub::DeviceSelect::Flagged(t, b, cub::CountingInputIterator<uint32_t>(0), solid.p, solid_seg.p,
-                                          (uint32_t*)&c->d_sc->v[3], (uint32_t)D, st);
-    }));
-    Tmp<uint32_t> seq_g;
-    if (want_seqlines) {
-        MDBG_CK(c, seq_g.get(c->pool, K));
+    // ---- K-D: stable sort by slot, segments ------------------------------------------------------
+    if (K > 0) {
+        MDBG_CK(c, sslot.get(c->pool, K)); MDBG_CK(c, sj.get(c->pool, K));
         RC(R.cub([&](void* t, size_t& b) {
-            return cub::DeviceSelect::Flagged(t, b, cub::CountingInputIterator<uint32_t>(0), flag_seq.p, seq_g.p,
-                                              (uint32_t*)&c->d_sc->v[4], (uint32_t)K, st);
+            return cub::DeviceRadixSort::SortPairs(t, b, slot.p, sslot.p, iota.p, sj.p, (uint32_t)K, 0, cap_bits, st);
         }));
-    }
-    RC(read_scalars(c));
-    const uint32_t S = (uint32_t)(c->h_sc->v[3] & 0xFFFFFFFFu);
-    const uint32_t Q = want_seqlines ? (uint32_t)(c->h_sc->v[4] & 0xFFFFFFFFu) : 0;
-    G->n_nodes = S;
-    G->n_seqlines = Q;
-    flag_first.reset();
-    flag_seq.reset();
-    solid.reset();
-
-    // nodes in ascending index order
-    MDBG_CK(c, G->index.get(c->pool, S));
-    MDBG_CK(c, G->abundance.get(c->pool, S));
-    MDBG_CK(c, G->seqlen.get(c->pool, S));
-    MDBG_CK(c, G->shift.get(c->pool, 2 * (uint64_t)S));
-    MDBG_CK(c, G->tuple.get(c->pool, (uint64_t)S * k));
-    if (S > 0) {
-        Tmp<uint32_t> nkey, nkey_s, nseg_s;
-        MDBG_CK(c, nkey.get(c->pool, S));
-        MDBG_CK(c, nkey_s.get(c->pool, S));
-        MDBG_CK(c, nseg_s.get(c->pool, S));
-        kd_node_keys_kernel<<<nblk(S), 256, 0, st>>>(solid_seg, S, seg_first, first_rank, nkey);
+        Tmp<uint8_t> head;
+        MDBG_CK(c, head.get(c->pool, K)); MDBG_CK(c, seg_start.get(c->pool, K + 1));
+        kd_heads_kernel<<<nblk(K), 256, 0, st>>>(sslot, K, head);
         LAUNCHED(c);
         RC(R.cub([&](void* t, size_t& b) {
-            return cub::DeviceRadixSort::SortPairs(t, b, nkey.p, nkey_s.p, solid_seg.p, nseg_s.p, S, 0, 32, st);
+            return cub::DeviceSelect::Flagged(t, b, cub::CountingInputIterator<uint32_t>(0), head.p, seg_start.p,
+                                              (uint32_t*)&c->d_sc->v[2], (uint32_t)K, st);
         }));
-        NodeOut NO{G->index, G->abundance, G->seqlen, G->shift, G->tuple};
-        kd_nodes_kernel<<<nblk(S), 256, 0, st>>>(A, S, k, minab, K, D, nkey_s, nseg_s, seg_start, sg, loc, rev, 0, NO);
-        LAUNCHED(c);
+        RC(read_scalars(c));
+        D = (uint32_t)(c->h_sc->v[2] & 0xFFFFFFFFu);
     }
-    if (want_seqlines) {
-        MDBG_CK(c, G->q_index.get(c->pool, Q));
-        MDBG_CK(c, G->q_read.get(c->pool, Q));
-        MDBG_CK(c, G->q_start.get(c->pool, Q));
-        MDBG_CK(c, G->q_end.get(c->pool, Q));
-        MDBG_CK(c, G->q_rev.get(c->pool, Q));
-        MDBG_CK(c, G->q_shift.get(c->pool, 2 * (uint64_t)Q));
-        if (Q > 0) {
-            SeqOut SO{G->q_index, G->q_read, G->q_start, G->q_end, G->q_rev, G->q_shift};
-            kd_seqlines_kernel<<<nblk(Q), 256, 0, st>>>(A, kmer_off, Q, k, l, seq_g, slot, first, first_rank, loc, rev,
-                                                        0, 0, SO);
+    slot.reset(); first.reset(); iota.reset(); sslot.reset();
+    MDBG_CK(c, first_ord.get(c->pool, D)); MDBG_CK(c, solid.get(c->pool, D)); MDBG_CK(c, nseq.get(c->pool, (uint64_t)D + 1));
+    MDBG_CK(c, seq_off.get(c->pool, (uint64_t)D + 1)); MDBG_CK(c, seg_index.get(c->pool, D)); MDBG_CK(c, solid_seg.get(c->pool, D));
+    Tmp<uint64_t> first_sorted;
+    MDBG_CK(c, first_sorted.get(c->pool, D));
+    if (D > 0) {
+        kd_segments_kernel<<<nblk(D), 256, 0, st>>>(seg_start, D, K, sj, r_ord, minab, first_ord, solid, nseq);
+        LAUNCHED(c);
+        RC(R.cub([&](void* t, size_t& b) { return cub::DeviceRadixSort::SortKeys(t, b, first_ord.p, first_sorted.p, D, 0, 63, st); }));
+        RC(R.cub([&](void* t, size_t& b) {
+            return cub::DeviceSelect::Flagged(t, b, cub::CountingInputIterator<uint32_t>(0), solid.p, solid_seg.p,
+                                              (uint32_t*)&c->d_sc->v[3], D, st);
+        }));
+        MDBG_CK(c, cudaMemsetAsync(nseq.p + D, 0, 4, st));
+        RC(R.cub([&](void* t, size_t& b) { return cub::DeviceScan::ExclusiveSum(t, b, nseq.p, seq_off.p, D + 1, st); }));
+        MDBG_CK(c, cudaMemcpyAsync(&c->h_sc->v[4], seq_off.p + D, 4, cudaMemcpyDeviceToHost, st));
+        RC(read_scalars(c));
+        S_local = (uint32_t)(c->h_sc->v[3] & 0xFFFFFFFFu);
+        Q_local = (uint32_t)(c->h_sc->v[4] & 0xFFFFFFFFu);
+    }
+    // node index: first sightings of every GPU, sorted per GPU
+    std::vector<uint64_t> allD;
+    { uint64_t mine[3] = {D, S_local, Q_local}; RC(allgather_u64(c, mine, 3, allD)); }
+    std::vector<uint64_t> dcnt(W), scnt(W), qcnt(W), loff(W + 1, 0);
+    uint64_t Dtot = 0, Stot = 0, Qtot = 0;
+    for (int r = 0; r < W; r++) {
+        dcnt[r] = allD[3 * r]; scnt[r] = allD[3 * r + 1]; qcnt[r] = allD[3 * r + 2];
+        Dtot += dcnt[r]; Stot += scnt[r]; Qtot += qcnt[r];
+        loff[r + 1] = loff[r] + dcnt[r];
+    }
+    if (Dtot >= 0xFFFFFFF0ull) { c->err = "more than 2^32 distinct k-min-mers"; return MDBG_ERR_RANGE; }
+    G->n_distinct = Dtot; G->n_nodes = Stot; G->n_seqlines = want_seqlines ? Qtot : 0;
+    {
+        Tmp<uint64_t> all_first, d_loff;
+        MDBG_CK(c, all_first.get(c->pool, Dtot)); MDBG_CK(c, d_loff.get(c->pool, W + 1));
+        RC(allgatherv(c, first_sorted, D, dcnt, all_first, 8));
+        MDBG_CK(c, cudaMemcpyAsync(d_loff, loff.data(), (W + 1) * 8, cudaMemcpyHostToDevice, st));
+        if (D > 0) {
+            kd_index_kernel<<<nblk(D), 256, 0, st>>>(first_ord, D, all_first, d_loff, (uint32_t)W, seg_index);
             LAUNCHED(c);
+        }
+        MDBG_CK(c, cudaStreamSynchronize(st));   // loff / temporaries go out of scope
+    }
+    first_sorted.reset(); first_ord.reset(); solid.reset();
+
+    // solid nodes of this owner -> all GPUs, ascending index
+    MDBG_CK(c, G->index.get(c->pool, Stot)); MDBG_CK(c, G->abundance.get(c->pool, Stot));
+    MDBG_CK(c, G->seqlen.get(c->pool, Stot)); MDBG_CK(c, G->shift.get(c->pool, 2 * Stot));
+    MDBG_CK(c, G->tuple.get(c->pool, Stot * k));
+    if (Stot >= 0x7FFFFFF0ull) { c->err = "more than 2^31 nodes"; return MDBG_ERR_RANGE; }
+    {
+        Tmp<NodeRec> my_nodes, all_nodes;
+        Tmp<uint64_t> my_tuple, all_tuple;
+        MDBG_CK(c, my_nodes.get(c->pool, S_local)); MDBG_CK(c, my_tuple.get(c->pool, (uint64_t)S_local * k));
+        if (S_local > 0) {
+            kd_nodes_kernel<<<nblk(S_local), 256, 0, st>>>(S_local, k, minab, K, D, solid_seg, seg_start, sj, seg_index,
+                                                           r_tuple, r_ord, r_info, my_nodes, my_tuple);
+            LAUNCHED(c);
+        }
+        NodeRec* nodes_all = my_nodes; uint64_t* tuple_all = my_tuple;
+        if (W > 1) {
+            MDBG_CK(c, all_nodes.get(c->pool, Stot)); MDBG_CK(c, all_tuple.get(c->pool, Stot * k));
+            RC(allgatherv(c, my_nodes, S_local, scnt, all_nodes, sizeof(NodeRec)));
+            std::vector<uint64_t> tcnt(W);
+            for (int r = 0; r < W; r++) tcnt[r] = scnt[r] * k;
+            RC(allgatherv(c, my_tuple, (uint64_t)S_local * k, tcnt, all_tuple, 8));
+            nodes_all = all_nodes; tuple_all = all_tuple;
+        }
+        if (Stot > 0) {
+            Tmp<uint32_t> nkey, nkey_s, nid, nid_s;
+            MDBG_CK(c, nkey.get(c->pool, Stot)); MDBG_CK(c, nkey_s.get(c->pool, Stot));
+            MDBG_CK(c, nid.get(c->pool, Stot)); MDBG_CK(c, nid_s.get(c->pool, Stot));
+            kd_node_keys_kernel<<<nblk(Stot), 256, 0, st>>>(nodes_all, (uint32_t)Stot, nkey, nid);
+            LAUNCHED(c);
+            RC(R.cub([&](void* t, size_t& b) {
+                return cub::DeviceRadixSort::SortPairs(t, b, nkey.p, nkey_s.p, nid.p, nid_s.p, (uint32_t)Stot, 0, 32, st);
+            }));
+            kd_unpack_nodes_kernel<<<nblk(Stot), 256, 0, st>>>(nodes_all, nid_s, (uint32_t)Stot, k, tuple_all, G->index,
+                                                               G->abundance, G->seqlen, G->shift, G->tuple);
+            LAUNCHED(c);
+        }
+        MDBG_CK(c, cudaStreamSynchronize(st));
+    }
+    // .sequences lines of this owner, in ordinal (= emission) order
+    G->n_seq_local = 0;
+    if (want_seqlines) {
+        MDBG_CK(c, G->seq.get(c->pool, Q_local));
+        G->n_seq_local = Q_local;
+        if (Q_local > 0) {
+            Tmp<SeqRec> raw;
+            Tmp<uint64_t> qk, qk_s; Tmp<uint32_t> qi, qi_s;
+            MDBG_CK(c, raw.get(c->pool, Q_local));
+            MDBG_CK(c, qk.get(c->pool, Q_local)); MDBG_CK(c, qk_s.get(c->pool, Q_local));
+            MDBG_CK(c, qi.get(c->pool, Q_local)); MDBG_CK(c, qi_s.get(c->pool, Q_local));
+            kd_seqlines_kernel<<<nblk(D), 256, 0, st>>>(D, K, minab, l, seg_start, sj, nseq, seq_off, seg_index, r_ord,
+                                                        r_info, raw);
+            LAUNCHED(c);
+            kd_seq_keys_kernel<<<nblk(Q_local), 256, 0, st>>>(raw, Q_local, qk, qi);
+            LAUNCHED(c);
+            RC(R.cub([&](void* t, size_t& b) { return cub::DeviceRadixSort::SortPairs(t, b, qk.p, qk_s.p, qi.p, qi_s.p, Q_local, 0, 63, st); }));
+            kd_seq_gather_kernel<<<nblk(Q_local), 256, 0, st>>>(raw, qi_s, Q_local, G->seq);
+            LAUNCHED(c);
+            MDBG_CK(c, cudaStreamSynchronize(st));
         }
     }
     MDBG_CK(c, cudaEventRecord(c->ev[8], st));
-    cudaEventElapsedTime(&c->tm.ms_kb, c->ev[5], c->ev[6]);
-    c->tm.ms_kb += ms_kb;
-    c->tm.ms_kc = ms_kc;
     // free table-stage scratch before the edge stage
-    seq_g.reset(); slot.reset(); first.reset(); first_rank.reset(); solid_seg.reset(); seg_first.reset();
-    seg_start.reset(); sg.reset(); loc.reset(); rev.reset(); cnt.reset(); kmer_off.reset();
+    nseq.reset(); seq_off.reset(); seg_index.reset(); solid_seg.reset(); seg_start.reset(); sj.reset();
+    x_tuple.reset(); x_ord.reset(); x_info.reset(); l_tuple.reset(); l_ord.reset(); l_info.reset();
 
-    // ---- K-E: edges -----------------------------------------------------------------------------
-    if (S > 0) {
+    // ---- K-E: edges of this GPU's slice of the nodes ----------------------------------------------
+    uint32_t E = 0;
+    uint64_t rem_local = 0;
+    if (Stot > 0) {
+        const uint32_t S = (uint32_t)Stot;
         NodeView NV{G->index, G->abundance, G->seqlen, G->shift, G->tuple, S, k};
         const uint32_t E2 = 2 * S;
+        uint64_t n_lo, n_hi;
+        mdbg_shard_reads(S, W, rank, &n_lo, &n_hi);
+        const uint32_t q_lo = 2 * (uint32_t)n_lo, q_n = 2 * (uint32_t)(n_hi - n_lo);
         Tmp<uint64_t> ekey, skey; Tmp<uint32_t> eval, sval; Tmp<uint8_t> erev;
-        MDBG_CK(c, ekey.get(c->pool, E2));
-        MDBG_CK(c, skey.get(c->pool, E2));
-        MDBG_CK(c, eval.get(c->pool, E2));
-        MDBG_CK(c, sval.get(c->pool, E2));
-        MDBG_CK(c, erev.get(c->pool, E2));
+        MDBG_CK(c, ekey.get(c->pool, E2)); MDBG_CK(c, skey.get(c->pool, E2));
+        MDBG_CK(c, eval.get(c->pool, E2)); MDBG_CK(c, sval.get(c->pool, E2)); MDBG_CK(c, erev.get(c->pool, E2));
         ke_entries_kernel<<<nblk(E2), 256, 0, st>>>(NV, 0x656467657300ull, ekey, eval, erev);
         LAUNCHED(c);
         RC(R.cub([&](void* t, size_t& b) {
             return cub::DeviceRadixSort::SortPairs(t, b, ekey.p, skey.p, eval.p, sval.p, E2, 0, 64, st);
         }));
         Tmp<uint32_t> cnt_e, cnt_r, off_e, off_r;
-        MDBG_CK(c, cnt_e.get(c->pool, E2 + 1));
-        MDBG_CK(c, cnt_r.get(c->pool, E2 + 1));
-        MDBG_CK(c, off_e.get(c->pool, E2 + 1));
-        MDBG_CK(c, off_r.get(c->pool, E2 + 1));
-        MDBG_CK(c, cudaMemsetAsync(cnt_e.p + E2, 0, 4, st));
-        MDBG_CK(c, cudaMemsetAsync(cnt_r.p + E2, 0, 4, st));
-        ke_join_kernel<false><<<nblk(E2, 128), 128, 0, st>>>(NV, ekey, erev, skey, sval, presimp, cnt_e, cnt_r, nullptr,
-                                                              nullptr, nullptr, nullptr);
-        LAUNCHED(c);
-        RC(R.cub([&](void* t, size_t& b) { return cub::DeviceScan::ExclusiveSum(t, b, cnt_e.p, off_e.p, E2 + 1, st); }));
-        RC(R.cub([&](void* t, size_t& b) { return cub::DeviceScan::ExclusiveSum(t, b, cnt_r.p, off_r.p, E2 + 1, st); }));
-        MDBG_CK(c, cudaMemcpyAsync(&c->h_sc->v[5], off_e.p + E2, 4, cudaMemcpyDeviceToHost, st));
-        MDBG_CK(c, cudaMemcpyAsync(&c->h_sc->v[6], off_r.p + E2, 4, cudaMemcpyDeviceToHost, st));
-        MDBG_CK(c, cudaStreamSynchronize(st));
-        uint32_t EP = (uint32_t)(c->h_sc->v[5] & 0xFFFFFFFFu), NR = (uint32_t)(c->h_sc->v[6] & 0xFFFFFFFFu);
-        G->presimp_removed = presimp > 0.0f ? NR : 0;
+        MDBG_CK(c, cnt_e.get(c->pool, (uint64_t)q_n + 1)); MDBG_CK(c, cnt_r.get(c->pool, (uint64_t)q_n + 1));
+        MDBG_CK(c, off_e.get(c->pool, (uint64_t)q_n + 1)); MDBG_CK(c, off_r.get(c->pool, (uint64_t)q_n + 1));
+        MDBG_CK(c, cudaMemsetAsync(cnt_e.p + q_n, 0, 4, st));
+        MDBG_CK(c, cudaMemsetAsync(cnt_r.p + q_n, 0, 4, st));
+        uint32_t EP = 0, NR = 0;
+        if (q_n > 0) {
+            ke_join_kernel<false><<<nblk(q_n, 128), 128, 0, st>>>(NV, ekey, erev, skey, sval, presimp, q_lo, q_n, cnt_e, cnt_r,
+                                                                  nullptr, nullptr, nullptr, nullptr);
+            LAUNCHED(c);
+            RC(R.cub([&](void* t, size_t& b) { return cub::DeviceScan::ExclusiveSum(t, b, cnt_e.p, off_e.p, q_n + 1, st); }));
+            RC(R.cub([&](void* t, size_t& b) { return cub::DeviceScan::ExclusiveSum(t, b, cnt_r.p, off_r.p, q_n + 1, st); }));
+            MDBG_CK(c, cudaMemcpyAsync(&c->h_sc->v[5], off_e.p + q_n, 4, cudaMemcpyDeviceToHost, st));
+            MDBG_CK(c, cudaMemcpyAsync(&c->h_sc->v[6], off_r.p + q_n, 4, cudaMemcpyDeviceToHost, st));
+            MDBG_CK(c, cudaStreamSynchronize(st));
+            EP = (uint32_t)(c->h_sc->v[5] & 0xFFFFFFFFu);
+            NR = (uint32_t)(c->h_sc->v[6] & 0xFFFFFFFFu);
+        }
+        rem_local = presimp > 0.0f ? NR : 0;
         Tmp<EdgeRec> pend, kept;
         Tmp<uint64_t> removed;
-        MDBG_CK(c, pend.get(c->pool, EP));
-        MDBG_CK(c, removed.get(c->pool, NR));
+        MDBG_CK(c, pend.get(c->pool, EP)); MDBG_CK(c, removed.get(c->pool, NR));
         if (EP > 0 || NR > 0) {
-            ke_join_kernel<true><<<nblk(E2, 128), 128, 0, st>>>(NV, ekey, erev, skey, sval, presimp, nullptr, nullptr, off_e,
-                                                                 off_r, pend, removed);
+            ke_join_kernel<true><<<nblk(q_n, 128), 128, 0, st>>>(NV, ekey, erev, skey, sval, presimp, q_lo, q_n, nullptr, nullptr,
+                                                                 off_e, off_r, pend, removed);
             LAUNCHED(c);
         }
+        // presimp removals of every GPU (an edge is dropped if it or its reverse was removed anywhere)
+        std::vector<uint64_t> allNR;
+        { uint64_t mine[1] = {NR}; RC(allgather_u64(c, mine, 1, allNR)); }
+        uint64_t NRtot = 0;
+        for (int r = 0; r < W; r++) NRtot += allNR[r];
         EdgeRec* edges = pend;
-        uint32_t E = EP;
-        if (NR > 0 && EP > 0) {  // drop (n1,n2) if it or its reverse was presimp-removed (main.rs:1107-1116)
-            Tmp<uint64_t> rem_s;
+        E = EP;
+        if (NRtot > 0) {
+            Tmp<uint64_t> rem_all, rem_s;
             Tmp<uint8_t> keep;
-            MDBG_CK(c, rem_s.get(c->pool, NR));
-            MDBG_CK(c, keep.get(c->pool, EP));
-            MDBG_CK(c, kept.get(c->pool, EP));
-            RC(R.cub([&](void* t, size_t& b) { return cub::DeviceRadixSort::SortKeys(t, b, removed.p, rem_s.p, NR, 0, 64, st); }));
-            ke_filter_kernel<<<nblk(EP), 256, 0, st>>>(pend, EP, rem_s, NR, keep);
-            LAUNCHED(c);
-            RC(R.cub([&](void* t, size_t& b) {
-                return cub::DeviceSelect::Flagged(t, b, pend.p, keep.p, kept.p, (uint32_t*)&c->d_sc->v[7], EP, st);
-            }));
-            RC(read_scalars(c));
-            E = (uint32_t)(c->h_sc->v[7] & 0xFFFFFFFFu);
-            edges = kept;
+            MDBG_CK(c, rem_all.get(c->pool, NRtot)); MDBG_CK(c, rem_s.get(c->pool, NRtot));
+            RC(allgatherv(c, removed, NR, allNR, rem_all, 8));
+            RC(R.cub([&](void* t, size_t& b) { return cub::DeviceRadixSort::SortKeys(t, b, rem_all.p, rem_s.p, (uint32_t)NRtot, 0, 64, st); }));
+            if (EP > 0) {
+                MDBG_CK(c, keep.get(c->pool, EP)); MDBG_CK(c, kept.get(c->pool, EP));
+                ke_filter_kernel<<<nblk(EP), 256, 0, st>>>(pend, EP, rem_s, (uint32_t)NRtot, keep);
+                LAUNCHED(c);
+                RC(R.cub([&](void* t, size_t& b) {
+                    return cub::DeviceSelect::Flagged(t, b, pend.p, keep.p, kept.p, (uint32_t*)&c->d_sc->v[7], EP, st);
+                }));
+                RC(read_scalars(c));
+                E = (uint32_t)(c->h_sc->v[7] & 0xFFFFFFFFu);
+                edges = kept;
+            } else MDBG_CK(c, cudaStreamSynchronize(st));
         }
-        G->n_edges = E;
-        MDBG_CK(c, G->e_n1.get(c->pool, E));
-        MDBG_CK(c, G->e_o1.get(c->pool, E));
-        MDBG_CK(c, G->e_n2.get(c->pool, E));
-        MDBG_CK(c, G->e_o2.get(c->pool, E));
-        MDBG_CK(c, G->e_ov.get(c->pool, E));
+        MDBG_CK(c, G->e_n1.get(c->pool, E)); MDBG_CK(c, G->e_o1.get(c->pool, E)); MDBG_CK(c, G->e_n2.get(c->pool, E));
+        MDBG_CK(c, G->e_o2.get(c->pool, E)); MDBG_CK(c, G->e_ov.get(c->pool, E));
         if (E > 0) {  // canonical order (n1, n2, o1, o2, overlap): two stable radix passes
             Tmp<uint64_t> k_a, k_b; Tmp<uint32_t> id_a, id_b, id_c;
-            MDBG_CK(c, k_a.get(c->pool, E));
-            MDBG_CK(c, k_b.get(c->pool, E));
-            MDBG_CK(c, id_a.get(c->pool, E));
-            MDBG_CK(c, id_b.get(c->pool, E));
-            MDBG_CK(c, id_c.get(c->pool, E));
+            MDBG_CK(c, k_a.get(c->pool, E)); MDBG_CK(c, k_b.get(c->pool, E));
+            MDBG_CK(c, id_a.get(c->pool, E)); MDBG_CK(c, id_b.get(c->pool, E)); MDBG_CK(c, id_c.get(c->pool, E));
             iota_kernel<<<nblk(E), 256, 0, st>>>(id_a, E);
             LAUNCHED(c);
             ke_sortkeys_kernel<<<nblk(E), 256, 0, st>>>(edges, nullptr, E, 0, k_a);
@@ -332,6 +517,15 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
             ke_gather_kernel<<<nblk(E), 256, 0, st>>>(edges, id_c, E, EO);
             LAUNCHED(c);
         }
+        MDBG_CK(c, cudaStreamSynchronize(st));
+    }
+    G->n_edges_local = E;
+    {   // job-wide counters
+        std::vector<uint64_t> all;
+        uint64_t mine[2] = {E, rem_local};
+        RC(allgather_u64(c, mine, 2, all));
+        G->n_edges = 0; G->presimp_removed = 0;
+        for (int r = 0; r < W; r++) { G->n_edges += all[2 * r]; G->presimp_removed += all[2 * r + 1]; }
     }
     MDBG_CK(c, cudaEventRecord(c->ev[9], st));
     return MDBG_OK;
@@ -349,6 +543,8 @@ void fill_counters(mdbg_ctx* c, mdbg_graph* out) {
 
 int finish_timings(mdbg_ctx* c) {
     MDBG_CK(c, cudaStreamSynchronize(c->st));
+    cudaEventElapsedTime(&c->tm.ms_kb, c->ev[5], c->ev[6]);
+    cudaEventElapsedTime(&c->tm.ms_kc, c->ev[6], c->ev[7]);
     cudaEventElapsedTime(&c->tm.ms_kd, c->ev[7], c->ev[8]);
     cudaEventElapsedTime(&c->tm.ms_ke, c->ev[8], c->ev[9]);
     cudaEventElapsedTime(&c->tm.ms_total_finish, c->ev[5], c->ev[9]);
@@ -384,6 +580,8 @@ int mdbg_finish_device(mdbg_ctx* c, mdbg_graph* out) {
     return MDBG_OK;
 }
 
+// Host copy.  With N GPUs every rank gets all nodes; rank 0 additionally gets ALL edges and
+// .sequences lines (gathered over NCCL), the other ranks their own slices.
 int mdbg_finish(mdbg_ctx* c, int want_seqlines, mdbg_graph* out) {
     if (!c || !out) return MDBG_ERR_BAD_ARG;
     MDBG_CK(c, cudaSetDevice(c->device));
@@ -394,25 +592,71 @@ int mdbg_finish(mdbg_ctx* c, int want_seqlines, mdbg_graph* out) {
     DeviceGraph* G = c->dg;
     HostGraph* H = new HostGraph();
     out->_owner = H;
-    const uint64_t S = G->n_nodes, E = G->n_edges, Q = G->n_seqlines, k = G->k;
+    const int W = c->world;
+    const uint64_t S = G->n_nodes, k = G->k;
     MDBG_CK(c, cudaEventRecord(c->ev[13], c->st));
     RC(d2h(c, H->index, G->index.p, S));
     RC(d2h(c, H->abundance, G->abundance.p, S));
     RC(d2h(c, H->seqlen, G->seqlen.p, S));
     RC(d2h(c, H->shift, G->shift.p, 2 * S));
     RC(d2h(c, H->tuple, G->tuple.p, S * k));
-    RC(d2h(c, H->e_n1, G->e_n1.p, E));
-    RC(d2h(c, H->e_o1, G->e_o1.p, E));
-    RC(d2h(c, H->e_n2, G->e_n2.p, E));
-    RC(d2h(c, H->e_o2, G->e_o2.p, E));
-    RC(d2h(c, H->e_ov, G->e_ov.p, E));
+    // edges / seqlines: gather on rank 0
+    uint64_t E = G->n_edges_local, Q = G->n_seq_local;
+    Tmp<uint32_t> g_n1, g_n2, g_ov; Tmp<uint8_t> g_o1, g_o2; Tmp<SeqRec> g_seq, g_seq_s;
+    const uint32_t* p_n1 = G->e_n1; const uint32_t* p_n2 = G->e_n2; const uint32_t* p_ov = G->e_ov;
+    const uint8_t* p_o1 = G->e_o1; const uint8_t* p_o2 = G->e_o2; const SeqRec* p_seq = G->seq;
+    if (W > 1) {
+        std::vector<uint64_t> all;
+        uint64_t mine[2] = {E, Q};
+        RC(allgather_u64(c, mine, 2, all));
+        std::vector<uint64_t> ec(W), qc(W);
+        uint64_t Et = 0, Qt = 0;
+        for (int r = 0; r < W; r++) { ec[r] = all[2 * r]; qc[r] = all[2 * r + 1]; Et += ec[r]; Qt += qc[r]; }
+        uint64_t En = c->rank == 0 ? Et : 0, Qn = c->rank == 0 ? Qt : 0;
+        MDBG_CK(c, g_n1.get(c->pool, En)); MDBG_CK(c, g_n2.get(c->pool, En)); MDBG_CK(c, g_ov.get(c->pool, En));
+        MDBG_CK(c, g_o1.get(c->pool, En)); MDBG_CK(c, g_o2.get(c->pool, En)); MDBG_CK(c, g_seq.get(c->pool, Qn));
+        RC(gatherv_root(c, G->e_n1, E, ec, g_n1, 4)); RC(gatherv_root(c, G->e_n2, E, ec, g_n2, 4));
+        RC(gatherv_root(c, G->e_ov, E, ec, g_ov, 4)); RC(gatherv_root(c, G->e_o1, E, ec, g_o1, 1));
+        RC(gatherv_root(c, G->e_o2, E, ec, g_o2, 1));
+        if (want_seqlines) RC(gatherv_root(c, G->seq, Q, qc, g_seq, sizeof(SeqRec)));
+        MDBG_CK(c, cudaStreamSynchronize(c->st));
+        if (c->rank == 0) {   // slices are contiguous node ranges: the concatenation is already sorted
+            E = Et; p_n1 = g_n1; p_n2 = g_n2; p_ov = g_ov; p_o1 = g_o1; p_o2 = g_o2;
+            if (want_seqlines && Qt > 0) {   // emission order = ordinal order over all owners
+                Runner R{c};
+                Tmp<uint64_t> qk, qk_s; Tmp<uint32_t> qi, qi_s;
+                MDBG_CK(c, qk.get(c->pool, Qt)); MDBG_CK(c, qk_s.get(c->pool, Qt));
+                MDBG_CK(c, qi.get(c->pool, Qt)); MDBG_CK(c, qi_s.get(c->pool, Qt)); MDBG_CK(c, g_seq_s.get(c->pool, Qt));
+                kd_seq_keys_kernel<<<nblk(Qt), 256, 0, c->st>>>(g_seq, (uint32_t)Qt, qk, qi);
+                RC(R.cub([&](void* t, size_t& b) { return cub::DeviceRadixSort::SortPairs(t, b, qk.p, qk_s.p, qi.p, qi_s.p, (uint32_t)Qt, 0, 63, c->st); }));
+                kd_seq_gather_kernel<<<nblk(Qt), 256, 0, c->st>>>(g_seq, qi_s, (uint32_t)Qt, g_seq_s);
+                MDBG_CK(c, cudaGetLastError());
+                MDBG_CK(c, cudaStreamSynchronize(c->st));
+                p_seq = g_seq_s;
+            }
+            Q = Qt;
+        }
+    }
+    RC(d2h(c, H->e_n1, p_n1, E)); RC(d2h(c, H->e_o1, p_o1, E)); RC(d2h(c, H->e_n2, p_n2, E));
+    RC(d2h(c, H->e_o2, p_o2, E)); RC(d2h(c, H->e_ov, p_ov, E));
+    out->n_edges = (W > 1 && c->rank != 0) ? E : out->n_edges;
     if (want_seqlines) {
-        RC(d2h(c, H->q_index, G->q_index.p, Q));
-        RC(d2h(c, H->q_read, G->q_read.p, Q));
-        RC(d2h(c, H->q_start, G->q_start.p, Q));
-        RC(d2h(c, H->q_end, G->q_end.p, Q));
-        RC(d2h(c, H->q_rev, G->q_rev.p, Q));
-        RC(d2h(c, H->q_shift, G->q_shift.p, 2 * Q));
+        Tmp<uint32_t> q_index; Tmp<uint64_t> q_read, q_start, q_end, q_shift; Tmp<uint8_t> q_rev;
+        MDBG_CK(c, q_index.get(c->pool, Q)); MDBG_CK(c, q_read.get(c->pool, Q)); MDBG_CK(c, q_start.get(c->pool, Q));
+        MDBG_CK(c, q_end.get(c->pool, Q)); MDBG_CK(c, q_rev.get(c->pool, Q)); MDBG_CK(c, q_shift.get(c->pool, 2 * Q));
+        if (Q > 0) {
+            Tmp<uint32_t> idn;
+            MDBG_CK(c, idn.get(c->pool, Q));
+            iota_kernel<<<nblk(Q), 256, 0, c->st>>>(idn, (uint32_t)Q);
+            SeqOut SO{q_index, q_read, q_start, q_end, q_rev, q_shift};
+            kd_unpack_seq_kernel<<<nblk(Q), 256, 0, c->st>>>(p_seq, idn, (uint32_t)Q, SO);
+            MDBG_CK(c, cudaGetLastError());
+            MDBG_CK(c, cudaStreamSynchronize(c->st));
+        }
+        RC(d2h(c, H->q_index, q_index.p, Q)); RC(d2h(c, H->q_read, q_read.p, Q)); RC(d2h(c, H->q_start, q_start.p, Q));
+        RC(d2h(c, H->q_end, q_end.p, Q)); RC(d2h(c, H->q_rev, q_rev.p, Q)); RC(d2h(c, H->q_shift, q_shift.p, 2 * Q));
+        MDBG_CK(c, cudaStreamSynchronize(c->st));
+        out->n_seqlines = (W > 1 && c->rank != 0) ? Q : out->n_seqlines;
     }
     MDBG_CK(c, cudaEventRecord(c->ev[14], c->st));
     MDBG_CK(c, cudaStreamSynchronize(c->st));

@@ -59,27 +59,97 @@ __device__ __forceinline__ bool window_reversed(const uint64_t* __restrict__ h, 
     return true;  // palindrome => reversed (kmer_vec.rs:37-38)
 }
 
-// one thread per k-min-mer ordinal g (global (read, i) order)
-__global__ void kb_window_kernel(MinArena A, const uint64_t* __restrict__ kmer_off, uint64_t K, uint32_t k,
-                                 uint64_t seed, uint64_t fp_mask, uint64_t* __restrict__ fp,
-                                 uint32_t* __restrict__ loc, uint8_t* __restrict__ rev,
-                                 uint32_t* __restrict__ iota) {
+// Record of one k-min-mer sighting, as exchanged between GPUs (SoA: tuple / ord / info).
+//   tuple : k u64, canonical orientation
+//   ord   : global ordinal of the sighting (serial (read, i) order over the whole job), bit 63 =
+//           the window was reversed
+//   info  : what add_kminmer needs from the sighting (main.rs:769-778)
+struct RecInfo {
+    uint32_t p0;      // raw position of the first minimizer           (read_offsets.0)
+    uint32_t d01;     // p[i+1] - p[i]
+    uint32_t dlast;   // p[i+k-1] - p[i+k-2]
+    uint32_t span;    // p[i+k-1] - p[i]   (seqlen = span + 2, end = p0 + span + l)
+    uint64_t read;    // global read index
+};
+constexpr uint64_t ORD_REV = 1ull << 63;
+constexpr uint64_t ORD_MASK = ORD_REV - 1;
+
+// one thread per local k-min-mer ordinal g: canonical tuple + fingerprint that decides the owner
+__global__ void kb_records_kernel(MinArena A, const uint64_t* __restrict__ kmer_off, uint64_t K, uint32_t k,
+                                  uint64_t seed, uint64_t ord_base, uint64_t read_base,
+                                  uint64_t* __restrict__ tuple, uint64_t* __restrict__ ord,
+                                  RecInfo* __restrict__ info, uint64_t* __restrict__ fp) {
     uint64_t g = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (g >= K) return;
     uint64_t r = owner_read(kmer_off, A.R, g);
     uint64_t i = g - __ldg(kmer_off + r);
     uint64_t lo = __ldg(A.off + r) + i;
     const uint64_t* h = A.hash + lo;
+    const uint32_t* p = A.pos + lo;
     bool rv = window_reversed(h, k);
     uint64_t f = fp_init(seed, k);
-    if (rv) for (uint32_t j = 0; j < k; j++) f = fp_mix(f, __ldg(h + k - 1 - j));
-    else for (uint32_t j = 0; j < k; j++) f = fp_mix(f, __ldg(h + j));
+    uint64_t* t = tuple + g * k;
+    for (uint32_t j = 0; j < k; j++) {
+        uint64_t v = rv ? __ldg(h + k - 1 - j) : __ldg(h + j);
+        t[j] = v;
+        f = fp_mix(f, v);
+    }
+    fp[g] = f;
+    ord[g] = (ord_base + g) | (rv ? ORD_REV : 0);
+    RecInfo ri;
+    ri.p0 = p[0];
+    ri.d01 = p[1] - p[0];
+    ri.dlast = p[k - 1] - p[k - 2];
+    ri.span = p[k - 1] - p[0];
+    ri.read = read_base + r;
+    info[g] = ri;
+}
+
+// owner rank of a record: range partition on the fingerprint (mdbg_owner_of_fingerprint)
+__global__ void kb_owner_kernel(const uint64_t* __restrict__ fp, uint64_t K, uint32_t world,
+                                uint32_t* __restrict__ owner, uint32_t* __restrict__ iota) {
+    uint64_t g = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (g >= K) return;
+    owner[g] = (uint32_t)__umul64hi(fp[g], (uint64_t)world);
+    iota[g] = (uint32_t)g;
+}
+// owner_sorted is ascending: cnt[w] = #records of owner w (one thread per boundary)
+__global__ void kb_owner_counts_kernel(const uint32_t* __restrict__ owner_sorted, uint64_t K, uint32_t world,
+                                       unsigned long long* __restrict__ start /* [world+1] */) {
+    uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (j > K) return;
+    uint32_t cur = j < K ? owner_sorted[j] : world;
+    uint32_t prev = j > 0 ? owner_sorted[j - 1] : 0;
+    if (j == 0) { for (uint32_t w = 0; w <= cur && w <= world; w++) start[w] = 0; }
+    else for (uint32_t w = prev + 1; w <= cur && w <= world; w++) start[w] = j;
+}
+// gather records into send order
+__global__ void kb_permute_kernel(const uint32_t* __restrict__ perm, uint64_t K, uint32_t k,
+                                  const uint64_t* __restrict__ tuple, const uint64_t* __restrict__ ord,
+                                  const RecInfo* __restrict__ info, uint64_t* __restrict__ tuple_o,
+                                  uint64_t* __restrict__ ord_o, RecInfo* __restrict__ info_o) {
+    uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (j >= K) return;
+    uint32_t g = perm[j];
+    const uint64_t* s = tuple + (uint64_t)g * k;
+    uint64_t* d = tuple_o + j * k;
+    for (uint32_t q = 0; q < k; q++) d[q] = s[q];
+    ord_o[j] = ord[g];
+    info_o[j] = info[g];
+}
+
+// table fingerprint of the (already canonical) received tuples
+__global__ void kc_fp_kernel(const uint64_t* __restrict__ tuple, uint64_t K, uint32_t k, uint64_t seed,
+                             uint64_t fp_mask, uint64_t* __restrict__ fp, uint32_t* __restrict__ iota) {
+    uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (j >= K) return;
+    const uint64_t* t = tuple + j * k;
+    uint64_t f = fp_init(seed, k);
+    for (uint32_t q = 0; q < k; q++) f = fp_mix(f, __ldg(t + q));
     f &= fp_mask;
     if (f == KC_EMPTY) f = KC_EMPTY - 1;
-    fp[g] = f;
-    loc[g] = (uint32_t)lo;
-    rev[g] = rv ? 1 : 0;
-    iota[g] = (uint32_t)g;
+    fp[j] = f;
+    iota[j] = (uint32_t)j;
 }
 
 // export form for mdbg_window (Entry 2): canonical tuple, reversed, shift pair, read_offsets
@@ -144,23 +214,18 @@ __global__ void kc_insert_kernel(const uint64_t* __restrict__ fp, uint64_t K, ui
     }
 }
 
-// exactness: every ordinal must carry the same TUPLE as the first ordinal of its slot
-__global__ void kc_verify_kernel(MinArena A, uint64_t K, uint32_t k, const uint32_t* __restrict__ slot,
-                                 const uint32_t* __restrict__ first, const uint32_t* __restrict__ loc,
-                                 const uint8_t* __restrict__ rev, unsigned long long* collisions) {
-    uint64_t g = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (g >= K) return;
-    uint32_t f = __ldg(first + __ldg(slot + g));
-    if (f == g) return;
-    const uint64_t* a = A.hash + loc[g];
-    const uint64_t* b = A.hash + loc[f];
-    bool ra = rev[g], rb = rev[f];
+// exactness: every record must carry the same TUPLE as the first record of its slot
+__global__ void kc_verify_kernel(const uint64_t* __restrict__ tuple, uint64_t K, uint32_t k,
+                                 const uint32_t* __restrict__ slot, const uint32_t* __restrict__ first,
+                                 unsigned long long* collisions) {
+    uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (j >= K) return;
+    uint32_t f = __ldg(first + __ldg(slot + j));
+    if (f == j) return;
+    const uint64_t* a = tuple + j * k;
+    const uint64_t* b = tuple + (uint64_t)f * k;
     bool same = true;
-    for (uint32_t j = 0; j < k && same; j++) {
-        uint64_t x = ra ? __ldg(a + k - 1 - j) : __ldg(a + j);
-        uint64_t y = rb ? __ldg(b + k - 1 - j) : __ldg(b + j);
-        same = x == y;
-    }
+    for (uint32_t q = 0; q < k && same; q++) same = __ldg(a + q) == __ldg(b + q);
     if (!same) atomicAdd(collisions, 1ull);
 }
 
@@ -171,87 +236,146 @@ __global__ void kd_heads_kernel(const uint32_t* __restrict__ sslot, uint64_t K, 
     head[j] = (j == 0 || sslot[j] != sslot[j - 1]) ? 1 : 0;
 }
 
-// one thread per distinct tuple (segment of the slot-sorted ordinals, ascending ordinal inside)
+// One thread per distinct tuple = segment of the slot-sorted records (ascending ordinal inside,
+// because records arrive in ordinal order and the sort is stable).
+//   first_ord : ordinal of the first sighting (it consumed a node index, main.rs:662)
+//   solid     : abundance(u16) >= minabund (main.rs:922-929)
+//   nseq      : sightings with previous_abundance == minabund-1 (u16 counter): main.rs:680,696
 __global__ void kd_segments_kernel(const uint32_t* __restrict__ seg_start, uint32_t D, uint64_t K,
-                                   const uint32_t* __restrict__ sg, uint32_t minab,
-                                   uint8_t* __restrict__ flag_first, uint8_t* __restrict__ flag_seq,
-                                   uint8_t* __restrict__ solid, uint32_t* __restrict__ seg_first) {
+                                   const uint32_t* __restrict__ sj, const uint64_t* __restrict__ ord,
+                                   uint32_t minab, uint64_t* __restrict__ first_ord,
+                                   uint8_t* __restrict__ solid, uint32_t* __restrict__ nseq) {
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= D) return;
     uint32_t st = seg_start[s];
     uint32_t en = (s + 1 < D) ? seg_start[s + 1] : (uint32_t)K;
     uint32_t cnt = en - st;
-    uint32_t fg = sg[st];
-    seg_first[s] = fg;
-    flag_first[fg] = 1;  // this sighting consumed a node index (main.rs:662)
-    // sightings where previous_abundance == minabund-1 (u16 counter, wraps): main.rs:680,696
-    for (uint32_t q = minab - 1; q < cnt; q += 65536u) flag_seq[sg[st + q]] = 1;
+    first_ord[s] = ord[sj[st]] & ORD_MASK;
     uint32_t ab = cnt & 0xFFFFu;
-    solid[s] = (minab == 1 || ab >= minab) ? 1 : 0;  // main.rs:922-929
+    solid[s] = (minab == 1 || ab >= minab) ? 1 : 0;
+    nseq[s] = cnt >= minab ? 1 + (cnt - minab) / 65536u : 0;
 }
 
-__global__ void kd_node_keys_kernel(const uint32_t* __restrict__ solid_seg, uint32_t S,
-                                    const uint32_t* __restrict__ seg_first,
-                                    const uint32_t* __restrict__ first_rank, uint32_t* __restrict__ key) {
-    uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= S) return;
-    key[n] = first_rank[seg_first[solid_seg[n]]];
+// node index = number of distinct tuples (on any GPU) first seen earlier: sum over the W sorted
+// first-sighting lists of lower_bound(first_ord)
+__global__ void kd_index_kernel(const uint64_t* __restrict__ first_ord, uint32_t D,
+                                const uint64_t* __restrict__ all_first, const uint64_t* __restrict__ list_off,
+                                uint32_t world, uint32_t* __restrict__ index) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= D) return;
+    uint64_t x = first_ord[s], acc = 0;
+    for (uint32_t w = 0; w < world; w++) {
+        uint64_t lo = list_off[w], hi = list_off[w + 1];
+        const uint64_t base = lo;
+        while (lo < hi) { uint64_t m = (lo + hi) >> 1; if (__ldg(all_first + m) < x) lo = m + 1; else hi = m; }
+        acc += lo - base;
+    }
+    index[s] = (uint32_t)acc;
 }
 
-struct NodeOut {
-    uint32_t* index; uint16_t* abundance; uint32_t* seqlen; uint16_t* shift; uint64_t* tuple;
-};
+struct NodeRec { uint32_t index, seqlen; uint16_t abundance, shift0, shift1, pad; };
 
-__global__ void kd_nodes_kernel(MinArena A, uint32_t S, uint32_t k, uint32_t minab, uint64_t K, uint32_t D,
-                                const uint32_t* __restrict__ node_key, const uint32_t* __restrict__ node_seg,
-                                const uint32_t* __restrict__ seg_start, const uint32_t* __restrict__ sg,
-                                const uint32_t* __restrict__ loc, const uint8_t* __restrict__ rev,
-                                uint32_t index_base, NodeOut O) {
+// solid nodes of this owner (arbitrary order; sorted by index afterwards)
+__global__ void kd_nodes_kernel(uint32_t S, uint32_t k, uint32_t minab, uint64_t K, uint32_t D,
+                                const uint32_t* __restrict__ solid_seg, const uint32_t* __restrict__ seg_start,
+                                const uint32_t* __restrict__ sj, const uint32_t* __restrict__ seg_index,
+                                const uint64_t* __restrict__ tuple, const uint64_t* __restrict__ ord,
+                                const RecInfo* __restrict__ info, NodeRec* __restrict__ node,
+                                uint64_t* __restrict__ node_tuple) {
     uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= S) return;
-    uint32_t s = node_seg[n];
+    uint32_t s = solid_seg[n];
     uint32_t st = seg_start[s];
     uint32_t en = (s + 1 < D) ? seg_start[s + 1] : (uint32_t)K;
     uint32_t cnt = en - st;
     uint32_t rep_rank = (minab - 1) + 65536u * ((cnt - minab) / 65536u);  // last overwrite, main.rs:680-684
-    uint32_t g = sg[st + rep_rank];
-    uint32_t lo = loc[g];
-    bool rv = rev[g];
-    const uint32_t* p = A.pos + lo;
-    uint32_t a = p[1] - p[0], b = p[k - 1] - p[k - 2];
-    O.index[n] = index_base + node_key[n];
-    O.abundance[n] = (uint16_t)(cnt & 0xFFFFu);
-    O.seqlen[n] = p[k - 1] + 1 - p[0] + 1;                    // read_offsets.2, main.rs:778
-    O.shift[2 * n] = (uint16_t)(rv ? b : a);                  // lowprec_shift, main.rs:675
-    O.shift[2 * n + 1] = (uint16_t)(rv ? a : b);
-    const uint64_t* h = A.hash + lo;
-    for (uint32_t j = 0; j < k; j++) O.tuple[(uint64_t)n * k + j] = rv ? h[k - 1 - j] : h[j];
+    uint32_t j = sj[st + rep_rank];
+    bool rv = (ord[j] & ORD_REV) != 0;
+    RecInfo ri = info[j];
+    NodeRec o;
+    o.index = seg_index[s];
+    o.seqlen = ri.span + 2;                                   // read_offsets.2, main.rs:778
+    o.abundance = (uint16_t)(cnt & 0xFFFFu);
+    o.shift0 = (uint16_t)(rv ? ri.dlast : ri.d01);            // lowprec_shift, main.rs:675
+    o.shift1 = (uint16_t)(rv ? ri.d01 : ri.dlast);
+    o.pad = 0;
+    node[n] = o;
+    const uint64_t* t = tuple + (uint64_t)sj[st] * k;
+    for (uint32_t q = 0; q < k; q++) node_tuple[(uint64_t)n * k + q] = t[q];
 }
 
+struct SeqRec { uint64_t ord; uint32_t index, pad; uint64_t read, start, end, shift0, shift1; };
+
+// .sequences lines of this owner: one thread per segment, seq_off = exclusive scan of nseq
+__global__ void kd_seqlines_kernel(uint32_t D, uint64_t K, uint32_t minab, uint32_t l,
+                                   const uint32_t* __restrict__ seg_start, const uint32_t* __restrict__ sj,
+                                   const uint32_t* __restrict__ nseq, const uint32_t* __restrict__ seq_off,
+                                   const uint32_t* __restrict__ seg_index, const uint64_t* __restrict__ ord,
+                                   const RecInfo* __restrict__ info, SeqRec* __restrict__ out) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= D) return;
+    uint32_t n = nseq[s];
+    uint32_t st = seg_start[s];
+    for (uint32_t t = 0; t < n; t++) {
+        uint32_t j = sj[st + (minab - 1) + 65536u * t];
+        uint64_t o = ord[j];
+        bool rv = (o & ORD_REV) != 0;
+        RecInfo ri = info[j];
+        SeqRec q;
+        q.ord = o;
+        q.index = seg_index[s];
+        q.pad = 0;
+        q.read = ri.read;
+        q.start = ri.p0;
+        q.end = (uint64_t)ri.p0 + ri.span + l;
+        q.shift0 = rv ? ri.dlast : ri.d01;      // untruncated (usize, usize), main.rs:702
+        q.shift1 = rv ? ri.d01 : ri.dlast;
+        out[seq_off[s] + t] = q;
+    }
+}
+
+__global__ void kd_unpack_nodes_kernel(const NodeRec* __restrict__ rec, const uint32_t* __restrict__ perm, uint32_t S,
+                                       uint32_t k, const uint64_t* __restrict__ tuple_in, uint32_t* __restrict__ index,
+                                       uint16_t* __restrict__ abundance, uint32_t* __restrict__ seqlen,
+                                       uint16_t* __restrict__ shift, uint64_t* __restrict__ tuple_out) {
+    uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= S) return;
+    uint32_t src = perm[n];
+    NodeRec r = rec[src];
+    index[n] = r.index; abundance[n] = r.abundance; seqlen[n] = r.seqlen;
+    shift[2 * n] = r.shift0; shift[2 * n + 1] = r.shift1;
+    for (uint32_t q = 0; q < k; q++) tuple_out[(uint64_t)n * k + q] = tuple_in[(uint64_t)src * k + q];
+}
+__global__ void kd_node_keys_kernel(const NodeRec* __restrict__ rec, uint32_t S, uint32_t* __restrict__ key,
+                                    uint32_t* __restrict__ iota) {
+    uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= S) return;
+    key[n] = rec[n].index;
+    iota[n] = n;
+}
+__global__ void kd_seq_keys_kernel(const SeqRec* __restrict__ rec, uint32_t Q, uint64_t* __restrict__ key,
+                                   uint32_t* __restrict__ iota) {
+    uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= Q) return;
+    key[n] = rec[n].ord & ORD_MASK;
+    iota[n] = n;
+}
+__global__ void kd_seq_gather_kernel(const SeqRec* __restrict__ in, const uint32_t* __restrict__ perm, uint32_t n,
+                                     SeqRec* __restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[perm[i]];
+}
 struct SeqOut {
     uint32_t* index; uint64_t* read; uint64_t* start; uint64_t* end; uint8_t* reversed; uint64_t* shift;
 };
-
-__global__ void kd_seqlines_kernel(MinArena A, const uint64_t* __restrict__ kmer_off, uint32_t Q, uint32_t k,
-                                   uint32_t l, const uint32_t* __restrict__ seq_g,
-                                   const uint32_t* __restrict__ slot, const uint32_t* __restrict__ first,
-                                   const uint32_t* __restrict__ first_rank, const uint32_t* __restrict__ loc,
-                                   const uint8_t* __restrict__ rev, uint32_t index_base, uint64_t read_base,
-                                   SeqOut O) {
-    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= Q) return;
-    uint32_t g = seq_g[q];
-    uint32_t lo = loc[g];
-    bool rv = rev[g];
-    const uint32_t* p = A.pos + lo;
-    uint64_t a = (uint64_t)p[1] - p[0], b = (uint64_t)p[k - 1] - p[k - 2];
-    O.index[q] = index_base + first_rank[first[slot[g]]];
-    O.read[q] = read_base + owner_read(kmer_off, A.R, g);
-    O.start[q] = p[0];
-    O.end[q] = (uint64_t)p[k - 1] + l;
-    O.reversed[q] = rv ? 1 : 0;
-    O.shift[2 * q] = rv ? b : a;
-    O.shift[2 * q + 1] = rv ? a : b;
+__global__ void kd_unpack_seq_kernel(const SeqRec* __restrict__ rec, const uint32_t* __restrict__ perm, uint32_t Q,
+                                     SeqOut O) {
+    uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= Q) return;
+    SeqRec r = rec[perm[n]];
+    O.index[n] = r.index; O.read[n] = r.read; O.start[n] = r.start; O.end[n] = r.end;
+    O.reversed[n] = (r.ord & ORD_REV) ? 1 : 0;
+    O.shift[2 * n] = r.shift0; O.shift[2 * n + 1] = r.shift1;
 }
 
 // ---- K-E ---------------------------------------------------------------------------------------
@@ -293,12 +417,15 @@ __device__ __forceinline__ bool eq_range(const uint64_t* a, int sa, const uint64
 template <bool WRITE>
 __global__ void ke_join_kernel(NodeView N, const uint64_t* __restrict__ ekey, const uint8_t* __restrict__ erev,
                                const uint64_t* __restrict__ skey, const uint32_t* __restrict__ sval,
-                               float presimp, uint32_t* __restrict__ cnt_edge, uint32_t* __restrict__ cnt_rem,
+                               float presimp, uint32_t q_lo, uint32_t q_n,
+                               uint32_t* __restrict__ cnt_edge, uint32_t* __restrict__ cnt_rem,
                                const uint32_t* __restrict__ off_edge, const uint32_t* __restrict__ off_rem,
                                EdgeRec* __restrict__ edges, uint64_t* __restrict__ removed) {
-    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    // queries [q_lo, q_lo + q_n) of the 2S (n1, key) pairs: the slice of nodes this GPU emits edges for
+    uint32_t qq = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t S = N.S, k = N.k, k1 = k - 1;
-    if (q >= 2 * S) return;
+    if (qq >= q_n) return;
+    uint32_t q = q_lo + qq;
     uint32_t n1 = q >> 1, which = q & 1;
     uint32_t qe = 2 * n1 + (which == 0 ? 1 : 0);  // which 0: suffix entry, 1: prefix entry
     uint64_t kf = ekey[qe];
@@ -315,7 +442,7 @@ __global__ void ke_join_kernel(NodeView N, const uint64_t* __restrict__ ekey, co
     uint32_t ab1 = N.abundance[n1];
     // pass 0: number of potential edges and max abundance; pass 1: decide each edge
     uint32_t npot = 0, abmax = 0, ne = 0, nr = 0;
-    uint32_t oe = WRITE ? off_edge[q] : 0, orr = WRITE ? off_rem[q] : 0;
+    uint32_t oe = WRITE ? off_edge[qq] : 0, orr = WRITE ? off_rem[qq] : 0;
     for (int pass = 0; pass < 2; pass++) {
         uint32_t abref = abmax < ab1 ? abmax : ab1;
         for (uint32_t e = b0; e < b1; e++) {
@@ -355,7 +482,7 @@ __global__ void ke_join_kernel(NodeView N, const uint64_t* __restrict__ ekey, co
         }
         if (npot == 0) break;
     }
-    if (!WRITE) { cnt_edge[q] = ne; cnt_rem[q] = nr; }
+    if (!WRITE) { cnt_edge[qq] = ne; cnt_rem[qq] = nr; }
 }
 
 // keep[e] = 0 if (n1,n2) or (n2,n1) was presimp-removed (main.rs:1109)

@@ -241,6 +241,9 @@ class Context:
         buf = (ctypes.c_uint8 * 128).from_buffer_copy(bytes(unique_id))
         self._ck(self.L.mdbg_comm_init(self.h, buf, rank, world))
 
+    def set_read_base(self, first_read):
+        self._ck(self.L.mdbg_comm_set_read_base(self.h, first_read))
+
 
 def nccl_unique_id():
     L = ffi.lib()

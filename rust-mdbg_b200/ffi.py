@@ -98,6 +98,7 @@ SYMBOLS = {
     "mdbg_flush_l2": (ctypes.c_int, [vp]),
     "mdbg_nccl_unique_id": (ctypes.c_int, [vp]),
     "mdbg_comm_init": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int]),
+    "mdbg_comm_set_read_base": (ctypes.c_int, [vp, u64]),
     "mdbg_shard_reads": (None, [u64, ctypes.c_int, ctypes.c_int, ctypes.POINTER(u64), ctypes.POINTER(u64)]),
     "mdbg_owner_of_fingerprint": (u32, [u64, ctypes.c_int]),
     "mdbg_tuple_fingerprint": (u64, [vp, u32, u64]),

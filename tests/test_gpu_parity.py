@@ -262,3 +262,19 @@ def test_full_size_properties(mdbg, oracle):
     assert set(g1.e_n1.tolist()) <= idx and set(g1.e_n2.tolist()) <= idx
     for a in ("index", "abundance", "seqlen", "shift", "tuple", "e_n1", "e_n2", "e_o1", "e_o2", "e_ov"):
         assert np.array_equal(getattr(g1, a), getattr(g2, a))
+
+
+def test_multi_gpu_equals_oracle(mdbg):
+    """N-GPU graph (reads sharded by record, NCCL all-to-all by fingerprint range) == oracle.
+    Needs >= 2 GPUs on the box; tests/multi_gpu_check.py is the program run under torchrun."""
+    import subprocess
+    import sys
+    import torch
+    n = min(torch.cuda.device_count(), 4)
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr",
+           "127.0.0.1", "--master-port", "29517", os.path.join(root, "tests", "multi_gpu_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
