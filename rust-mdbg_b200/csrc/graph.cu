@@ -334,8 +334,8 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
         }));
         MDBG_CK(c, cudaMemsetAsync(nseq.p + D, 0, 4, st));
         RC(R.cub([&](void* t, size_t& b) { return cub::DeviceScan::ExclusiveSum(t, b, nseq.p, seq_off.p, D + 1, st); }));
-        MDBG_CK(c, cudaMemcpyAsync(&c->h_sc->v[4], seq_off.p + D, 4, cudaMemcpyDeviceToHost, st));
-        RC(read_scalars(c));
+        MDBG_CK(c, cudaMemcpyAsync(&c->d_sc->v[4], seq_off.p + D, 4, cudaMemcpyDeviceToDevice, st));
+        RC(read_scalars(c));   // v[3] = solid count, v[4] = .sequences lines
         S_local = (uint32_t)(c->h_sc->v[3] & 0xFFFFFFFFu);
         Q_local = (uint32_t)(c->h_sc->v[4] & 0xFFFFFFFFu);
     }
