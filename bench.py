@@ -202,6 +202,7 @@ def main():
         ids = [m.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         ctx.comm_init(ids[0], rank, world)
+        ctx.set_read_base(rank * reads_per_rank)
 
     first = rank * reads_per_rank
     ro, total = synth.plan(first, reads_per_rank)
