@@ -6,11 +6,12 @@
 //   filter(<= hash_bound)+push  src/read.rs:183,196-208
 //
 // Layout.  The batch is ONE byte array (ASCII bases of all reads, concatenated) plus
-// read_off[R+1].  The array is cut into fixed 16 KiB tiles on absolute offsets, so the grid
-// does not depend on read lengths; a persistent CTA (128 threads) claims tiles from an atomic
-// counter.  A tile is staged in shared memory with coalesced 128-bit loads into rows of 128
-// bytes padded to 144 (conflict-free 128-bit reads with one row per thread).  Each thread
-// then walks ITS 128 bytes sequentially, entirely in registers:
+// read_off[R+1].  The array is cut into fixed 4 KiB tiles on absolute offsets, so the grid
+// does not depend on read lengths; every WARP of a persistent CTA claims tiles from an atomic
+// counter and owns a private slice of shared memory, so warps never wait for each other (the
+// only CTA-wide barrier is before the loop).  A tile is staged with coalesced 128-bit loads
+// into rows of 128 bytes padded to 144 (conflict-free 128-bit reads with one row per thread).
+// Each thread then walks ITS 128 bytes sequentially, entirely in registers:
 //   * run start  = byte differs from its predecessor (no compaction pass, no position array:
 //     the raw position of a run IS the loop counter);
 //   * the density test uses the 32-bit rolling filter of mdbg_common.cuh (2 shifts, 2 xors,
@@ -41,35 +42,38 @@ namespace mdbg {
 
 namespace {
 
-constexpr int NT = KA_THREADS;
+constexpr int NT = 32;                 // threads per tile: one warp owns one tile, warps never wait
+constexpr int NWARP = KA_THREADS / 32;  // for each other (no CTA barrier inside the tile loop)
 constexpr int SEG = KA_SEG;
 constexpr int TILE = KA_TILE;
 constexpr int PRE = 128;
 constexpr int HALO = 256;
-constexpr int ROWS = (PRE + TILE + HALO) / 128;  // 131
+constexpr int ROWS = (PRE + TILE + HALO) / 128;  // 35
 constexpr int RSTRIDE = 144;
 constexpr int WIN = ROWS * 128;
-constexpr int QCAP = 1024;
-constexpr int WORDS = TILE / 32;  // 512
+constexpr int QCAP = 256;
+constexpr int WORDS = TILE / 32;  // 128
 
 constexpr uint32_t Q_DROP = 0xFFFFFFFFu;
 constexpr uint32_t Q_VERIFIED = 0x80000000u;
 constexpr uint64_t VALID_BY_CLASS = 0x4E00000047544341ull;  // "ACTG\0\0\0N": the byte a class must equal
 
-struct __align__(16) Smem {
+struct __align__(16) Smem {   // one per warp
     uint8_t raw[ROWS * RSTRIDE];
     uint64_t hq[QCAP];        // exact hash of a verified queue entry
     uint32_t queue[QCAP];     // candidates: window-relative position of the LAST run; after phase B:
                               // tile-relative start position of a verified minimizer, or Q_DROP
     uint32_t bitmap[WORDS];
     uint32_t prefix[WORDS];
-    __align__(128) uint32_t tab[32];   // [0,16): TF, [16,32): bit-reversed TG
-    uint64_t hfw[8], hrc[8];  // ntHash seeds by base class (c>>1)&7: A0 C1 T2 G3 N7
-    uint32_t warp_sum[NT / 32];
     uint32_t qn;
     uint32_t total;
     uint32_t tile;
     unsigned long long base;
+};
+struct __align__(128) CtaSmem {
+    __align__(128) uint32_t tab[32];   // [0,16): TF, [16,32): bit-reversed TG
+    uint64_t hfw[8], hrc[8];           // ntHash seeds by base class (c>>1)&7: A0 C1 T2 G3 N7
+    Smem w[NWARP];
 };
 
 struct Win {  // byte access through the staged window, falling back to global memory
@@ -220,30 +224,32 @@ __global__ void ka_tile_lb_kernel(const uint64_t* __restrict__ read_off, uint64_
 }
 
 template <bool HPC>
-__global__ void __launch_bounds__(NT, 5) ka_minimizers_kernel(const KAArgs A) {
-    __shared__ Smem sm;
-    const int tid = threadIdx.x;
-    const int lane = tid & 31, warp = tid >> 5;
+__global__ void __launch_bounds__(KA_THREADS, 5) ka_minimizers_kernel(const KAArgs A) {
+    __shared__ CtaSmem cs;
+    const int ctid = threadIdx.x;
+    const int tid = ctid & 31, lane = tid;      // position inside the warp's tile
+    Smem& sm = cs.w[ctid >> 5];
     const uint32_t l = A.l;
     const uint64_t bound = A.bound;
-    if (tid < 16) { sm.tab[tid] = A.fc.tab_f[tid]; sm.tab[16 + tid] = A.fc.tab_g[tid]; }
-    if (tid < 8) {
-        sm.hfw[tid] = tid < 4 ? nt_fwd_code(tid) : 0;   // classes 4..7 (illegal bytes and N) hash as 0
-        sm.hrc[tid] = tid < 4 ? nt_rc_code(tid) : 0;
+    if (ctid < 16) { cs.tab[ctid] = A.fc.tab_f[ctid]; cs.tab[16 + ctid] = A.fc.tab_g[ctid]; }
+    if (ctid < 8) {
+        cs.hfw[ctid] = ctid < 4 ? nt_fwd_code(ctid) : 0;   // classes 4..7 (illegal bytes and N) hash as 0
+        cs.hrc[ctid] = ctid < 4 ? nt_rc_code(ctid) : 0;
     }
+    __syncthreads();   // the only CTA-wide barrier: tables are read-only from here on
     const bool use_filter = A.fc.usable && !A.force_dense;
     const uint32_t SH = A.fc.hist_shift, fth = A.fc.f_thresh, gz = A.fc.g_zero;
     const uint8_t* __restrict__ gb = A.bases;
     const int64_t B = (int64_t)A.n_bases;
 
     for (;;) {
-        __syncthreads();  // previous tile fully done with shared memory
+        __syncwarp();  // previous tile fully done with this warp's shared memory
         if (tid == 0) {
             sm.tile = atomicAdd(A.tile_counter, 1u);
             sm.qn = 0;
         }
         for (int i = tid; i < WORDS; i += NT) sm.bitmap[i] = 0;
-        __syncthreads();
+        __syncwarp();
         const uint64_t tile = sm.tile;
         if (tile >= A.n_tiles) break;
         const int64_t t0 = (int64_t)tile * TILE;
@@ -273,9 +279,9 @@ __global__ void __launch_bounds__(NT, 5) ka_minimizers_kernel(const KAArgs A) {
             }
             *reinterpret_cast<uint4*>(sm.raw + (q >> 3) * RSTRIDE + (q & 7) * 16) = v;
         }
-        __syncthreads();
-        Win W{sm.raw, gb, w0, sm.hfw, sm.hrc};
-        const uint32_t tab_s = (uint32_t)__cvta_generic_to_shared(sm.tab);
+        __syncwarp();
+        Win W{sm.raw, gb, w0, cs.hfw, cs.hrc};
+        const uint32_t tab_s = (uint32_t)__cvta_generic_to_shared(cs.tab);
         const uint32_t raw_s = (uint32_t)__cvta_generic_to_shared(sm.raw);
 
         const int64_t a = t0 + (int64_t)tid * SEG;
@@ -321,8 +327,8 @@ __global__ void __launch_bounds__(NT, 5) ka_minimizers_kernel(const KAArgs A) {
             auto run_step = [&](uint32_t code) -> bool {   // hist pre-scaled by 4, G bit-reversed
                 hist = (hist << 2) | (code << 2);
                 uint32_t idx = ((hist >> SH) & 0x30u) | (code << 2);
-                F = (F << 1) ^ sm.tab[idx >> 2];
-                G = (G << 1) ^ sm.tab[16 + (idx >> 2)];
+                F = (F << 1) ^ cs.tab[idx >> 2];
+                G = (G << 1) ^ cs.tab[16 + (idx >> 2)];
                 return F <= fth || (G & gz) == 0;
             };
             // The same step for byte J of a word, hand-scheduled in PTX: every instruction is
@@ -530,13 +536,13 @@ __global__ void __launch_bounds__(NT, 5) ka_minimizers_kernel(const KAArgs A) {
         bool queue_mode = use_filter;
         if (use_filter) for_each_portion(fast_portion, true);
         else for_each_portion(exact_portion, false);
-        __syncthreads();
+        __syncwarp();
         if (use_filter) {
             const uint32_t qn = sm.qn;
             if (qn > QCAP) {  // low-complexity sequence flooded the queue: exact path for the tile
                 queue_mode = false;
                 for (int i = tid; i < WORDS; i += NT) sm.bitmap[i] = 0;
-                __syncthreads();
+                __syncwarp();
                 if (tid == 0) atomicAdd(A.dense_tiles, 1u);
                 for_each_portion(exact_portion, false);
             } else {
@@ -557,7 +563,7 @@ __global__ void __launch_bounds__(NT, 5) ka_minimizers_kernel(const KAArgs A) {
                     int64_t p0;
                     uint64_t h;
                     int rel_p0;
-                    if (verify_fast<HPC>(sm.raw, sm.hfw, sm.hrc, (int)ent, rs - w0, l, rel_p0, h)) {
+                    if (verify_fast<HPC>(sm.raw, cs.hfw, cs.hrc, (int)ent, rs - w0, l, rel_p0, h)) {
                         p0 = w0 + rel_p0;
                         if (p0 < t0 || p0 >= t1) continue;  // owned by another tile
                     } else {
@@ -579,7 +585,7 @@ __global__ void __launch_bounds__(NT, 5) ka_minimizers_kernel(const KAArgs A) {
         } else if (tid == 0) {
             atomicAdd(A.dense_tiles, 1u);
         }
-        __syncthreads();
+        __syncwarp();
 
         // ---- count + block scan of the bitmap -------------------------------------------
         uint32_t wv[4], cnt = 0;
@@ -591,15 +597,7 @@ __global__ void __launch_bounds__(NT, 5) ka_minimizers_kernel(const KAArgs A) {
             uint32_t n = __shfl_up_sync(0xffffffffu, inc, d);
             if (lane >= d) inc += n;
         }
-        if (lane == 31) sm.warp_sum[warp] = inc;
-        __syncthreads();
-        uint32_t woff = 0, total = 0;
-#pragma unroll
-        for (int i = 0; i < NT / 32; i++) {
-            uint32_t s = sm.warp_sum[i];
-            if (i < warp) woff += s;
-            total += s;
-        }
+        const uint32_t woff = 0, total = __shfl_sync(0xffffffffu, inc, 31);
         uint32_t ex = woff + inc - cnt;
 #pragma unroll
         for (int i = 0; i < 4; i++) { sm.prefix[tid * 4 + i] = ex; ex += __popc(wv[i]); }
@@ -613,7 +611,7 @@ __global__ void __launch_bounds__(NT, 5) ka_minimizers_kernel(const KAArgs A) {
             A.tile_cnt[tile] = total;
             A.tile_soff[tile] = sb;
         }
-        __syncthreads();
+        __syncwarp();
         const uint64_t obase = sm.base;
 
         // ---- emit: per-read offsets, then (hash, pos) at the final positions ---------------
@@ -696,8 +694,8 @@ cudaError_t ka_launch(const KAArgs& A, int hpc, int grid, cudaStream_t st, uint6
     if (e != cudaSuccess) return e;
     unsigned nb = (unsigned)((nt + 1 + 255) / 256);
     ka_tile_lb_kernel<<<nb, 256, 0, st>>>(A.read_off, A.n_reads, nt, A.tile_lb);
-    if (hpc) ka_minimizers_kernel<true><<<grid, NT, 0, st>>>(A);
-    else ka_minimizers_kernel<false><<<grid, NT, 0, st>>>(A);
+    if (hpc) ka_minimizers_kernel<true><<<grid, KA_THREADS, 0, st>>>(A);
+    else ka_minimizers_kernel<false><<<grid, KA_THREADS, 0, st>>>(A);
     if (launches) *launches += 2;
     return cudaGetLastError();
 }
@@ -711,8 +709,8 @@ cudaError_t ka_finalize(const KAArgs& A, const uint64_t* tile_excl, cudaStream_t
 
 int ka_max_blocks_per_sm(int hpc) {
     int n = 0;
-    if (hpc) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ka_minimizers_kernel<true>, NT, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ka_minimizers_kernel<false>, NT, 0);
+    if (hpc) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ka_minimizers_kernel<true>, KA_THREADS, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ka_minimizers_kernel<false>, KA_THREADS, 0);
     return n;
 }
 

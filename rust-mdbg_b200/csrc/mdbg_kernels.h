@@ -8,9 +8,9 @@
 namespace mdbg {
 
 // ---- K-A (ka_minimizers.cu) ----------------------------------------------------------------
-constexpr int KA_THREADS = 128;
+constexpr int KA_THREADS = 128;                // CTA size: 4 independent warps
 constexpr int KA_SEG = 128;                    // bytes walked by one thread
-constexpr int KA_TILE = KA_THREADS * KA_SEG;   // 16 KiB of bases per CTA iteration
+constexpr int KA_TILE = 32 * KA_SEG;           // 4 KiB of bases per WARP iteration (one tile per warp)
 
 struct KAArgs {
     const uint8_t* bases;        // concatenated ASCII reads (16-byte aligned)
