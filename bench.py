@@ -274,10 +274,15 @@ def main():
         ctx.d2h(hb_arr, d_bases)     # same bytes as the device copy (generated on the device)
         d2h_bytes = 0
 
+        e2e_parts = {"h2d": 0.0, "push": 0.0, "finish": 0.0, "d2h": 0.0}
+
         def step_e2e():
             ctx.reset()
             ctx.push_reads_ptr(hb, ho, reads_per_rank)
             cg = ctx.finish_raw(want_seqlines=False)
+            tm = ctx.timings()
+            e2e_parts["h2d"] += tm["ms_h2d"]; e2e_parts["push"] += tm["ms_total_push"]
+            e2e_parts["finish"] += tm["ms_total_finish"]; e2e_parts["d2h"] += tm["ms_d2h"]
             nb = cg.n_nodes * (4 + 2 + 4 + 4 + 8 * cg.k) + cg.n_edges * (4 + 1 + 4 + 1 + 4)
             ctx.graph_free(cg)
             return nb
@@ -285,6 +290,8 @@ def main():
         for _ in range(max(1, warmup)):
             step_e2e()
         ctx.sync(); barrier()
+        for k_ in e2e_parts:
+            e2e_parts[k_] = 0.0
         t0 = time.perf_counter()
         for _ in range(steps):
             d2h_bytes = step_e2e()
@@ -293,7 +300,8 @@ def main():
         barrier()
         e2e = {"value": bases_all * steps / (e2e_ms * 1e-3) / 1e9, "unit": "Gbases/s",
                "h2d_bytes_per_step": int(total + 8 * (reads_per_rank + 1)), "d2h_bytes_per_step": int(d2h_bytes),
-               "ms_per_step": e2e_ms / steps, "timing": "host wall clock around K steps, max over ranks"}
+               "ms_per_step": e2e_ms / steps, "timing": "host wall clock around K steps, max over ranks",
+               "stage_ms_per_step": {k_: v_ / steps for k_, v_ in e2e_parts.items()}}
         ctx.host_free_pinned(hb); ctx.host_free_pinned(ho)
 
     # ------------------------------------------------------------------ CPU baseline (rank 0, N=1)

@@ -205,6 +205,7 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
     for (int r = 0; r < W; r++) { if (r < rank) ord_base += allK[2 * r]; Ktot += allK[2 * r]; }
     if (W > 1 && !c->read_base_set) { read_base = 0; for (int r = 0; r < rank; r++) read_base += allK[2 * r + 1]; }
     G->n_kminmers = Ktot;
+    const int ord_bits = std::max(1, log2_ceil(Ktot + 1));   // serial ordinals are < Ktot
 
     Tmp<uint64_t> l_tuple, l_ord, l_fp;
     Tmp<RecInfo> l_info;
@@ -270,7 +271,7 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
     l_fp.reset();
     MDBG_CK(c, cudaEventRecord(c->ev[6], st));
 
-    // ---- K-C table (retry with a new seed on a fingerprint collision) ---------------------------
+    // ---- K-C table + K-D sort by slot (retry with a new seed on a fingerprint collision) ---------
     uint32_t D = 0, S_local = 0, Q_local = 0;
     Tmp<uint32_t> slot, first, iota, sslot, sj, seg_start, seg_index, solid_seg, nseq, seq_off;
     Tmp<uint64_t> first_ord;
@@ -278,9 +279,12 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
     const int cap_bits = std::max(12, log2_ceil(2 * std::max<uint64_t>(K, 1)));
     if (K > 0) {
         Tmp<uint64_t> fp, keys;
+        Tmp<uint8_t> head;
         const uint64_t cap = 1ull << cap_bits;
         MDBG_CK(c, fp.get(c->pool, K)); MDBG_CK(c, iota.get(c->pool, K)); MDBG_CK(c, slot.get(c->pool, K));
         MDBG_CK(c, keys.get(c->pool, cap)); MDBG_CK(c, first.get(c->pool, cap));
+        MDBG_CK(c, sslot.get(c->pool, K)); MDBG_CK(c, sj.get(c->pool, K));
+        MDBG_CK(c, head.get(c->pool, K)); MDBG_CK(c, seg_start.get(c->pool, K + 1));
         for (int attempt = 0;; attempt++) {
             if (attempt >= 8) { c->err = "fingerprint collisions persisted over 8 seeds"; return MDBG_ERR_RANGE; }
             c->tm.table_attempts = attempt + 1;
@@ -296,29 +300,23 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
             LAUNCHED(c);
             kc_verify_kernel<<<nblk(K), 256, 0, st>>>(r_tuple, K, k, slot, first, &c->d_sc->v[1]);
             LAUNCHED(c);
+            // K-D: stable sort by slot, segment heads (speculatively: the collision flag is read
+            // together with the segment count, one host round trip for both)
+            RC(R.cub([&](void* t, size_t& b) {
+                return cub::DeviceRadixSort::SortPairs(t, b, slot.p, sslot.p, iota.p, sj.p, (uint32_t)K, 0, cap_bits, st);
+            }));
+            kd_heads_kernel<<<nblk(K), 256, 0, st>>>(sslot, K, head);
+            LAUNCHED(c);
+            RC(R.cub([&](void* t, size_t& b) {
+                return cub::DeviceSelect::Flagged(t, b, cub::CountingInputIterator<uint32_t>(0), head.p, seg_start.p,
+                                                  (uint32_t*)&c->d_sc->v[2], (uint32_t)K, st);
+            }));
             RC(read_scalars(c));
             if (c->h_sc->v[1] == 0) break;  // every slot holds exactly one tuple
         }
-    }
-    MDBG_CK(c, cudaEventRecord(c->ev[7], st));
-
-    // ---- K-D: stable sort by slot, segments ------------------------------------------------------
-    if (K > 0) {
-        MDBG_CK(c, sslot.get(c->pool, K)); MDBG_CK(c, sj.get(c->pool, K));
-        RC(R.cub([&](void* t, size_t& b) {
-            return cub::DeviceRadixSort::SortPairs(t, b, slot.p, sslot.p, iota.p, sj.p, (uint32_t)K, 0, cap_bits, st);
-        }));
-        Tmp<uint8_t> head;
-        MDBG_CK(c, head.get(c->pool, K)); MDBG_CK(c, seg_start.get(c->pool, K + 1));
-        kd_heads_kernel<<<nblk(K), 256, 0, st>>>(sslot, K, head);
-        LAUNCHED(c);
-        RC(R.cub([&](void* t, size_t& b) {
-            return cub::DeviceSelect::Flagged(t, b, cub::CountingInputIterator<uint32_t>(0), head.p, seg_start.p,
-                                              (uint32_t*)&c->d_sc->v[2], (uint32_t)K, st);
-        }));
-        RC(read_scalars(c));
         D = (uint32_t)(c->h_sc->v[2] & 0xFFFFFFFFu);
     }
+    MDBG_CK(c, cudaEventRecord(c->ev[7], st));   // ms_kc = table + sort by slot, ms_kd = reduce + nodes
     slot.reset(); first.reset(); iota.reset(); sslot.reset();
     MDBG_CK(c, first_ord.get(c->pool, D)); MDBG_CK(c, solid.get(c->pool, D)); MDBG_CK(c, nseq.get(c->pool, (uint64_t)D + 1));
     MDBG_CK(c, seq_off.get(c->pool, (uint64_t)D + 1)); MDBG_CK(c, seg_index.get(c->pool, D)); MDBG_CK(c, solid_seg.get(c->pool, D));
@@ -327,7 +325,7 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
     if (D > 0) {
         kd_segments_kernel<<<nblk(D), 256, 0, st>>>(seg_start, D, K, sj, r_ord, minab, first_ord, solid, nseq);
         LAUNCHED(c);
-        RC(R.cub([&](void* t, size_t& b) { return cub::DeviceRadixSort::SortKeys(t, b, first_ord.p, first_sorted.p, D, 0, 63, st); }));
+        RC(R.cub([&](void* t, size_t& b) { return cub::DeviceRadixSort::SortKeys(t, b, first_ord.p, first_sorted.p, D, 0, ord_bits, st); }));
         RC(R.cub([&](void* t, size_t& b) {
             return cub::DeviceSelect::Flagged(t, b, cub::CountingInputIterator<uint32_t>(0), solid.p, solid_seg.p,
                                               (uint32_t*)&c->d_sc->v[3], D, st);
@@ -350,6 +348,7 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
         loff[r + 1] = loff[r] + dcnt[r];
     }
     if (Dtot >= 0xFFFFFFF0ull) { c->err = "more than 2^32 distinct k-min-mers"; return MDBG_ERR_RANGE; }
+    const int idx_bits = std::max(1, log2_ceil(Dtot + 1));   // node indices are < Dtot
     G->n_distinct = Dtot; G->n_nodes = Stot; G->n_seqlines = want_seqlines ? Qtot : 0;
     {
         Tmp<uint64_t> all_first, d_loff;
@@ -360,7 +359,6 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
             kd_index_kernel<<<nblk(D), 256, 0, st>>>(first_ord, D, all_first, d_loff, (uint32_t)W, seg_index);
             LAUNCHED(c);
         }
-        MDBG_CK(c, cudaStreamSynchronize(st));   // loff / temporaries go out of scope
     }
     first_sorted.reset(); first_ord.reset(); solid.reset();
 
@@ -394,13 +392,12 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
             kd_node_keys_kernel<<<nblk(Stot), 256, 0, st>>>(nodes_all, (uint32_t)Stot, nkey, nid);
             LAUNCHED(c);
             RC(R.cub([&](void* t, size_t& b) {
-                return cub::DeviceRadixSort::SortPairs(t, b, nkey.p, nkey_s.p, nid.p, nid_s.p, (uint32_t)Stot, 0, 32, st);
+                return cub::DeviceRadixSort::SortPairs(t, b, nkey.p, nkey_s.p, nid.p, nid_s.p, (uint32_t)Stot, 0, idx_bits, st);
             }));
             kd_unpack_nodes_kernel<<<nblk(Stot), 256, 0, st>>>(nodes_all, nid_s, (uint32_t)Stot, k, tuple_all, G->index,
                                                                G->abundance, G->seqlen, G->shift, G->tuple);
             LAUNCHED(c);
         }
-        MDBG_CK(c, cudaStreamSynchronize(st));
     }
     // .sequences lines of this owner, in ordinal (= emission) order
     G->n_seq_local = 0;
@@ -418,10 +415,9 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
             LAUNCHED(c);
             kd_seq_keys_kernel<<<nblk(Q_local), 256, 0, st>>>(raw, Q_local, qk, qi);
             LAUNCHED(c);
-            RC(R.cub([&](void* t, size_t& b) { return cub::DeviceRadixSort::SortPairs(t, b, qk.p, qk_s.p, qi.p, qi_s.p, Q_local, 0, 63, st); }));
+            RC(R.cub([&](void* t, size_t& b) { return cub::DeviceRadixSort::SortPairs(t, b, qk.p, qk_s.p, qi.p, qi_s.p, Q_local, 0, ord_bits, st); }));
             kd_seq_gather_kernel<<<nblk(Q_local), 256, 0, st>>>(raw, qi_s, Q_local, G->seq);
             LAUNCHED(c);
-            MDBG_CK(c, cudaStreamSynchronize(st));
         }
     }
     MDBG_CK(c, cudaEventRecord(c->ev[8], st));
@@ -445,7 +441,7 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
         ke_entries_kernel<<<nblk(E2), 256, 0, st>>>(NV, 0x656467657300ull, ekey, eval, erev);
         LAUNCHED(c);
         RC(R.cub([&](void* t, size_t& b) {
-            return cub::DeviceRadixSort::SortPairs(t, b, ekey.p, skey.p, eval.p, sval.p, E2, 0, 64, st);
+            return cub::DeviceRadixSort::SortPairs(t, b, ekey.p, skey.p, eval.p, sval.p, E2, 0, 32, st);
         }));
         Tmp<uint32_t> cnt_e, cnt_r, off_e, off_r;
         MDBG_CK(c, cnt_e.get(c->pool, (uint64_t)q_n + 1)); MDBG_CK(c, cnt_r.get(c->pool, (uint64_t)q_n + 1));
@@ -497,7 +493,7 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
                 RC(read_scalars(c));
                 E = (uint32_t)(c->h_sc->v[7] & 0xFFFFFFFFu);
                 edges = kept;
-            } else MDBG_CK(c, cudaStreamSynchronize(st));
+            }
         }
         MDBG_CK(c, G->e_n1.get(c->pool, E)); MDBG_CK(c, G->e_o1.get(c->pool, E)); MDBG_CK(c, G->e_n2.get(c->pool, E));
         MDBG_CK(c, G->e_o2.get(c->pool, E)); MDBG_CK(c, G->e_ov.get(c->pool, E));
@@ -507,17 +503,16 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
             MDBG_CK(c, id_a.get(c->pool, E)); MDBG_CK(c, id_b.get(c->pool, E)); MDBG_CK(c, id_c.get(c->pool, E));
             iota_kernel<<<nblk(E), 256, 0, st>>>(id_a, E);
             LAUNCHED(c);
-            ke_sortkeys_kernel<<<nblk(E), 256, 0, st>>>(edges, nullptr, E, 0, k_a);
+            ke_sortkeys_kernel<<<nblk(E), 256, 0, st>>>(edges, nullptr, E, 0, 0, k_a);
             LAUNCHED(c);
             RC(R.cub([&](void* t, size_t& b) { return cub::DeviceRadixSort::SortPairs(t, b, k_a.p, k_b.p, id_a.p, id_b.p, E, 0, 34, st); }));
-            ke_sortkeys_kernel<<<nblk(E), 256, 0, st>>>(edges, id_b, E, 1, k_a);
+            ke_sortkeys_kernel<<<nblk(E), 256, 0, st>>>(edges, id_b, E, 1, idx_bits <= 32 ? idx_bits : 32, k_a);
             LAUNCHED(c);
-            RC(R.cub([&](void* t, size_t& b) { return cub::DeviceRadixSort::SortPairs(t, b, k_a.p, k_b.p, id_b.p, id_c.p, E, 0, 64, st); }));
+            RC(R.cub([&](void* t, size_t& b) { return cub::DeviceRadixSort::SortPairs(t, b, k_a.p, k_b.p, id_b.p, id_c.p, E, 0, 2 * std::min(idx_bits, 32), st); }));
             EdgeOut EO{G->e_n1, G->e_o1, G->e_n2, G->e_o2, G->e_ov};
             ke_gather_kernel<<<nblk(E), 256, 0, st>>>(edges, id_c, E, EO);
             LAUNCHED(c);
         }
-        MDBG_CK(c, cudaStreamSynchronize(st));
     }
     G->n_edges_local = E;
     {   // job-wide counters

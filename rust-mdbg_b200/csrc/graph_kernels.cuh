@@ -398,7 +398,7 @@ __global__ void ke_entries_kernel(NodeView N, uint64_t seed, uint64_t* __restric
     }
     uint64_t f = fp_init(seed, k1);
     for (uint32_t j = 0; j < k1; j++) f = fp_mix(f, rv ? t[k1 - 1 - j] : t[j]);
-    ekey[e] = f;
+    ekey[e] = f >> 32;   // 32-bit bucket key (4 radix passes); equality is decided on the tuples
     eval[e] = e;
     erev[e] = rv ? 1 : 0;
 }
@@ -503,11 +503,11 @@ __global__ void ke_filter_kernel(const EdgeRec* __restrict__ edges, uint32_t E, 
 }
 
 __global__ void ke_sortkeys_kernel(const EdgeRec* __restrict__ edges, const uint32_t* __restrict__ ids, uint32_t E,
-                                   int major, uint64_t* __restrict__ key) {
+                                   int major, int idx_bits, uint64_t* __restrict__ key) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= E) return;
     EdgeRec r = edges[ids ? ids[i] : i];
-    key[i] = major ? (((uint64_t)r.n1 << 32) | r.n2) : (((uint64_t)r.o1 << 33) | ((uint64_t)r.o2 << 32) | r.ov);
+    key[i] = major ? (((uint64_t)r.n1 << idx_bits) | r.n2) : (((uint64_t)r.o1 << 33) | ((uint64_t)r.o2 << 32) | r.ov);
 }
 
 struct EdgeOut { uint32_t* n1; uint8_t* o1; uint32_t* n2; uint8_t* o2; uint32_t* ov; };
