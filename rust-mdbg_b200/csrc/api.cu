@@ -8,6 +8,7 @@
 #include <cstring>
 #include <cub/cub.cuh>
 #include <string>
+#include <vector>
 
 #include "ctx.h"
 
@@ -86,6 +87,7 @@ int mdbg_ctx_create(const mdbg_params* p, mdbg_ctx** out) {
     c->fc = make_filter(p->l, c->bound);
     cudaError_t e = cudaSetDevice(c->device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->st_copy, cudaStreamNonBlocking);
     cudaDeviceProp prop;
     if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, c->device);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_sc, sizeof(Scalars));
@@ -120,6 +122,9 @@ void mdbg_ctx_destroy(mdbg_ctx* c) {
     if (c->h_sc) cudaFreeHost(c->h_sc);
     for (int i = 0; i < 24; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     c->pool.trim();
+    for (auto ev : c->copy_ev) cudaEventDestroy(ev);
+    for (auto& pb : c->pinned_cache) cudaFreeHost(pb.second);
+    if (c->st_copy) cudaStreamDestroy(c->st_copy);
     if (c->st) cudaStreamDestroy(c->st);
     delete c;
 }
@@ -175,8 +180,13 @@ static int ensure_arena(mdbg_ctx* c, uint64_t m_items, uint64_t r_items) {
     return MDBG_OK;
 }
 
-// Run K-A on a device-resident batch, appending to the arena.
-static int run_ka(mdbg_ctx* c, const uint8_t* d_bases, const uint64_t* d_read_off, uint64_t R, uint64_t B) {
+// One launch of K-A covers tiles [prev tile_end, tile_end) and may first wait for an upload event.
+struct KaChunk { uint64_t tile_end; cudaEvent_t wait; };
+
+// Run K-A on a device-resident batch (or on one that is still being uploaded chunk by chunk),
+// appending to the arena.
+static int run_ka(mdbg_ctx* c, const uint8_t* d_bases, const uint64_t* d_read_off, uint64_t R, uint64_t B,
+                  const std::vector<KaChunk>* plan = nullptr) {
     if (((uintptr_t)d_bases & 15) != 0) { c->err = "bases must be 16-byte aligned"; return MDBG_ERR_BAD_ARG; }
     // expected minimizers: ~2.2*density of the HPC positions; start with a generous estimate and
     // re-run the batch once with the exact size if it did not fit.
@@ -219,7 +229,19 @@ static int run_ka(mdbg_ctx* c, const uint8_t* d_bases, const uint64_t* d_read_of
         A.stage_counter = &c->d_sc->stage_counter; A.tile_cnt = tile_cnt; A.tile_soff = tile_soff;
         A.tile_lb = tile_lb; A.n_tiles = n_tiles;
         MDBG_CK(c, cudaEventRecord(c->ev[0], c->st));
-        MDBG_CK(c, ka_launch(A, c->p.hpc, c->ka_grid, c->st, &c->tm.launches_push));
+        MDBG_CK(c, ka_prepare(A, c->st, &c->tm.launches_push));
+        if (plan && attempt == 0) {
+            uint64_t tb = 0;
+            for (const KaChunk& ch : *plan) {
+                if (ch.wait) MDBG_CK(c, cudaStreamWaitEvent(c->st, ch.wait, 0));
+                A.tile_begin = tb; A.tile_end = ch.tile_end;
+                MDBG_CK(c, ka_launch(A, c->p.hpc, c->ka_grid, c->st, &c->tm.launches_push));
+                tb = ch.tile_end;
+            }
+        } else {
+            A.tile_begin = 0; A.tile_end = n_tiles;
+            MDBG_CK(c, ka_launch(A, c->p.hpc, c->ka_grid, c->st, &c->tm.launches_push));
+        }
         MDBG_CK(c, cudaEventRecord(c->ev[16], c->st));
         MDBG_CK(c, cub::DeviceScan::ExclusiveSum(scan_tmp.p, scan_bytes, tile_cnt.p, tile_excl.p, n_tiles, c->st));
         c->tm.launches_push += 2;
@@ -283,10 +305,37 @@ int mdbg_push_reads(mdbg_ctx* c, const uint8_t* bases, const uint64_t* read_off,
     MDBG_CK(c, d_bases.get(c->pool, B + 16));
     MDBG_CK(c, d_off.get(c->pool, n_reads + 1));
     MDBG_CK(c, cudaEventRecord(c->ev[2], c->st));
-    if (B) MDBG_CK(c, cudaMemcpyAsync(d_bases, bases, B, cudaMemcpyHostToDevice, c->st));
     MDBG_CK(c, cudaMemcpyAsync(d_off, read_off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, c->st));
-    MDBG_CK(c, cudaEventRecord(c->ev[4], c->st));
-    int rc = run_ka(c, d_bases, d_off, n_reads, B);
+    // Upload in ~32 MB chunks cut at read starts on a second stream; K-A runs on the tiles whose
+    // bytes have arrived, so the kernel hides behind the PCIe copy (pinned host memory).
+    const uint64_t CH = 32ull << 20;
+    std::vector<KaChunk> plan;
+    const uint64_t n_tiles = std::max<uint64_t>(1, (B + KA_TILE - 1) / KA_TILE);
+    MDBG_CK(c, cudaStreamWaitEvent(c->st_copy, c->ev[2], 0));   // the staging buffer is free again
+    MDBG_CK(c, cudaEventRecord(c->ev[17], c->st_copy));
+    uint64_t b0 = 0;
+    size_t nev = 0;
+    while (b0 < B) {
+        uint64_t target = b0 + CH;
+        uint64_t b1 = B;
+        if (target < B) {   // first read start >= target
+            const uint64_t* it = std::lower_bound(read_off, read_off + n_reads + 1, target);
+            b1 = *it;
+        }
+        MDBG_CK(c, cudaMemcpyAsync(d_bases.p + b0, bases + b0, b1 - b0, cudaMemcpyHostToDevice, c->st_copy));
+        if (nev == c->copy_ev.size()) {
+            cudaEvent_t ev;
+            MDBG_CK(c, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            c->copy_ev.push_back(ev);
+        }
+        MDBG_CK(c, cudaEventRecord(c->copy_ev[nev], c->st_copy));
+        plan.push_back(KaChunk{b1 >= B ? n_tiles : b1 / KA_TILE, c->copy_ev[nev]});
+        nev++;
+        b0 = b1;
+    }
+    if (plan.empty()) plan.push_back(KaChunk{n_tiles, nullptr});
+    MDBG_CK(c, cudaEventRecord(c->ev[4], c->st_copy));
+    int rc = run_ka(c, d_bases, d_off, n_reads, B, &plan);
     if (rc == MDBG_ERR_ALPHABET) {  // turn the batch offset into (read, offset) like SURVEY 5 asks
         uint64_t pos = c->h_sc->err_pos;
         uint64_t r = std::upper_bound(read_off, read_off + n_reads + 1, pos) - read_off - 1;
@@ -295,10 +344,11 @@ int mdbg_push_reads(mdbg_ctx* c, const uint8_t* bases, const uint64_t* read_off,
                  (unsigned long long)(c->R + r), (unsigned long long)(pos - read_off[r]), bases[pos]);
         c->err = buf;
     }
-    if (rc) return rc;
+    if (rc) { cudaStreamSynchronize(c->st_copy); return rc; }
     MDBG_CK(c, cudaEventRecord(c->ev[3], c->st));
     MDBG_CK(c, cudaEventSynchronize(c->ev[3]));
-    cudaEventElapsedTime(&c->tm.ms_h2d, c->ev[2], c->ev[4]);
+    MDBG_CK(c, cudaStreamSynchronize(c->st_copy));
+    cudaEventElapsedTime(&c->tm.ms_h2d, c->ev[17], c->ev[4]);
     cudaEventElapsedTime(&c->tm.ms_total_push, c->ev[2], c->ev[3]);
     return MDBG_OK;
 }

@@ -72,6 +72,9 @@ struct mdbg_ctx {
     mdbg::FilterConsts fc{};
     int device = 0, num_sms = 0, ka_grid = 0;
     cudaStream_t st = nullptr;
+    cudaStream_t st_copy = nullptr;                 // uploads overlapped with K-A
+    std::vector<cudaEvent_t> copy_ev;
+    std::vector<std::pair<size_t, void*>> pinned_cache;   // host blocks of freed graphs
     std::string err;
     mdbg::Pool pool;
     // resident minimizer arena (global read order)

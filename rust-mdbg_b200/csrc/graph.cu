@@ -546,17 +546,39 @@ int finish_timings(mdbg_ctx* c) {
     return MDBG_OK;
 }
 
-struct HostGraph {  // owner of the host arrays handed out through mdbg_graph
-    std::vector<uint32_t> index, seqlen, e_n1, e_n2, e_ov, q_index;
-    std::vector<uint16_t> abundance, shift;
-    std::vector<uint64_t> tuple, q_read, q_start, q_end, q_shift;
-    std::vector<uint8_t> e_o1, e_o2, q_rev;
+// Owner of the host arrays handed out through mdbg_graph: ONE pinned block (so the D2H copies run
+// at PCIe speed), carved into the arrays; blocks of freed graphs are recycled through the context.
+struct HostGraph {
+    mdbg_ctx* c = nullptr;
+    void* block = nullptr;
+    size_t bytes = 0, used = 0;
+    template <class T>
+    T* take(uint64_t n) {
+        used = (used + 63) & ~(size_t)63;
+        T* p = (T*)((char*)block + used);
+        used += n * sizeof(T);
+        return p;
+    }
 };
 
+int host_block(mdbg_ctx* c, HostGraph* H, size_t need) {
+    need = (need + 4095) & ~(size_t)4095;
+    for (size_t i = 0; i < c->pinned_cache.size(); i++) {
+        if (c->pinned_cache[i].first >= need && c->pinned_cache[i].first <= 2 * need + (1u << 20)) {
+            H->block = c->pinned_cache[i].second;
+            H->bytes = c->pinned_cache[i].first;
+            c->pinned_cache.erase(c->pinned_cache.begin() + i);
+            return MDBG_OK;
+        }
+    }
+    MDBG_CK(c, cudaMallocHost(&H->block, need));
+    H->bytes = need;
+    return MDBG_OK;
+}
+
 template <class T>
-int d2h(mdbg_ctx* c, std::vector<T>& v, const T* d, uint64_t n) {
-    v.resize(n);
-    if (n) MDBG_CK(c, cudaMemcpyAsync(v.data(), d, n * sizeof(T), cudaMemcpyDeviceToHost, c->st));
+int d2h(mdbg_ctx* c, T* dst, const T* d, uint64_t n) {
+    if (n) MDBG_CK(c, cudaMemcpyAsync(dst, d, n * sizeof(T), cudaMemcpyDeviceToHost, c->st));
     return MDBG_OK;
 }
 
@@ -586,17 +608,13 @@ int mdbg_finish(mdbg_ctx* c, int want_seqlines, mdbg_graph* out) {
     fill_counters(c, out);
     DeviceGraph* G = c->dg;
     HostGraph* H = new HostGraph();
+    H->c = c;
     out->_owner = H;
     const int W = c->world;
     const uint64_t S = G->n_nodes, k = G->k;
     MDBG_CK(c, cudaEventRecord(c->ev[13], c->st));
-    RC(d2h(c, H->index, G->index.p, S));
-    RC(d2h(c, H->abundance, G->abundance.p, S));
-    RC(d2h(c, H->seqlen, G->seqlen.p, S));
-    RC(d2h(c, H->shift, G->shift.p, 2 * S));
-    RC(d2h(c, H->tuple, G->tuple.p, S * k));
     // edges / seqlines: gather on rank 0
-    uint64_t E = G->n_edges_local, Q = G->n_seq_local;
+    uint64_t E = G->n_edges_local, Q = want_seqlines ? G->n_seq_local : 0;
     Tmp<uint32_t> g_n1, g_n2, g_ov; Tmp<uint8_t> g_o1, g_o2; Tmp<SeqRec> g_seq, g_seq_s;
     const uint32_t* p_n1 = G->e_n1; const uint32_t* p_n2 = G->e_n2; const uint32_t* p_ov = G->e_ov;
     const uint8_t* p_o1 = G->e_o1; const uint8_t* p_o2 = G->e_o2; const SeqRec* p_seq = G->seq;
@@ -614,7 +632,6 @@ int mdbg_finish(mdbg_ctx* c, int want_seqlines, mdbg_graph* out) {
         RC(gatherv_root(c, G->e_ov, E, ec, g_ov, 4)); RC(gatherv_root(c, G->e_o1, E, ec, g_o1, 1));
         RC(gatherv_root(c, G->e_o2, E, ec, g_o2, 1));
         if (want_seqlines) RC(gatherv_root(c, G->seq, Q, qc, g_seq, sizeof(SeqRec)));
-        MDBG_CK(c, cudaStreamSynchronize(c->st));
         if (c->rank == 0) {   // slices are contiguous node ranges: the concatenation is already sorted
             E = Et; p_n1 = g_n1; p_n2 = g_n2; p_ov = g_ov; p_o1 = g_o1; p_o2 = g_o2;
             if (want_seqlines && Qt > 0) {   // emission order = ordinal order over all owners
@@ -626,17 +643,13 @@ int mdbg_finish(mdbg_ctx* c, int want_seqlines, mdbg_graph* out) {
                 RC(R.cub([&](void* t, size_t& b) { return cub::DeviceRadixSort::SortPairs(t, b, qk.p, qk_s.p, qi.p, qi_s.p, (uint32_t)Qt, 0, 63, c->st); }));
                 kd_seq_gather_kernel<<<nblk(Qt), 256, 0, c->st>>>(g_seq, qi_s, (uint32_t)Qt, g_seq_s);
                 MDBG_CK(c, cudaGetLastError());
-                MDBG_CK(c, cudaStreamSynchronize(c->st));
                 p_seq = g_seq_s;
             }
             Q = Qt;
         }
     }
-    RC(d2h(c, H->e_n1, p_n1, E)); RC(d2h(c, H->e_o1, p_o1, E)); RC(d2h(c, H->e_n2, p_n2, E));
-    RC(d2h(c, H->e_o2, p_o2, E)); RC(d2h(c, H->e_ov, p_ov, E));
-    out->n_edges = (W > 1 && c->rank != 0) ? E : out->n_edges;
+    Tmp<uint32_t> q_index; Tmp<uint64_t> q_read, q_start, q_end, q_shift; Tmp<uint8_t> q_rev;
     if (want_seqlines) {
-        Tmp<uint32_t> q_index; Tmp<uint64_t> q_read, q_start, q_end, q_shift; Tmp<uint8_t> q_rev;
         MDBG_CK(c, q_index.get(c->pool, Q)); MDBG_CK(c, q_read.get(c->pool, Q)); MDBG_CK(c, q_start.get(c->pool, Q));
         MDBG_CK(c, q_end.get(c->pool, Q)); MDBG_CK(c, q_rev.get(c->pool, Q)); MDBG_CK(c, q_shift.get(c->pool, 2 * Q));
         if (Q > 0) {
@@ -646,30 +659,44 @@ int mdbg_finish(mdbg_ctx* c, int want_seqlines, mdbg_graph* out) {
             SeqOut SO{q_index, q_read, q_start, q_end, q_rev, q_shift};
             kd_unpack_seq_kernel<<<nblk(Q), 256, 0, c->st>>>(p_seq, idn, (uint32_t)Q, SO);
             MDBG_CK(c, cudaGetLastError());
-            MDBG_CK(c, cudaStreamSynchronize(c->st));
         }
-        RC(d2h(c, H->q_index, q_index.p, Q)); RC(d2h(c, H->q_read, q_read.p, Q)); RC(d2h(c, H->q_start, q_start.p, Q));
-        RC(d2h(c, H->q_end, q_end.p, Q)); RC(d2h(c, H->q_rev, q_rev.p, Q)); RC(d2h(c, H->q_shift, q_shift.p, 2 * Q));
-        MDBG_CK(c, cudaStreamSynchronize(c->st));
+    }
+    size_t need = S * (4 + 2 + 4 + 4 + 8 * k) + E * 14 + Q * (4 + 8 * 3 + 1 + 16) + 64 * 20;
+    RC(host_block(c, H, need));
+    out->node_index = H->take<uint32_t>(S); out->abundance = H->take<uint16_t>(S); out->seqlen = H->take<uint32_t>(S);
+    out->shift = H->take<uint16_t>(2 * S); out->tuple = H->take<uint64_t>(S * k);
+    out->e_n1 = H->take<uint32_t>(E); out->e_o1 = H->take<uint8_t>(E); out->e_n2 = H->take<uint32_t>(E);
+    out->e_o2 = H->take<uint8_t>(E); out->e_overlap = H->take<uint32_t>(E);
+    RC(d2h(c, out->node_index, G->index.p, S)); RC(d2h(c, out->abundance, G->abundance.p, S));
+    RC(d2h(c, out->seqlen, G->seqlen.p, S)); RC(d2h(c, out->shift, G->shift.p, 2 * S));
+    RC(d2h(c, out->tuple, G->tuple.p, S * k));
+    RC(d2h(c, out->e_n1, p_n1, E)); RC(d2h(c, out->e_o1, p_o1, E)); RC(d2h(c, out->e_n2, p_n2, E));
+    RC(d2h(c, out->e_o2, p_o2, E)); RC(d2h(c, out->e_overlap, p_ov, E));
+    out->n_edges = (W > 1 && c->rank != 0) ? E : out->n_edges;
+    if (want_seqlines) {
+        out->q_index = H->take<uint32_t>(Q); out->q_read = H->take<uint64_t>(Q); out->q_start = H->take<uint64_t>(Q);
+        out->q_end = H->take<uint64_t>(Q); out->q_reversed = H->take<uint8_t>(Q); out->q_shift = H->take<uint64_t>(2 * Q);
+        RC(d2h(c, out->q_index, q_index.p, Q)); RC(d2h(c, out->q_read, q_read.p, Q)); RC(d2h(c, out->q_start, q_start.p, Q));
+        RC(d2h(c, out->q_end, q_end.p, Q)); RC(d2h(c, out->q_reversed, q_rev.p, Q)); RC(d2h(c, out->q_shift, q_shift.p, 2 * Q));
         out->n_seqlines = (W > 1 && c->rank != 0) ? Q : out->n_seqlines;
     }
     MDBG_CK(c, cudaEventRecord(c->ev[14], c->st));
     MDBG_CK(c, cudaStreamSynchronize(c->st));
     cudaEventElapsedTime(&c->tm.ms_d2h, c->ev[13], c->ev[14]);
-    out->node_index = H->index.data(); out->abundance = H->abundance.data(); out->seqlen = H->seqlen.data();
-    out->shift = H->shift.data(); out->tuple = H->tuple.data();
-    out->e_n1 = H->e_n1.data(); out->e_o1 = H->e_o1.data(); out->e_n2 = H->e_n2.data();
-    out->e_o2 = H->e_o2.data(); out->e_overlap = H->e_ov.data();
-    if (want_seqlines) {
-        out->q_index = H->q_index.data(); out->q_read = H->q_read.data(); out->q_start = H->q_start.data();
-        out->q_end = H->q_end.data(); out->q_reversed = H->q_rev.data(); out->q_shift = H->q_shift.data();
-    }
     return MDBG_OK;
 }
 
+// Graphs must be freed before their context is destroyed (the pinned block returns to its cache).
 void mdbg_graph_free(mdbg_graph* g) {
     if (!g) return;
-    delete (HostGraph*)g->_owner;
+    HostGraph* H = (HostGraph*)g->_owner;
+    if (H) {
+        if (H->block) {
+            if (H->c && H->c->pinned_cache.size() < 8) H->c->pinned_cache.emplace_back(H->bytes, H->block);
+            else cudaFreeHost(H->block);
+        }
+        delete H;
+    }
     memset(g, 0, sizeof(*g));
 }
 

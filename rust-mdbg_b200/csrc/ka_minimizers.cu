@@ -250,8 +250,8 @@ __global__ void __launch_bounds__(KA_THREADS, 5) ka_minimizers_kernel(const KAAr
         }
         for (int i = tid; i < WORDS; i += NT) sm.bitmap[i] = 0;
         __syncwarp();
-        const uint64_t tile = sm.tile;
-        if (tile >= A.n_tiles) break;
+        const uint64_t tile = A.tile_begin + sm.tile;
+        if (tile >= A.tile_end) break;
         const int64_t t0 = (int64_t)tile * TILE;
         const int64_t t1 = (t0 + TILE < B) ? t0 + TILE : B;
         const int64_t w0 = t0 - PRE;
@@ -686,17 +686,26 @@ __global__ void ka_finalize_kernel(const KAArgs A, const uint64_t* __restrict__ 
 }
 
 // ---- host launchers ------------------------------------------------------------------------
-cudaError_t ka_launch(const KAArgs& A, int hpc, int grid, cudaStream_t st, uint64_t* launches) {
+cudaError_t ka_prepare(const KAArgs& A, cudaStream_t st, uint64_t* launches) {
     uint64_t nt = A.n_tiles;
-    cudaError_t e = cudaMemsetAsync(A.tile_counter, 0, sizeof(uint32_t), st);
-    if (e != cudaSuccess) return e;
-    e = cudaMemsetAsync(A.stage_counter, 0, sizeof(unsigned long long), st);
+    cudaError_t e = cudaMemsetAsync(A.stage_counter, 0, sizeof(unsigned long long), st);
     if (e != cudaSuccess) return e;
     unsigned nb = (unsigned)((nt + 1 + 255) / 256);
     ka_tile_lb_kernel<<<nb, 256, 0, st>>>(A.read_off, A.n_reads, nt, A.tile_lb);
-    if (hpc) ka_minimizers_kernel<true><<<grid, KA_THREADS, 0, st>>>(A);
-    else ka_minimizers_kernel<false><<<grid, KA_THREADS, 0, st>>>(A);
-    if (launches) *launches += 2;
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t ka_launch(const KAArgs& A, int hpc, int grid, cudaStream_t st, uint64_t* launches) {
+    if (A.tile_end <= A.tile_begin) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(A.tile_counter, 0, sizeof(uint32_t), st);
+    if (e != cudaSuccess) return e;
+    uint64_t warps = A.tile_end - A.tile_begin;
+    uint64_t need = (warps + NWARP - 1) / NWARP;
+    unsigned g = (unsigned)(need < (uint64_t)grid ? need : (uint64_t)grid);
+    if (hpc) ka_minimizers_kernel<true><<<g, KA_THREADS, 0, st>>>(A);
+    else ka_minimizers_kernel<false><<<g, KA_THREADS, 0, st>>>(A);
+    if (launches) *launches += 1;
     return cudaGetLastError();
 }
 

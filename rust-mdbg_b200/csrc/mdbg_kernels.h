@@ -39,7 +39,10 @@ struct KAArgs {
     uint64_t* tile_lb;           // [n_tiles + 1]
     unsigned int* tile_counter;
     uint64_t n_tiles;
+    uint64_t tile_begin, tile_end;   // tiles handled by this launch (chunked, overlapped uploads)
 };
+// prepare: per-tile read lookup + counters; launch: tiles [A.tile_begin, A.tile_end); finalize: order
+cudaError_t ka_prepare(const KAArgs& A, cudaStream_t st, uint64_t* launches);
 cudaError_t ka_launch(const KAArgs& A, int hpc, int grid, cudaStream_t st, uint64_t* launches);
 cudaError_t ka_finalize(const KAArgs& A, const uint64_t* tile_excl, cudaStream_t st, uint64_t* launches);
 int ka_max_blocks_per_sm(int hpc);
