@@ -9,7 +9,12 @@ CPP := $(wildcard $(CSRC)/*.cpp)
 OBJ := $(CU:.cu=.o) $(CPP:.cpp=.o)
 HDR := $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh include/*.h)
 
-all: $(OUT) oracle
+CLI := rust-mdbg_b200/rust-mdbg
+
+all: $(OUT) $(CLI) oracle
+
+$(CLI): rust-mdbg_b200/cli/rust_mdbg_main.cpp include/mdbg.h $(OUT)
+	g++ -O2 -std=c++17 -Wall -o $@ $< -Lrust-mdbg_b200 -lmdbg_b200 -lz -Wl,-rpath,'$$ORIGIN'
 
 $(CSRC)/%.o: $(CSRC)/%.cu $(HDR)
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $@.ptxas.log || (cat $@.ptxas.log; exit 1)
@@ -24,7 +29,7 @@ oracle:
 	$(MAKE) -C oracle
 
 clean:
-	rm -f $(CSRC)/*.o $(CSRC)/*.log $(OUT)
+	rm -f $(CSRC)/*.o $(CSRC)/*.log $(OUT) $(CLI)
 	$(MAKE) -C oracle clean
 
 .PHONY: all oracle clean

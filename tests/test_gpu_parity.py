@@ -278,3 +278,60 @@ def test_multi_gpu_equals_oracle(mdbg):
            "127.0.0.1", "--master-port", "29517", os.path.join(root, "tests", "multi_gpu_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def _lz4_stored_frame_decode(raw):
+    """Minimal LZ4 frame reader (only what a conforming decoder needs for stored blocks)."""
+    assert raw[:4] == b"\x04\x22\x4d\x18"
+    flg, bd = raw[4], raw[5]
+    assert flg >> 6 == 1 and not (flg & 0x08) and not (flg & 0x04) and not (flg & 0x01)   # v1, no size/checksum/dict
+    import struct
+
+    def xxh32(data, seed=0):
+        P1, P2, P3, P4, P5, M = 2654435761, 2246822519, 3266489917, 668265263, 374761393, 0xFFFFFFFF
+        rot = lambda x, r: ((x << r) | (x >> (32 - r))) & M
+        h = (seed + P5 + len(data)) & M
+        for b in data:
+            h = (rot((h + b * P5) & M, 11) * P1) & M
+        h ^= h >> 15; h = (h * P2) & M; h ^= h >> 13; h = (h * P3) & M; h ^= h >> 16
+        return h
+    assert raw[6] == (xxh32(raw[4:6]) >> 8) & 0xFF, "bad frame header checksum"
+    out, p = bytearray(), 7
+    while True:
+        (sz,) = struct.unpack_from("<I", raw, p); p += 4
+        if sz == 0:
+            break
+        assert sz & 0x80000000, "block is not stored"
+        sz &= 0x7FFFFFFF
+        out += raw[p:p + sz]; p += sz
+    assert p == len(raw)
+    return bytes(out)
+
+
+def test_cli_example_config1(mdbg, oracle, example_reads, tmp_path):
+    """The flag-compatible front end on BASELINE config #1 (README.md:40 of the reference):
+    same stdout counters, sorted .gfa lines and LZ4-framed .sequences lines as the oracle."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "rust-mdbg_b200", "rust-mdbg")
+    prefix = str(tmp_path / "example")
+    r = subprocess.run([exe, os.path.join(root, "tests", "golden", "reads-0.00.fa.gz"), "-k", "7", "--density", "0.0008",
+                        "-l", "10", "--minabund", "2", "--prefix", prefix], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    for line in ("Format: FASTA", "Parsing input sequences...", "Number of reads: 657",
+                 "Number of nodes before abundance filter: 104", "Number of nodes after abundance filter: 104",
+                 "Number of mdBG edges: 206", "Pre-simp = 0.01: 0 edges removed."):
+        assert line in r.stdout, (line, r.stdout)
+    assert "Converted reads to k-min-mers." in r.stderr
+    bases, off, _ = example_reads
+    o = oracle.build_graph(bases, off, 7, 10, 0.0008, 2, 0.01)
+    ogfa, oseq = str(tmp_path / "o.gfa"), str(tmp_path / "o.sequences")
+    o.write_gfa(ogfa); o.write_sequences(oseq)
+    canon = lambda text, skip: sorted(x for x in text.splitlines(True) if not x.startswith(skip))
+    assert canon(open(prefix + ".gfa").read(), "H") == canon(open(ogfa).read(), "H")
+    seq = _lz4_stored_frame_decode(open(prefix + ".0.sequences", "rb").read()).decode()
+    assert seq.startswith("# k = 7\n# l = 10\n# Structure of remaining of the file:\n# [node name]\t[list of minimizers]")
+    assert canon(seq, "#") == canon(open(oseq).read(), "#")
+    # refused modes fail loudly
+    r = subprocess.run([exe, "x.fa", "--syncmers"], capture_output=True, text=True)
+    assert r.returncode != 0 and "outside the reads->mdBG hot path" in r.stderr
