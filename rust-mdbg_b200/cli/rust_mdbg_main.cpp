@@ -85,6 +85,12 @@ std::string rust_f64(double v) {  // Rust `{}` of an f64: shortest representatio
     return s;
 }
 
+std::string rust_f32(float v) {  // Rust `{}` of an f32
+    char b[64];
+    for (int p = 1; p <= 9; p++) { snprintf(b, sizeof b, "%.*g", p, (double)v); if (strtof(b, nullptr) == v) break; }
+    return std::string(b);
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
@@ -211,7 +217,7 @@ int main(int argc, char** argv) {
         mdbg_write_sequences(&g, all_bases.data(), all_off.data(), (prefix + ".0.sequences").c_str(), 1) != MDBG_OK)
         die("Couldn't create file: " + prefix + ".0.sequences");
     printf("Number of mdBG edges: %llu\n", (unsigned long long)g.n_edges);
-    if (ps > 0.0f) printf("Pre-simp = %s: %llu edges removed.\n", rust_f64((double)ps).c_str(), (unsigned long long)g.presimp_removed);
+    if (ps > 0.0f) printf("Pre-simp = %s: %llu edges removed.\n", rust_f32(ps).c_str(), (unsigned long long)g.presimp_removed);
     mdbg_graph_free(&g);
     mdbg_host_free_pinned(pin);
     mdbg_ctx_destroy(ctx);
