@@ -50,7 +50,11 @@ typedef struct {
     int32_t  keep_bases;     /* 1 = keep pushed bases resident (needed for .sequences slices) */
     uint32_t debug_fp_bits;  /* test hook: truncate tuple fingerprints to this many bits on the
                                 first attempt to force the exact-collision path; 0 = off     */
-    uint32_t reserved[7];
+    uint32_t bf;             /* 1 = --bf numbering (main.rs:639-655) with an ideal filter: a tuple
+                                enters the table at its SECOND sighting (index order = second
+                                sightings, "nodes before filter" = tuples seen >= 2 times);
+                                ignored when min_abundance == 1, as in the reference            */
+    uint32_t reserved[6];
 } mdbg_params;
 
 typedef struct mdbg_ctx mdbg_ctx;

@@ -245,6 +245,35 @@ inline void add_kminmer(Map& table, uint32_t& next_index, const orc_params& p, c
     uint16_t previous_abundance;
     uint32_t cur_node_index;
     auto it = table.find(node);
+    const bool use_bf = p.bf && minab > 1;   // main.rs:639
+    if (use_bf) {
+        // main.rs:641-655 with an ideal filter: the first sighting only enters the filter (the
+        // entry below, index -1 = "in the filter, not in dbg_nodes"); the second one inserts the
+        // node with abundance previous_abundance+1 = 2 and consumes an index (main.rs:687-691).
+        if (it == table.end()) {
+            Entry e;
+            e.index = 0xFFFFFFFFu; e.abundance = 0; e.seqlen = 0; e.shift0 = e.shift1 = 0;
+            table.emplace(node, e);
+            return;
+        }
+        Entry& e = it->second;
+        if (e.index == 0xFFFFFFFFu) {
+            previous_abundance = 1;
+            e.index = next_index++;
+            e.abundance = (uint16_t)(previous_abundance + 1);
+            e.seqlen = (uint32_t)off2;
+            e.shift0 = (uint16_t)shift0; e.shift1 = (uint16_t)shift1;
+            cur_node_index = e.index;
+        } else {
+            cur_node_index = e.index;
+            previous_abundance = e.abundance;
+            if (previous_abundance == (uint16_t)(minab - 1)) {
+                e.seqlen = (uint32_t)off2;
+                e.shift0 = (uint16_t)shift0; e.shift1 = (uint16_t)shift1;
+            }
+            e.abundance = (uint16_t)(e.abundance + 1);
+        }
+    } else {
     if (it == table.end()) {  // main.rs:662-670: new key consumes an index, abundance 0
         Entry e;
         e.index = next_index++;
@@ -264,6 +293,7 @@ inline void add_kminmer(Map& table, uint32_t& next_index, const orc_params& p, c
             e.shift1 = (uint16_t)shift1;
         }
         e.abundance = (uint16_t)(e.abundance + 1);  // u16 += 1, wraps in --release
+    }
     }
     if (previous_abundance >= 1 || minab == 1) {          // main.rs:693
         if (previous_abundance == (uint16_t)(minab - 1)) {  // main.rs:696
@@ -463,15 +493,18 @@ orc_graph* orc_build(const uint8_t* bases, const uint64_t* read_off, uint64_t R,
         });
     }
     g->st.n_minimizers = g->mhash.size();
-    g->st.n_distinct = table.size();
     g->st.n_seqlines = g->seqlines.size();
     std::vector<Node> nodes;
     nodes.reserve(table.size());
+    uint64_t in_table = 0;
     for (auto& kv : table) {
+        if (kv.second.index == 0xFFFFFFFFu) continue;   // --bf: seen once, only in the filter
+        in_table++;
         // main.rs:922-929: retain(abundance >= minabund) only when minabund > 1
         if (p.min_abundance > 1 && kv.second.abundance < (uint16_t)p.min_abundance) continue;
         nodes.push_back({kv.first, kv.second});
     }
+    g->st.n_distinct = in_table;
     emit_graph(g, nodes);
     return g;
 }

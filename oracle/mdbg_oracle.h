@@ -47,6 +47,7 @@ typedef struct {
     uint32_t min_abundance; /* DbgAbundance = u16, main.rs:53,101; must be >= 1     */
     float    presimp;       /* f32, main.rs:449                                     */
     int32_t  hpc;           /* 1 = homopolymer-compress (default), 0 = --skiphpc    */
+    int32_t  bf;            /* 1 = --bf with an IDEAL Bloom filter (no false positives): main.rs:639-655 */
 } orc_params;
 
 /* ---- ntHash (crate nthash) --------------------------------------------------- */

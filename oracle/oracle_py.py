@@ -29,7 +29,7 @@ def build(force=False):
 class OrcParams(ctypes.Structure):
     _fields_ = [("k", ctypes.c_uint32), ("l", ctypes.c_uint32), ("density", ctypes.c_double),
                 ("min_abundance", ctypes.c_uint32), ("presimp", ctypes.c_float),
-                ("hpc", ctypes.c_int32)]
+                ("hpc", ctypes.c_int32), ("bf", ctypes.c_int32)]
 
 
 class OrcStats(ctypes.Structure):
@@ -89,8 +89,8 @@ def _buf(b):
     return np.ascontiguousarray(b, dtype=np.uint8)
 
 
-def params(k, l, density, min_abundance=2, presimp=0.01, hpc=True):
-    return OrcParams(k, l, float(density), int(min_abundance), float(presimp), 1 if hpc else 0)
+def params(k, l, density, min_abundance=2, presimp=0.01, hpc=True, bf=False):
+    return OrcParams(k, l, float(density), int(min_abundance), float(presimp), 1 if hpc else 0, 1 if bf else 0)
 
 
 def hash_bound(density):
@@ -215,11 +215,11 @@ class Graph:
 
 
 def build_graph(bases, read_off, k, l, density, min_abundance=2, presimp=0.01, hpc=True,
-                threads=0):
+                threads=0, bf=False):
     """threads == 0: serial-order oracle; threads >= 1: reference thread structure (timing)."""
     b = _buf(bases)
     ro = np.ascontiguousarray(read_off, dtype=np.uint64)
-    p = params(k, l, density, min_abundance, presimp, hpc)
+    p = params(k, l, density, min_abundance, presimp, hpc, bf)
     L = lib()
     if threads:
         h = L.orc_build_mt(b.ctypes.data, ro.ctypes.data, len(ro) - 1, ctypes.byref(p), threads)

@@ -99,7 +99,7 @@ int main(int argc, char** argv) {
     long k = -1, l = -1, minabund = -1, threads = -1;
     double density = -1;
     float presimp = -1;
-    bool skiphpc = false, no_basespace = false;
+    bool skiphpc = false, no_basespace = false, use_bf = false;
     int device = 0;
     auto need = [&](int& i) -> const char* { if (i + 1 >= argc) die(std::string("missing value for ") + argv[i]); return argv[++i]; };
     for (int i = 1; i < argc; i++) {
@@ -115,7 +115,8 @@ int main(int argc, char** argv) {
         else if (a == "--no-basespace") no_basespace = true;
         else if (a == "--debug") {}
         else if (a == "--device") device = atoi(need(i));   // extension: CUDA device ordinal
-        else if (a == "--bf" || a == "--syncmers" || a == "--uhs" || a == "--lcp" || a == "--error-correct" ||
+        else if (a == "--bf") use_bf = true;   // ideal-filter numbering, main.rs:639-655
+        else if (a == "--syncmers" || a == "--uhs" || a == "--lcp" || a == "--error-correct" ||
                  a == "--restart-from-postcor" || a == "--reference" || a == "--read-stats" || a == "--lmer-counts" ||
                  a == "--lmer-counts-min" || a == "--lmer-counts-max" || a == "-n" || a == "-t" || a == "-s" ||
                  a == "--distance" || a == "--correction-threshold")
@@ -167,7 +168,7 @@ int main(int argc, char** argv) {
     mdbg_params P;
     memset(&P, 0, sizeof P);
     P.k = (uint32_t)kk; P.l = (uint32_t)ll; P.density = dd; P.min_abundance = (uint32_t)mab; P.presimp = ps;
-    P.hpc = skiphpc ? 0 : 1; P.device = device;
+    P.hpc = skiphpc ? 0 : 1; P.device = device; P.bf = use_bf ? 1 : 0;
     mdbg_ctx* ctx = nullptr;
     if (mdbg_ctx_create(&P, &ctx) != MDBG_OK) die(mdbg_last_error(nullptr));
 

@@ -171,6 +171,7 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
     c->dg = G;
     const uint32_t k = c->p.k, l = c->p.l, minab = c->p.min_abundance;
     const float presimp = c->p.presimp;
+    const uint32_t bf = (c->p.bf && minab > 1) ? 1 : 0;   // main.rs:639
     const int W = c->world, rank = c->rank;
     G->k = k;
     c->tm.launches_finish = 0;
@@ -322,10 +323,22 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
     MDBG_CK(c, seq_off.get(c->pool, (uint64_t)D + 1)); MDBG_CK(c, seg_index.get(c->pool, D)); MDBG_CK(c, solid_seg.get(c->pool, D));
     Tmp<uint64_t> first_sorted;
     MDBG_CK(c, first_sorted.get(c->pool, D));
+    Tmp<uint8_t> counted;
+    MDBG_CK(c, counted.get(c->pool, D));
+    uint32_t Dc = D;   // tuples that are in the table (all of them without --bf)
     if (D > 0) {
-        kd_segments_kernel<<<nblk(D), 256, 0, st>>>(seg_start, D, K, sj, r_ord, minab, first_ord, solid, nseq);
+        kd_segments_kernel<<<nblk(D), 256, 0, st>>>(seg_start, D, K, sj, r_ord, minab, bf, first_ord, counted, solid, nseq);
         LAUNCHED(c);
-        RC(R.cub([&](void* t, size_t& b) { return cub::DeviceRadixSort::SortKeys(t, b, first_ord.p, first_sorted.p, D, 0, ord_bits, st); }));
+        // sorted list of the index-consuming sightings (uncounted ones carry ORD_MASK and sort last)
+        RC(R.cub([&](void* t, size_t& b) { return cub::DeviceRadixSort::SortKeys(t, b, first_ord.p, first_sorted.p, D, 0, bf ? 63 : ord_bits, st); }));
+        if (bf) {
+            Tmp<uint32_t> cidx;
+            MDBG_CK(c, cidx.get(c->pool, D));
+            RC(R.cub([&](void* t, size_t& b) {
+                return cub::DeviceSelect::Flagged(t, b, cub::CountingInputIterator<uint32_t>(0), counted.p, cidx.p,
+                                                  (uint32_t*)&c->d_sc->v[8], D, st);
+            }));
+        }
         RC(R.cub([&](void* t, size_t& b) {
             return cub::DeviceSelect::Flagged(t, b, cub::CountingInputIterator<uint32_t>(0), solid.p, solid_seg.p,
                                               (uint32_t*)&c->d_sc->v[3], D, st);
@@ -333,13 +346,14 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
         MDBG_CK(c, cudaMemsetAsync(nseq.p + D, 0, 4, st));
         RC(R.cub([&](void* t, size_t& b) { return cub::DeviceScan::ExclusiveSum(t, b, nseq.p, seq_off.p, D + 1, st); }));
         MDBG_CK(c, cudaMemcpyAsync(&c->d_sc->v[4], seq_off.p + D, 4, cudaMemcpyDeviceToDevice, st));
-        RC(read_scalars(c));   // v[3] = solid count, v[4] = .sequences lines
+        RC(read_scalars(c));   // v[3] = solid count, v[4] = .sequences lines, v[8] = tuples in the table (--bf)
+        if (bf) Dc = (uint32_t)(c->h_sc->v[8] & 0xFFFFFFFFu);
         S_local = (uint32_t)(c->h_sc->v[3] & 0xFFFFFFFFu);
         Q_local = (uint32_t)(c->h_sc->v[4] & 0xFFFFFFFFu);
     }
     // node index: first sightings of every GPU, sorted per GPU
     std::vector<uint64_t> allD;
-    { uint64_t mine[3] = {D, S_local, Q_local}; RC(allgather_u64(c, mine, 3, allD)); }
+    { uint64_t mine[3] = {Dc, S_local, Q_local}; RC(allgather_u64(c, mine, 3, allD)); }
     std::vector<uint64_t> dcnt(W), scnt(W), qcnt(W), loff(W + 1, 0);
     uint64_t Dtot = 0, Stot = 0, Qtot = 0;
     for (int r = 0; r < W; r++) {
@@ -353,7 +367,7 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
     {
         Tmp<uint64_t> all_first, d_loff;
         MDBG_CK(c, all_first.get(c->pool, Dtot)); MDBG_CK(c, d_loff.get(c->pool, W + 1));
-        RC(allgatherv(c, first_sorted, D, dcnt, all_first, 8));
+        RC(allgatherv(c, first_sorted, Dc, dcnt, all_first, 8));
         MDBG_CK(c, cudaMemcpyAsync(d_loff, loff.data(), (W + 1) * 8, cudaMemcpyHostToDevice, st));
         if (D > 0) {
             kd_index_kernel<<<nblk(D), 256, 0, st>>>(first_ord, D, all_first, d_loff, (uint32_t)W, seg_index);

@@ -241,16 +241,21 @@ __global__ void kd_heads_kernel(const uint32_t* __restrict__ sslot, uint64_t K, 
 //   first_ord : ordinal of the first sighting (it consumed a node index, main.rs:662)
 //   solid     : abundance(u16) >= minabund (main.rs:922-929)
 //   nseq      : sightings with previous_abundance == minabund-1 (u16 counter): main.rs:680,696
+//   bf (main.rs:639-655, ideal filter): a tuple enters the table at its SECOND sighting, so the
+//   index order is the order of second sightings and tuples seen once are not counted
 __global__ void kd_segments_kernel(const uint32_t* __restrict__ seg_start, uint32_t D, uint64_t K,
                                    const uint32_t* __restrict__ sj, const uint64_t* __restrict__ ord,
-                                   uint32_t minab, uint64_t* __restrict__ first_ord,
-                                   uint8_t* __restrict__ solid, uint32_t* __restrict__ nseq) {
+                                   uint32_t minab, uint32_t bf, uint64_t* __restrict__ first_ord,
+                                   uint8_t* __restrict__ counted, uint8_t* __restrict__ solid,
+                                   uint32_t* __restrict__ nseq) {
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= D) return;
     uint32_t st = seg_start[s];
     uint32_t en = (s + 1 < D) ? seg_start[s + 1] : (uint32_t)K;
     uint32_t cnt = en - st;
-    first_ord[s] = ord[sj[st]] & ORD_MASK;
+    const bool in_table = !bf || cnt >= 2;
+    first_ord[s] = in_table ? (ord[sj[st + (bf ? 1 : 0)]] & ORD_MASK) : ORD_MASK;
+    counted[s] = in_table ? 1 : 0;
     uint32_t ab = cnt & 0xFFFFu;
     solid[s] = (minab == 1 || ab >= minab) ? 1 : 0;
     nseq[s] = cnt >= minab ? 1 + (cnt - minab) / 65536u : 0;

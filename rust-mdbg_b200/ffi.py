@@ -29,7 +29,7 @@ class MdbgError(RuntimeError):
 class CParams(ctypes.Structure):
     _fields_ = [("k", u32), ("l", u32), ("density", ctypes.c_double), ("min_abundance", u32),
                 ("presimp", ctypes.c_float), ("hpc", i32), ("device", i32), ("keep_bases", i32),
-                ("debug_fp_bits", u32), ("reserved", u32 * 7)]
+                ("debug_fp_bits", u32), ("bf", u32), ("reserved", u32 * 6)]
 
 
 class CGraph(ctypes.Structure):

@@ -150,3 +150,68 @@ def test_alphabet_predicate_model():
                 bw = badword(w)
                 for j in range(4):
                     assert (((bw >> (8 * j)) & 0xFF) != 0) == (j == lane and chr(c) not in "ACGT")
+
+
+def _lz4_stored_frame_decode(raw):
+    import struct
+
+    def xxh32(data, seed=0):
+        P1, P2, P3, P5, M = 2654435761, 2246822519, 3266489917, 374761393, 0xFFFFFFFF
+        rot = lambda x, r: ((x << r) | (x >> (32 - r))) & M
+        h = (seed + P5 + len(data)) & M
+        for b in data:
+            h = (rot((h + b * P5) & M, 11) * P1) & M
+        h ^= h >> 15; h = (h * P2) & M; h ^= h >> 13; h = (h * P3) & M; h ^= h >> 16
+        return h
+    assert raw[:4] == b"\x04\x22\x4d\x18" and raw[4] == 0x60 and raw[5] == 0x70
+    assert raw[6] == (xxh32(raw[4:6]) >> 8) & 0xFF
+    out, p = bytearray(), 7
+    while True:
+        (sz,) = struct.unpack_from("<I", raw, p); p += 4
+        if sz == 0:
+            break
+        assert sz & 0x80000000
+        out += raw[p:p + (sz & 0x7FFFFFFF)]; p += sz & 0x7FFFFFFF
+    assert p == len(raw)
+    return bytes(out)
+
+
+def test_file_writers_on_host(mdbg, oracle, example_reads, tmp_path):
+    """mdbg_write_gfa / mdbg_write_sequences are host code: feed them a graph (the oracle's, through
+    the C struct) and compare with the oracle's own canonical text -- .gfa S/L grammar
+    (main.rs:1021,1095), .sequences header + lines (main.rs:625-628,702), LZ4 frame validity."""
+    bases, off, _ = example_reads
+    o = oracle.build_graph(bases, off, 7, 10, 0.0008, 2, 0.01)
+    F = mdbg.ffi
+    cg = F.CGraph()
+    keep = []
+
+    def put(name, arr):
+        a = np.ascontiguousarray(arr)
+        keep.append(a)
+        setattr(cg, name, a.ctypes.data)
+    cg.n_nodes, cg.n_edges, cg.n_seqlines = len(o.index), len(o.e_n1), len(o.q_index)
+    cg.k, cg.l = 7, 10
+    for name, arr in (("node_index", o.index), ("abundance", o.abundance), ("seqlen", o.seqlen), ("shift", o.shift),
+                      ("tuple", o.tuple), ("e_n1", o.e_n1), ("e_o1", o.e_o1), ("e_n2", o.e_n2), ("e_o2", o.e_o2),
+                      ("e_overlap", o.e_ov), ("q_index", o.q_index), ("q_read", o.q_read), ("q_start", o.q_start),
+                      ("q_end", o.q_end), ("q_reversed", o.q_rev), ("q_shift", o.q_shift)):
+        put(name, arr)
+    L = F.lib()
+    gfa, seq, seqz = str(tmp_path / "p.gfa"), str(tmp_path / "p.sequences"), str(tmp_path / "p.lz4.sequences")
+    assert L.mdbg_write_gfa(ctypes.byref(cg), gfa.encode()) == 0
+    assert L.mdbg_write_sequences(ctypes.byref(cg), bases.ctypes.data, off.ctypes.data, seq.encode(), 0) == 0
+    assert L.mdbg_write_sequences(ctypes.byref(cg), bases.ctypes.data, off.ctypes.data, seqz.encode(), 1) == 0
+    ogfa, oseq = str(tmp_path / "o.gfa"), str(tmp_path / "o.sequences")
+    o.write_gfa(ogfa); o.write_sequences(oseq)
+    text = open(gfa).read().splitlines(True)
+    assert text[0] == "H\tVN:Z:1.0\n"
+    n_s = sum(1 for x in text if x.startswith("S"))
+    assert all(x.startswith("S") for x in text[1:1 + n_s]) and all(x.startswith("L") for x in text[1 + n_s:])
+    assert sorted(text[1:]) == sorted(open(ogfa).read().splitlines(True)[1:])
+    plain = open(seq).read()
+    assert plain.startswith("# k = 7\n# l = 10\n# Structure of remaining of the file:\n"
+                            "# [node name]\t[list of minimizers]\t[sequence of node]\t[abundance]\t[origin]\t[shift]\n")
+    body = sorted(x for x in plain.splitlines(True) if not x.startswith("#"))
+    assert body == sorted(open(oseq).read().splitlines(True))
+    assert _lz4_stored_frame_decode(open(seqz, "rb").read()).decode() == plain

@@ -335,3 +335,21 @@ def test_cli_example_config1(mdbg, oracle, example_reads, tmp_path):
     # refused modes fail loudly
     r = subprocess.run([exe, "x.fa", "--syncmers"], capture_output=True, text=True)
     assert r.returncode != 0 and "outside the reads->mdBG hot path" in r.stderr
+
+
+@pytest.mark.parametrize("k,l,d,minab", [(5, 10, 0.01, 2), (8, 10, 0.02, 3), (6, 10, 0.01, 1)])
+def test_graph_bf_numbering(mdbg, oracle, k, l, d, minab):
+    """--bf (main.rs:639-655) with an ideal filter: tuples enter the table at their second
+    sighting; with minabund == 1 the flag is ignored, as in the reference."""
+    rng = np.random.default_rng(4242 + k)
+    seqs = genome_reads(rng, 50000, 250, mean=5000, sd=2000, err=0.004)
+    bases, off = pack_reads(seqs)
+    with mdbg.Context(mdbg.Params(k=k, l=l, density=d, min_abundance=minab, presimp=0.01, bf=True)) as ctx:
+        ctx.push_reads(bases, off)
+        g = ctx.finish()
+    o = oracle.build_graph(bases, off, k, l, d, minab, 0.01, bf=True)
+    plain = oracle.build_graph(bases, off, k, l, d, minab, 0.01)
+    assert o.stats["n_nodes"] == plain.stats["n_nodes"] > 0
+    if minab > 1:
+        assert o.stats["n_distinct"] < plain.stats["n_distinct"]
+    compare_graph(g, o)
