@@ -199,15 +199,10 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
         Kl = c->h_sc->v[0];
     }
     if (Kl >= 0x7FFFFFF0ull) { c->err = "more than 2^31 k-min-mers on one GPU"; return MDBG_ERR_RANGE; }
-    // global ordinal / read bases
-    std::vector<uint64_t> allK;
-    { uint64_t mine[2] = {Kl, c->R}; RC(allgather_u64(c, mine, 2, allK)); }
-    uint64_t ord_base = 0, read_base = c->read_base, Ktot = 0;
-    for (int r = 0; r < W; r++) { if (r < rank) ord_base += allK[2 * r]; Ktot += allK[2 * r]; }
-    if (W > 1 && !c->read_base_set) { read_base = 0; for (int r = 0; r < rank; r++) read_base += allK[2 * r + 1]; }
-    G->n_kminmers = Ktot;
-    const int ord_bits = std::max(1, log2_ceil(Ktot + 1));   // serial ordinals are < Ktot
-
+    // Records are produced with LOCAL ordinals / read indices; with N > 1 the global bases are
+    // added when the records are packed for sending (they come out of the same all-gather as the
+    // exchange counts, one host round trip for both).
+    uint64_t Ktot = Kl;
     Tmp<uint64_t> l_tuple, l_ord, l_fp;
     Tmp<RecInfo> l_info;
     MDBG_CK(c, l_tuple.get(c->pool, Kl * k));
@@ -215,8 +210,12 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
     MDBG_CK(c, l_info.get(c->pool, Kl));
     MDBG_CK(c, l_fp.get(c->pool, Kl));
     if (Kl) {
-        kb_records_kernel<<<nblk(Kl), 256, 0, st>>>(A, kmer_off, Kl, k, 0x6d64626700000000ull, ord_base, read_base,
-                                                    l_tuple, l_ord, l_info, l_fp);
+        Tmp<uint32_t> wloc;
+        MDBG_CK(c, wloc.get(c->pool, Kl));
+        kb_records_kernel<<<nblk(Kl), 256, 0, st>>>(A, kmer_off, Kl, k, 0x6d64626700000000ull, 0,
+                                                    W == 1 ? c->read_base : 0, W > 1 ? 1 : 0, wloc, l_ord, l_info, l_fp);
+        LAUNCHED(c);
+        kb_tuples_kernel<<<nblk(Kl * k), 256, 0, st>>>(c->m_hash, wloc, l_ord, Kl * k, k, l_tuple);
         LAUNCHED(c);
     }
     cnt.reset();
@@ -236,7 +235,6 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
         MDBG_CK(c, iota.get(c->pool, Kl)); MDBG_CK(c, perm.get(c->pool, Kl));
         MDBG_CK(c, s_tuple.get(c->pool, Kl * k)); MDBG_CK(c, s_ord.get(c->pool, Kl)); MDBG_CK(c, s_info.get(c->pool, Kl));
         MDBG_CK(c, d_start.get(c->pool, W + 1));
-        std::vector<uint64_t> send_cnt(W, 0);
         if (Kl) {
             kb_owner_kernel<<<nblk(Kl), 256, 0, st>>>(l_fp, Kl, (uint32_t)W, owner, iota);
             LAUNCHED(c);
@@ -244,31 +242,50 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
                 return cub::DeviceRadixSort::SortPairs(t, b, owner.p, owner_s.p, iota.p, perm.p, (uint32_t)Kl, 0,
                                                        std::max(1, log2_ceil(W)), st);
             }));
-            kb_permute_kernel<<<nblk(Kl), 256, 0, st>>>(perm, Kl, k, l_tuple, l_ord, l_info, s_tuple, s_ord, s_info);
-            LAUNCHED(c);
         }
         kb_owner_counts_kernel<<<nblk(Kl + 1), 256, 0, st>>>(owner_s, Kl, (uint32_t)W, d_start);
         LAUNCHED(c);
         std::vector<unsigned long long> h_start(W + 1);
         MDBG_CK(c, cudaMemcpyAsync(h_start.data(), d_start, (W + 1) * 8, cudaMemcpyDeviceToHost, st));
         MDBG_CK(c, cudaStreamSynchronize(st));
-        for (int p = 0; p < W; p++) send_cnt[p] = h_start[p + 1] - h_start[p];
-        std::vector<uint64_t> mat;
-        RC(allgather_u64(c, send_cnt.data(), W, mat));
-        std::vector<uint64_t> recv_cnt(W);
+        std::vector<uint64_t> mine(W + 2), mat;
+        mine[0] = Kl; mine[1] = c->R;
+        for (int p = 0; p < W; p++) mine[2 + p] = h_start[p + 1] - h_start[p];
+        RC(allgather_u64(c, mine.data(), W + 2, mat));
+        const size_t row = (size_t)W + 2;
+        uint64_t ord_base = 0, read_base = 0;
+        Ktot = 0;
+        for (int r = 0; r < W; r++) {
+            if (r < rank) { ord_base += mat[r * row]; read_base += mat[r * row + 1]; }
+            Ktot += mat[r * row];
+        }
+        if (c->read_base_set) read_base = c->read_base;
+        std::vector<uint64_t> send_cnt(W), recv_cnt(W);
         K = 0;
-        for (int s = 0; s < W; s++) { recv_cnt[s] = mat[(size_t)s * W + rank]; K += recv_cnt[s]; }
+        for (int p = 0; p < W; p++) {
+            send_cnt[p] = mine[2 + p];
+            recv_cnt[p] = mat[p * row + 2 + rank];
+            K += recv_cnt[p];
+        }
         if (K >= 0x7FFFFFF0ull) { c->err = "more than 2^31 k-min-mers owned by one GPU"; return MDBG_ERR_RANGE; }
+        if (Kl) {
+            kb_permute_kernel<<<nblk(Kl), 256, 0, st>>>(perm, Kl, k, ord_base, read_base, l_tuple, l_ord, l_info, s_tuple,
+                                                        s_ord, s_info);
+            LAUNCHED(c);
+        }
         MDBG_CK(c, x_tuple.get(c->pool, K * k)); MDBG_CK(c, x_ord.get(c->pool, K)); MDBG_CK(c, x_info.get(c->pool, K));
         std::vector<uint64_t> sc_t(W), rc_t(W);
         for (int p = 0; p < W; p++) { sc_t[p] = send_cnt[p] * k; rc_t[p] = recv_cnt[p] * k; }
+        NCK(c, nccl().GroupStart());   // ONE fused all-to-all for the three record arrays
         RC(alltoallv(c, s_tuple, sc_t.data(), x_tuple, rc_t.data(), 8));
         RC(alltoallv(c, s_ord, send_cnt.data(), x_ord, recv_cnt.data(), 8));
         RC(alltoallv(c, s_info, send_cnt.data(), x_info, recv_cnt.data(), sizeof(RecInfo)));
-        MDBG_CK(c, cudaStreamSynchronize(st));   // send buffers are released below
+        NCK(c, nccl().GroupEnd());
         r_tuple = x_tuple; r_ord = x_ord; r_info = x_info;
         l_tuple.reset(); l_ord.reset(); l_info.reset();
     }
+    G->n_kminmers = Ktot;
+    const int ord_bits = std::max(1, log2_ceil(Ktot + 1));   // serial ordinals are < Ktot
     l_fp.reset();
     MDBG_CK(c, cudaEventRecord(c->ev[6], st));
 
@@ -393,10 +410,12 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
         NodeRec* nodes_all = my_nodes; uint64_t* tuple_all = my_tuple;
         if (W > 1) {
             MDBG_CK(c, all_nodes.get(c->pool, Stot)); MDBG_CK(c, all_tuple.get(c->pool, Stot * k));
-            RC(allgatherv(c, my_nodes, S_local, scnt, all_nodes, sizeof(NodeRec)));
             std::vector<uint64_t> tcnt(W);
             for (int r = 0; r < W; r++) tcnt[r] = scnt[r] * k;
+            NCK(c, nccl().GroupStart());
+            RC(allgatherv(c, my_nodes, S_local, scnt, all_nodes, sizeof(NodeRec)));
             RC(allgatherv(c, my_tuple, (uint64_t)S_local * k, tcnt, all_tuple, 8));
+            NCK(c, nccl().GroupEnd());
             nodes_all = all_nodes; tuple_all = all_tuple;
         }
         if (Stot > 0) {
@@ -483,6 +502,10 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
             ke_join_kernel<true><<<nblk(q_n, 128), 128, 0, st>>>(NV, ekey, erev, skey, sval, presimp, q_lo, q_n, nullptr, nullptr,
                                                                  off_e, off_r, pend, removed);
             LAUNCHED(c);
+            if (EP > 0) {   // canonical order: nodes ascend already, sort each node's edges in place
+                ke_group_sort_kernel<<<nblk(q_n / 2), 256, 0, st>>>(pend, off_e, q_n / 2);
+                LAUNCHED(c);
+            }
         }
         // presimp removals of every GPU (an edge is dropped if it or its reverse was removed anywhere)
         std::vector<uint64_t> allNR;
@@ -511,20 +534,9 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
         }
         MDBG_CK(c, G->e_n1.get(c->pool, E)); MDBG_CK(c, G->e_o1.get(c->pool, E)); MDBG_CK(c, G->e_n2.get(c->pool, E));
         MDBG_CK(c, G->e_o2.get(c->pool, E)); MDBG_CK(c, G->e_ov.get(c->pool, E));
-        if (E > 0) {  // canonical order (n1, n2, o1, o2, overlap): two stable radix passes
-            Tmp<uint64_t> k_a, k_b; Tmp<uint32_t> id_a, id_b, id_c;
-            MDBG_CK(c, k_a.get(c->pool, E)); MDBG_CK(c, k_b.get(c->pool, E));
-            MDBG_CK(c, id_a.get(c->pool, E)); MDBG_CK(c, id_b.get(c->pool, E)); MDBG_CK(c, id_c.get(c->pool, E));
-            iota_kernel<<<nblk(E), 256, 0, st>>>(id_a, E);
-            LAUNCHED(c);
-            ke_sortkeys_kernel<<<nblk(E), 256, 0, st>>>(edges, nullptr, E, 0, 0, k_a);
-            LAUNCHED(c);
-            RC(R.cub([&](void* t, size_t& b) { return cub::DeviceRadixSort::SortPairs(t, b, k_a.p, k_b.p, id_a.p, id_b.p, E, 0, 34, st); }));
-            ke_sortkeys_kernel<<<nblk(E), 256, 0, st>>>(edges, id_b, E, 1, idx_bits <= 32 ? idx_bits : 32, k_a);
-            LAUNCHED(c);
-            RC(R.cub([&](void* t, size_t& b) { return cub::DeviceRadixSort::SortPairs(t, b, k_a.p, k_b.p, id_b.p, id_c.p, E, 0, 2 * std::min(idx_bits, 32), st); }));
+        if (E > 0) {   // (the stable compaction above kept the canonical order)
             EdgeOut EO{G->e_n1, G->e_o1, G->e_n2, G->e_o2, G->e_ov};
-            ke_gather_kernel<<<nblk(E), 256, 0, st>>>(edges, id_c, E, EO);
+            ke_gather_kernel<<<nblk(E), 256, 0, st>>>(edges, nullptr, E, EO);
             LAUNCHED(c);
         }
     }
@@ -642,10 +654,12 @@ int mdbg_finish(mdbg_ctx* c, int want_seqlines, mdbg_graph* out) {
         uint64_t En = c->rank == 0 ? Et : 0, Qn = c->rank == 0 ? Qt : 0;
         MDBG_CK(c, g_n1.get(c->pool, En)); MDBG_CK(c, g_n2.get(c->pool, En)); MDBG_CK(c, g_ov.get(c->pool, En));
         MDBG_CK(c, g_o1.get(c->pool, En)); MDBG_CK(c, g_o2.get(c->pool, En)); MDBG_CK(c, g_seq.get(c->pool, Qn));
+        NCK(c, nccl().GroupStart());
         RC(gatherv_root(c, G->e_n1, E, ec, g_n1, 4)); RC(gatherv_root(c, G->e_n2, E, ec, g_n2, 4));
         RC(gatherv_root(c, G->e_ov, E, ec, g_ov, 4)); RC(gatherv_root(c, G->e_o1, E, ec, g_o1, 1));
         RC(gatherv_root(c, G->e_o2, E, ec, g_o2, 1));
         if (want_seqlines) RC(gatherv_root(c, G->seq, Q, qc, g_seq, sizeof(SeqRec)));
+        NCK(c, nccl().GroupEnd());
         if (c->rank == 0) {   // slices are contiguous node ranges: the concatenation is already sorted
             E = Et; p_n1 = g_n1; p_n2 = g_n2; p_ov = g_ov; p_o1 = g_o1; p_o2 = g_o2;
             if (want_seqlines && Qt > 0) {   // emission order = ordinal order over all owners

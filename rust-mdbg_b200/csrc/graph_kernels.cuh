@@ -74,10 +74,12 @@ struct RecInfo {
 constexpr uint64_t ORD_REV = 1ull << 63;
 constexpr uint64_t ORD_MASK = ORD_REV - 1;
 
-// one thread per local k-min-mer ordinal g: canonical tuple + fingerprint that decides the owner
+// one thread per local k-min-mer ordinal g: orientation, ordinal, RecInfo, window location and (for
+// N > 1) the fingerprint that decides the owner.  The tuple itself is written by
+// kb_tuples_kernel, one thread per ELEMENT, so that the K x k x 8 bytes go out coalesced.
 __global__ void kb_records_kernel(MinArena A, const uint64_t* __restrict__ kmer_off, uint64_t K, uint32_t k,
-                                  uint64_t seed, uint64_t ord_base, uint64_t read_base,
-                                  uint64_t* __restrict__ tuple, uint64_t* __restrict__ ord,
+                                  uint64_t seed, uint64_t ord_base, uint64_t read_base, int want_fp,
+                                  uint32_t* __restrict__ wloc, uint64_t* __restrict__ ord,
                                   RecInfo* __restrict__ info, uint64_t* __restrict__ fp) {
     uint64_t g = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (g >= K) return;
@@ -87,14 +89,12 @@ __global__ void kb_records_kernel(MinArena A, const uint64_t* __restrict__ kmer_
     const uint64_t* h = A.hash + lo;
     const uint32_t* p = A.pos + lo;
     bool rv = window_reversed(h, k);
-    uint64_t f = fp_init(seed, k);
-    uint64_t* t = tuple + g * k;
-    for (uint32_t j = 0; j < k; j++) {
-        uint64_t v = rv ? __ldg(h + k - 1 - j) : __ldg(h + j);
-        t[j] = v;
-        f = fp_mix(f, v);
+    if (want_fp) {
+        uint64_t f = fp_init(seed, k);
+        for (uint32_t j = 0; j < k; j++) f = fp_mix(f, rv ? __ldg(h + k - 1 - j) : __ldg(h + j));
+        fp[g] = f;
     }
-    fp[g] = f;
+    wloc[g] = (uint32_t)lo;
     ord[g] = (ord_base + g) | (rv ? ORD_REV : 0);
     RecInfo ri;
     ri.p0 = p[0];
@@ -103,6 +103,17 @@ __global__ void kb_records_kernel(MinArena A, const uint64_t* __restrict__ kmer_
     ri.span = p[k - 1] - p[0];
     ri.read = read_base + r;
     info[g] = ri;
+}
+// canonical tuples, one thread per element (coalesced stores; the overlapping windows hit in L1/L2)
+__global__ void kb_tuples_kernel(const uint64_t* __restrict__ hash, const uint32_t* __restrict__ wloc,
+                                 const uint64_t* __restrict__ ord, uint64_t n_elem, uint32_t k,
+                                 uint64_t* __restrict__ tuple) {
+    uint64_t e = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (e >= n_elem) return;
+    uint64_t g = e / k;
+    uint32_t j = (uint32_t)(e - g * k);
+    bool rv = (__ldg(ord + g) & ORD_REV) != 0;
+    tuple[e] = __ldg(hash + __ldg(wloc + g) + (rv ? k - 1 - j : j));
 }
 
 // owner rank of a record: range partition on the fingerprint (mdbg_owner_of_fingerprint)
@@ -124,8 +135,8 @@ __global__ void kb_owner_counts_kernel(const uint32_t* __restrict__ owner_sorted
     else for (uint32_t w = prev + 1; w <= cur && w <= world; w++) start[w] = j;
 }
 // gather records into send order
-__global__ void kb_permute_kernel(const uint32_t* __restrict__ perm, uint64_t K, uint32_t k,
-                                  const uint64_t* __restrict__ tuple, const uint64_t* __restrict__ ord,
+__global__ void kb_permute_kernel(const uint32_t* __restrict__ perm, uint64_t K, uint32_t k, uint64_t ord_add,
+                                  uint64_t read_add, const uint64_t* __restrict__ tuple, const uint64_t* __restrict__ ord,
                                   const RecInfo* __restrict__ info, uint64_t* __restrict__ tuple_o,
                                   uint64_t* __restrict__ ord_o, RecInfo* __restrict__ info_o) {
     uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
@@ -134,8 +145,10 @@ __global__ void kb_permute_kernel(const uint32_t* __restrict__ perm, uint64_t K,
     const uint64_t* s = tuple + (uint64_t)g * k;
     uint64_t* d = tuple_o + j * k;
     for (uint32_t q = 0; q < k; q++) d[q] = s[q];
-    ord_o[j] = ord[g];
-    info_o[j] = info[g];
+    ord_o[j] = ord[g] + ord_add;      // local -> global serial ordinal (bit 63 keeps the reversed flag)
+    RecInfo ri = info[g];
+    ri.read += read_add;
+    info_o[j] = ri;
 }
 
 // table fingerprint of the (already canonical) received tuples
@@ -490,6 +503,27 @@ __global__ void ke_join_kernel(NodeView N, const uint64_t* __restrict__ ekey, co
     if (!WRITE) { cnt_edge[qq] = ne; cnt_rem[qq] = nr; }
 }
 
+// The join emits the edges of node n1 contiguously and nodes in ascending index order, so the
+// canonical order (n1, n2, o1, o2, overlap) only needs each node's few edges sorted among
+// themselves: one thread per node, insertion sort in place (no device-wide radix sort).
+__device__ __forceinline__ bool edge_less(const EdgeRec& a, const EdgeRec& b) {
+    if (a.n2 != b.n2) return a.n2 < b.n2;
+    if (a.o1 != b.o1) return a.o1 < b.o1;
+    if (a.o2 != b.o2) return a.o2 < b.o2;
+    return a.ov < b.ov;
+}
+__global__ void ke_group_sort_kernel(EdgeRec* __restrict__ edges, const uint32_t* __restrict__ off_edge, uint32_t n_nodes) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    uint32_t lo = off_edge[2 * i], hi = off_edge[2 * i + 2];
+    for (uint32_t a = lo + 1; a < hi; a++) {
+        EdgeRec x = edges[a];
+        uint32_t b = a;
+        while (b > lo && edge_less(x, edges[b - 1])) { edges[b] = edges[b - 1]; b--; }
+        edges[b] = x;
+    }
+}
+
 // keep[e] = 0 if (n1,n2) or (n2,n1) was presimp-removed (main.rs:1109)
 __global__ void ke_filter_kernel(const EdgeRec* __restrict__ edges, uint32_t E, const uint64_t* __restrict__ rem,
                                  uint32_t NR, uint8_t* __restrict__ keep) {
@@ -520,7 +554,7 @@ __global__ void ke_gather_kernel(const EdgeRec* __restrict__ edges, const uint32
                                  EdgeOut O) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= E) return;
-    EdgeRec r = edges[ids[i]];
+    EdgeRec r = edges[ids ? ids[i] : i];
     O.n1[i] = r.n1; O.o1[i] = r.o1; O.n2[i] = r.n2; O.o2[i] = r.o2; O.ov[i] = r.ov;
 }
 
