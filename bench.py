@@ -134,6 +134,8 @@ def main():
     ap.add_argument("--workload", default="ecoli50x", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--sweep-k", default="", help="comma list of k: also time finish() per k over the resident "
+                    "minimizers (BASELINE config 5, the multi-k idea of utils/multik)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -261,6 +263,24 @@ def main():
                 "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": ka_avg_ms,
                 "share_of_step": ka_avg_ms / (dev_ms / steps)}
 
+    # ------------------------------------------------------------------ multi-k sweep (config 5)
+    multik = None
+    if args.sweep_k:
+        multik = []
+        ctx.reset()
+        ctx.push_reads_device(d_bases, d_off, reads_per_rank, total)     # minimizers stay resident
+        for kk in [int(x) for x in args.sweep_k.split(",") if x]:
+            ctx.set_k(kk)
+            ctx.finish_device()                                         # warm-up for this k
+            ctx.sync(); barrier()
+            ctx.timer_start()
+            st_k = ctx.finish_device()
+            ms_k = max_over_ranks(ctx.timer_stop())
+            multik.append({"k": kk, "finish_ms": ms_k, "Gbases_per_s_graph_only": bases_all / (ms_k * 1e-3) / 1e9,
+                           "n_kminmers": int(st_k["n_kminmers"]), "n_nodes": int(st_k["n_nodes"]),
+                           "n_edges": int(st_k["n_edges"])})
+        ctx.set_k(wl["k"])
+
     # ------------------------------------------------------------------ e2e through the host ABI
     e2e = None
     if not args.no_e2e:
@@ -321,6 +341,8 @@ def main():
                "roofline": roofline, "cpu_baseline": cpu,
                "stage_ms_per_step": {k_: v_ / steps for k_, v_ in stage.items()},
                "counts": {k_: int(v_) for k_, v_ in stats.items()}}
+        if multik is not None:
+            out["multik"] = multik
         print(json.dumps(out))
     ctx.device_free(d_bases); ctx.device_free(d_off)
     ctx.close()

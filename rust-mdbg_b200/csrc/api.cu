@@ -299,6 +299,13 @@ int mdbg_push_reads(mdbg_ctx* c, const uint8_t* bases, const uint64_t* read_off,
     }
     MDBG_CK(c, cudaSetDevice(c->device));
     uint64_t B = read_off[n_reads];
+    for (uint64_t r = 0; r < n_reads; r++) {
+        if (read_off[r + 1] < read_off[r]) { c->err = "read_off is not non-decreasing"; return MDBG_ERR_BAD_ARG; }
+        if (read_off[r + 1] - read_off[r] >= 0xFFFFFFF0ull) {   // positions inside a read are u32 on the device
+            c->err = "a single record of 4 Gbases or more is not supported";
+            return MDBG_ERR_RANGE;
+        }
+    }
     c->tm.launches_push = 0;
     Tmp<uint8_t> d_bases;
     Tmp<uint64_t> d_off;
