@@ -51,7 +51,13 @@ constexpr int HALO = 256;
 constexpr int ROWS = (PRE + TILE + HALO) / 128;  // 35
 constexpr int RSTRIDE = 144;
 constexpr int WIN = ROWS * 128;
-constexpr int QCAP = 256;
+#ifndef MDBG_KA_QCAP
+#define MDBG_KA_QCAP 256
+#endif
+#ifndef MDBG_KA_MIN_BLOCKS
+#define MDBG_KA_MIN_BLOCKS 5
+#endif
+constexpr int QCAP = MDBG_KA_QCAP;
 constexpr int WORDS = TILE / 32;  // 128
 
 constexpr uint32_t Q_DROP = 0xFFFFFFFFu;
@@ -224,7 +230,7 @@ __global__ void ka_tile_lb_kernel(const uint64_t* __restrict__ read_off, uint64_
 }
 
 template <bool HPC>
-__global__ void __launch_bounds__(KA_THREADS, 5) ka_minimizers_kernel(const KAArgs A) {
+__global__ void __launch_bounds__(KA_THREADS, MDBG_KA_MIN_BLOCKS) ka_minimizers_kernel(const KAArgs A) {
     __shared__ CtaSmem cs;
     const int ctid = threadIdx.x;
     const int tid = ctid & 31, lane = tid;      // position inside the warp's tile

@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmdbg_b200.so")
+LIB_PATH = os.environ.get("MDBG_LIB", os.path.join(_HERE, "libmdbg_b200.so"))   # MDBG_LIB: tuning variants
 
 MDBG_OK = 0
 ERR_NAMES = {0: "MDBG_OK", -1: "MDBG_ERR_NO_DEVICE", -2: "MDBG_ERR_CUDA", -3: "MDBG_ERR_BAD_ARG",
