@@ -47,7 +47,7 @@ typedef struct {
     float    presimp;        /* main.rs:449; 0 disables                                      */
     int32_t  hpc;            /* 1 = homopolymer-compress (default); 0 = --skiphpc (main.rs:507) */
     int32_t  device;         /* CUDA device ordinal for this context                         */
-    int32_t  keep_bases;     /* 1 = keep pushed bases resident (needed for .sequences slices) */
+    int32_t  keep_bases;     /* reserved (the .sequences writer slices the caller's host copy) */
     uint32_t debug_fp_bits;  /* test hook: truncate tuple fingerprints to this many bits on the
                                 first attempt to force the exact-collision path; 0 = off     */
     uint32_t bf;             /* 1 = --bf numbering (main.rs:639-655) with an ideal filter: a tuple

@@ -541,14 +541,6 @@ __global__ void ke_filter_kernel(const EdgeRec* __restrict__ edges, uint32_t E, 
     keep[e] = found ? 0 : 1;
 }
 
-__global__ void ke_sortkeys_kernel(const EdgeRec* __restrict__ edges, const uint32_t* __restrict__ ids, uint32_t E,
-                                   int major, int idx_bits, uint64_t* __restrict__ key) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= E) return;
-    EdgeRec r = edges[ids ? ids[i] : i];
-    key[i] = major ? (((uint64_t)r.n1 << idx_bits) | r.n2) : (((uint64_t)r.o1 << 33) | ((uint64_t)r.o2 << 32) | r.ov);
-}
-
 struct EdgeOut { uint32_t* n1; uint8_t* o1; uint32_t* n2; uint8_t* o2; uint32_t* ov; };
 __global__ void ke_gather_kernel(const EdgeRec* __restrict__ edges, const uint32_t* __restrict__ ids, uint32_t E,
                                  EdgeOut O) {

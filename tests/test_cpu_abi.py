@@ -215,3 +215,18 @@ def test_file_writers_on_host(mdbg, oracle, example_reads, tmp_path):
     body = sorted(x for x in plain.splitlines(True) if not x.startswith("#"))
     assert body == sorted(open(oseq).read().splitlines(True))
     assert _lz4_stored_frame_decode(open(seqz, "rb").read()).decode() == plain
+
+
+def test_bench_reference_arm_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to ours) prints one JSON line
+    with the contract's keys; it needs no GPU."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "tiny",
+                        "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    j = json.loads(r.stdout.strip().splitlines()[-1])
+    assert j["impl"] == "reference" and j["unit"] == "Gbases/s" and j["higher_is_better"] is True
+    assert j["value"] > 0 and j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1
+    assert j["e2e"]["h2d_bytes_per_step"] == 0 and j["e2e"]["value"] == j["value"]

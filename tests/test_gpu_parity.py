@@ -353,3 +353,26 @@ def test_graph_bf_numbering(mdbg, oracle, k, l, d, minab):
     if minab > 1:
         assert o.stats["n_distinct"] < plain.stats["n_distinct"]
     compare_graph(g, o)
+
+
+def test_degenerate_inputs(mdbg, oracle):
+    """No reads, only empty reads, reads too short to window: every stage must cope with zero items."""
+    with mdbg.Context(mdbg.Params(k=5, l=10, density=0.01)) as ctx:
+        for seqs in ([], [b""], [b"", b"", b""], [b"ACGT"], [b"ACGTTGCAAC" * 30]):
+            ctx.reset()
+            bases, off = pack_reads(seqs)
+            ctx.push_reads(bases, off)
+            h, p, mo = ctx.get_minimizers()
+            eh, ep, eo = oracle_minimizers(oracle, seqs, 10, 0.01)
+            assert np.array_equal(h, eh) and np.array_equal(p, ep) and np.array_equal(mo, eo)
+            g = ctx.finish()
+            o = oracle.build_graph(bases, off, 5, 10, 0.01)
+            compare_graph(g, o)
+        # an empty batch between two real ones keeps the read numbering
+        rng = np.random.default_rng(3)
+        seqs = genome_reads(rng, 20000, 60, mean=4000, sd=1000, err=0.002)
+        ctx.reset()
+        b1, o1 = pack_reads(seqs[:30]); b0, o0 = pack_reads([]); b2, o2 = pack_reads(seqs[30:])
+        ctx.push_reads(b1, o1); ctx.push_reads(b0, o0); ctx.push_reads(b2, o2)
+        bases, off = pack_reads(seqs)
+        compare_graph(ctx.finish(), oracle.build_graph(bases, off, 5, 10, 0.01))
