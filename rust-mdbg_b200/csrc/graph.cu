@@ -269,8 +269,9 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
         }
         if (K >= 0x7FFFFFF0ull) { c->err = "more than 2^31 k-min-mers owned by one GPU"; return MDBG_ERR_RANGE; }
         if (Kl) {
-            kb_permute_kernel<<<nblk(Kl), 256, 0, st>>>(perm, Kl, k, ord_base, read_base, l_tuple, l_ord, l_info, s_tuple,
-                                                        s_ord, s_info);
+            kb_permute_kernel<<<nblk(Kl), 256, 0, st>>>(perm, Kl, ord_base, read_base, l_ord, l_info, s_ord, s_info);
+            LAUNCHED(c);
+            kb_permute_tuples_kernel<<<nblk(Kl * k), 256, 0, st>>>(perm, Kl * k, k, l_tuple, s_tuple);
             LAUNCHED(c);
         }
         MDBG_CK(c, x_tuple.get(c->pool, K * k)); MDBG_CK(c, x_ord.get(c->pool, K)); MDBG_CK(c, x_info.get(c->pool, K));

@@ -134,21 +134,25 @@ __global__ void kb_owner_counts_kernel(const uint32_t* __restrict__ owner_sorted
     if (j == 0) { for (uint32_t w = 0; w <= cur && w <= world; w++) start[w] = 0; }
     else for (uint32_t w = prev + 1; w <= cur && w <= world; w++) start[w] = j;
 }
-// gather records into send order
-__global__ void kb_permute_kernel(const uint32_t* __restrict__ perm, uint64_t K, uint32_t k, uint64_t ord_add,
-                                  uint64_t read_add, const uint64_t* __restrict__ tuple, const uint64_t* __restrict__ ord,
-                                  const RecInfo* __restrict__ info, uint64_t* __restrict__ tuple_o,
+// gather records into send order: ord / info per record, tuples per ELEMENT (coalesced stores)
+__global__ void kb_permute_kernel(const uint32_t* __restrict__ perm, uint64_t K, uint64_t ord_add, uint64_t read_add,
+                                  const uint64_t* __restrict__ ord, const RecInfo* __restrict__ info,
                                   uint64_t* __restrict__ ord_o, RecInfo* __restrict__ info_o) {
     uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (j >= K) return;
     uint32_t g = perm[j];
-    const uint64_t* s = tuple + (uint64_t)g * k;
-    uint64_t* d = tuple_o + j * k;
-    for (uint32_t q = 0; q < k; q++) d[q] = s[q];
     ord_o[j] = ord[g] + ord_add;      // local -> global serial ordinal (bit 63 keeps the reversed flag)
     RecInfo ri = info[g];
     ri.read += read_add;
     info_o[j] = ri;
+}
+__global__ void kb_permute_tuples_kernel(const uint32_t* __restrict__ perm, uint64_t n_elem, uint32_t k,
+                                         const uint64_t* __restrict__ tuple, uint64_t* __restrict__ tuple_o) {
+    uint64_t e = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (e >= n_elem) return;
+    uint64_t j = e / k;
+    uint32_t q = (uint32_t)(e - j * k);
+    tuple_o[e] = __ldg(tuple + (uint64_t)__ldg(perm + j) * k + q);
 }
 
 // table fingerprint of the (already canonical) received tuples
