@@ -26,4 +26,4 @@ def oracle():
 def example_reads():
     """BASELINE config #1 input: (bases u8[], read_off u64[R+1], names)."""
     from helpers import load_fasta
-    return load_fasta(os.path.join(GOLDEN, "reads-0.00.fa.gz"))
+    return load_fasta(os.path.join(GOLDEN, "config1_reads.fa.gz"))

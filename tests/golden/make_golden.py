@@ -10,15 +10,16 @@
       They pin: the ntHash restatement (17 exact 64-bit hashes), the inclusive density
       threshold (no other l-mer of the sequence may be selected), the slice convention
       seq = raw[p_i .. p_{i+k-1}+l) and the shift pair (main.rs:769-778).
-  reads-0.00.fa.gz
-      BASELINE config #1 input (example/reads-0.00.fa.gz), copied verbatim as test DATA.
+  config1_reads.fa.gz
+      BASELINE config #1 input: the 657 reads of the reference's example/reads-0.00.fa.gz,
+      re-compressed (test DATA, needed on the GPU box where /root/reference does not exist).
 
 Run:  python tests/golden/make_golden.py      (needs /root/reference)
 """
+import gzip
 import json
 import os
 import re
-import shutil
 
 REF = "/root/reference"
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -40,8 +41,9 @@ def main():
                 "parts": [a, b, c]})
     with open(os.path.join(HERE, "reference_sequences_lines.json"), "w") as f:
         json.dump(out, f, indent=1)
-    shutil.copyfile(os.path.join(REF, "example/reads-0.00.fa.gz"), os.path.join(HERE, "reads-0.00.fa.gz"))
-    os.chmod(os.path.join(HERE, "reads-0.00.fa.gz"), 0o644)
+    data = gzip.open(os.path.join(REF, "example/reads-0.00.fa.gz"), "rb").read()
+    with gzip.GzipFile(os.path.join(HERE, "config1_reads.fa.gz"), "wb", compresslevel=9, mtime=0) as f:
+        f.write(data)
     print("wrote", len(out), "golden lines + example reads")
 
 

@@ -315,7 +315,7 @@ def test_cli_example_config1(mdbg, oracle, example_reads, tmp_path):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     exe = os.path.join(root, "rust-mdbg_b200", "rust-mdbg")
     prefix = str(tmp_path / "example")
-    r = subprocess.run([exe, os.path.join(root, "tests", "golden", "reads-0.00.fa.gz"), "-k", "7", "--density", "0.0008",
+    r = subprocess.run([exe, os.path.join(root, "tests", "golden", "config1_reads.fa.gz"), "-k", "7", "--density", "0.0008",
                         "-l", "10", "--minabund", "2", "--prefix", prefix], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr
     for line in ("Format: FASTA", "Parsing input sequences...", "Number of reads: 657",
