@@ -294,7 +294,7 @@ def main():
         ctx.d2h(hb_arr, d_bases)     # same bytes as the device copy (generated on the device)
         d2h_bytes = 0
 
-        e2e_parts = {"h2d": 0.0, "push": 0.0, "finish": 0.0, "d2h": 0.0}
+        e2e_parts = {"h2d": 0.0, "push": 0.0, "ka_start": 0.0, "ka_kernels_done": 0.0, "ka_done": 0.0, "finish": 0.0, "d2h": 0.0}
 
         def step_e2e():
             ctx.reset()
@@ -303,6 +303,8 @@ def main():
             tm = ctx.timings()
             e2e_parts["h2d"] += tm["ms_h2d"]; e2e_parts["push"] += tm["ms_total_push"]
             e2e_parts["finish"] += tm["ms_total_finish"]; e2e_parts["d2h"] += tm["ms_d2h"]
+            e2e_parts["ka_kernels_done"] += tm["ms_ka_kernel"]; e2e_parts["ka_done"] += tm["ms_ka"]
+            e2e_parts["ka_start"] += tm["ms_ka_start"]
             nb = cg.n_nodes * (4 + 2 + 4 + 4 + 8 * cg.k) + cg.n_edges * (4 + 1 + 4 + 1 + 4)
             ctx.graph_free(cg)
             return nb

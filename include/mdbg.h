@@ -158,6 +158,7 @@ typedef struct {
     uint32_t table_attempts;                   /* fingerprint seeds tried by the last finish */
     uint32_t ka_dense_tiles;                   /* tiles that took the exact (dense) path     */
     float ms_ka_kernel;                        /* ka_minimizers_kernel alone (last push)     */
+    float ms_ka_start;                         /* push start -> first K-A work on the stream  */
 } mdbg_timings;
 int mdbg_get_timings(mdbg_ctx* ctx, mdbg_timings* out);
 void* mdbg_stream(mdbg_ctx* ctx);              /* the cudaStream_t all kernels run on        */

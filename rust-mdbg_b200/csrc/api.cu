@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cub/cub.cuh>
 #include <string>
@@ -193,14 +194,15 @@ static int run_ka(mdbg_ctx* c, const uint8_t* d_bases, const uint64_t* d_read_of
     double rho = std::min(1.0, 2.6 * c->p.density + 1e-4);
     uint64_t est = (uint64_t)((double)B * rho) + 4096;
     int rc;
+    bool fresh_arena = false;
     if (c->M == 0 && c->R == 0 && c->m_off == nullptr) {
         if ((rc = ensure_arena(c, est, R))) return rc;
-        MDBG_CK(c, cudaMemsetAsync(c->m_off, 0, 8, c->st));
+        fresh_arena = true;   // m_off[0] = 0, written by ka_prepare's kernel
     } else if ((rc = ensure_arena(c, c->M + est, c->R + R))) return rc;
 
     uint64_t n_tiles = std::max<uint64_t>(1, (B + KA_TILE - 1) / KA_TILE);
     Tmp<uint64_t> tile_cnt, tile_soff, tile_excl, tile_lb, stage_hash;
-    Tmp<uint32_t> stage_pos;
+    Tmp<uint32_t> stage_pos, chunk_cnt;
     Tmp<uint8_t> scan_tmp;
     MDBG_CK(c, tile_cnt.get(c->pool, n_tiles));
     MDBG_CK(c, tile_soff.get(c->pool, n_tiles));
@@ -214,32 +216,36 @@ static int run_ka(mdbg_ctx* c, const uint8_t* d_bases, const uint64_t* d_read_of
         const uint64_t stage_cap = c->m_cap_items - c->M;
         MDBG_CK(c, stage_hash.get(c->pool, stage_cap));
         MDBG_CK(c, stage_pos.get(c->pool, stage_cap));
-        Scalars init{};
-        init.err_pos = ~0ull;
-        *c->h_sc = init;
-        MDBG_CK(c, cudaMemcpyAsync(c->d_sc, c->h_sc, sizeof(Scalars), cudaMemcpyHostToDevice, c->st));
+        // All device-side state of the batch is reset by ka_prepare's KERNEL: a cudaMemsetAsync or
+        // an H2D copy here may be served by the copy engine and then queues behind the bulk upload
+        // of mdbg_push_reads, which serialises K-A after the copy instead of under it.
+        const size_t n_launch = (plan && attempt == 0) ? plan->size() : 1;
+        MDBG_CK(c, chunk_cnt.get(c->pool, n_launch));
+        KAInit I{&c->d_sc->total_out, &c->d_sc->err_pos, &c->d_sc->stage_counter, &c->d_sc->dense_tiles,
+                 chunk_cnt.p, (uint32_t)n_launch, fresh_arena ? c->m_off : nullptr};
         KAArgs A{};
         A.bases = d_bases; A.read_off = d_read_off; A.n_reads = R; A.n_bases = B;
         A.l = c->p.l; A.bound = c->bound; A.fc = c->fc; A.force_dense = 0;
         A.out_hash = c->m_hash; A.out_pos = c->m_pos; A.out_read_off = c->m_off;
         A.out_base = c->M; A.out_cap = c->m_cap_items; A.read_base = c->R;
         A.total_out = &c->d_sc->total_out; A.err_pos = &c->d_sc->err_pos;
-        A.dense_tiles = &c->d_sc->dense_tiles; A.tile_counter = &c->d_sc->tile_counter;
+        A.dense_tiles = &c->d_sc->dense_tiles; A.tile_counter = nullptr;
         A.stage_hash = stage_hash; A.stage_pos = stage_pos; A.stage_cap = stage_cap;
         A.stage_counter = &c->d_sc->stage_counter; A.tile_cnt = tile_cnt; A.tile_soff = tile_soff;
         A.tile_lb = tile_lb; A.n_tiles = n_tiles;
         MDBG_CK(c, cudaEventRecord(c->ev[0], c->st));
-        MDBG_CK(c, ka_prepare(A, c->st, &c->tm.launches_push));
+        MDBG_CK(c, ka_prepare(A, I, c->st, &c->tm.launches_push));
         if (plan && attempt == 0) {
             uint64_t tb = 0;
+            size_t li = 0;
             for (const KaChunk& ch : *plan) {
                 if (ch.wait) MDBG_CK(c, cudaStreamWaitEvent(c->st, ch.wait, 0));
-                A.tile_begin = tb; A.tile_end = ch.tile_end;
+                A.tile_begin = tb; A.tile_end = ch.tile_end; A.tile_counter = chunk_cnt.p + li++;
                 MDBG_CK(c, ka_launch(A, c->p.hpc, c->ka_grid, c->st, &c->tm.launches_push));
                 tb = ch.tile_end;
             }
         } else {
-            A.tile_begin = 0; A.tile_end = n_tiles;
+            A.tile_begin = 0; A.tile_end = n_tiles; A.tile_counter = chunk_cnt.p;
             MDBG_CK(c, ka_launch(A, c->p.hpc, c->ka_grid, c->st, &c->tm.launches_push));
         }
         MDBG_CK(c, cudaEventRecord(c->ev[16], c->st));
@@ -312,18 +318,25 @@ int mdbg_push_reads(mdbg_ctx* c, const uint8_t* bases, const uint64_t* read_off,
     MDBG_CK(c, d_bases.get(c->pool, B + 16));
     MDBG_CK(c, d_off.get(c->pool, n_reads + 1));
     MDBG_CK(c, cudaEventRecord(c->ev[2], c->st));
-    MDBG_CK(c, cudaMemcpyAsync(d_off, read_off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, c->st));
     // Upload in ~32 MB chunks cut at read starts on a second stream; K-A runs on the tiles whose
     // bytes have arrived, so the kernel hides behind the PCIe copy (pinned host memory).
-    const uint64_t CH = 32ull << 20;
+    uint64_t CH = 32ull << 20;
+    if (const char* e = getenv("MDBG_UPLOAD_CHUNK_MB")) { long v = atol(e); if (v >= 1 && v <= 4096) CH = (uint64_t)v << 20; }
     std::vector<KaChunk> plan;
     const uint64_t n_tiles = std::max<uint64_t>(1, (B + KA_TILE - 1) / KA_TILE);
     MDBG_CK(c, cudaStreamWaitEvent(c->st_copy, c->ev[2], 0));   // the staging buffer is free again
     MDBG_CK(c, cudaEventRecord(c->ev[17], c->st_copy));
+    // Every copy of the batch goes through the copy stream, the compute stream carries kernels only:
+    // channels that share the copy engine are time-sliced, so one small copy on the compute stream
+    // can sit behind the whole bulk upload and hold K-A back until the upload is over.
+    MDBG_CK(c, cudaMemcpyAsync(d_off, read_off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, c->st_copy));
+    MDBG_CK(c, cudaEventRecord(c->ev[18], c->st_copy));
+    MDBG_CK(c, cudaStreamWaitEvent(c->st, c->ev[18], 0));
     uint64_t b0 = 0;
     size_t nev = 0;
     while (b0 < B) {
         uint64_t target = b0 + CH;
+        if (B - b0 <= CH + CH / 4 && B - b0 > CH / 2) target = B - CH / 4;   // short last chunk: short tail after the copy
         uint64_t b1 = B;
         if (target < B) {   // first read start >= target
             const uint64_t* it = std::lower_bound(read_off, read_off + n_reads + 1, target);
@@ -357,6 +370,7 @@ int mdbg_push_reads(mdbg_ctx* c, const uint8_t* bases, const uint64_t* read_off,
     MDBG_CK(c, cudaStreamSynchronize(c->st_copy));
     cudaEventElapsedTime(&c->tm.ms_h2d, c->ev[17], c->ev[4]);
     cudaEventElapsedTime(&c->tm.ms_total_push, c->ev[2], c->ev[3]);
+    cudaEventElapsedTime(&c->tm.ms_ka_start, c->ev[2], c->ev[0]);
     return MDBG_OK;
 }
 

@@ -203,21 +203,27 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
     // added when the records are packed for sending (they come out of the same all-gather as the
     // exchange counts, one host round trip for both).
     uint64_t Ktot = Kl;
-    Tmp<uint64_t> l_tuple, l_ord, l_fp;
+    Tmp<uint64_t> l_ord, l_fp;
     Tmp<RecInfo> l_info;
-    MDBG_CK(c, l_tuple.get(c->pool, Kl * k));
+    Tmp<uint32_t> wloc, iota;
     MDBG_CK(c, l_ord.get(c->pool, Kl));
     MDBG_CK(c, l_info.get(c->pool, Kl));
     MDBG_CK(c, l_fp.get(c->pool, Kl));
+    MDBG_CK(c, wloc.get(c->pool, Kl));
+    if (W == 1) MDBG_CK(c, iota.get(c->pool, Kl));
+    // The canonical tuples are NOT materialised on the GPU that cut the windows: a record is a
+    // window of the (L2-resident) minimizer arena, read through TupleSrc.  On one GPU the same
+    // pass also computes the table fingerprint of the first seed.
+    const uint64_t table_seed0 = 0x7461626c65000000ull;
+    uint64_t fp_mask0 = ~0ull;
+    if (c->p.debug_fp_bits > 0 && c->p.debug_fp_bits < 64) fp_mask0 = (1ull << c->p.debug_fp_bits) - 1;
     if (Kl) {
-        Tmp<uint32_t> wloc;
-        MDBG_CK(c, wloc.get(c->pool, Kl));
-        kb_records_kernel<<<nblk(Kl), 256, 0, st>>>(A, kmer_off, Kl, k, 0x6d64626700000000ull, 0,
-                                                    W == 1 ? c->read_base : 0, W > 1 ? 1 : 0, wloc, l_ord, l_info, l_fp);
-        LAUNCHED(c);
-        kb_tuples_kernel<<<nblk(Kl * k), 256, 0, st>>>(c->m_hash, wloc, l_ord, Kl * k, k, l_tuple);
+        kb_records_kernel<<<nblk(Kl), 256, 0, st>>>(A, kmer_off, Kl, k, W == 1 ? table_seed0 : 0x6d64626700000000ull,
+                                                    fp_mask0, 0, W == 1 ? c->read_base : 0, W == 1 ? 2 : 1, wloc, l_ord,
+                                                    l_info, l_fp, W == 1 ? iota.p : nullptr);
         LAUNCHED(c);
     }
+    const TupleSrc local_src{nullptr, c->m_hash, wloc.p, l_ord.p, k};
     cnt.reset();
     kmer_off.reset();
 
@@ -225,7 +231,8 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
     uint64_t K = Kl;  // records this GPU owns
     Tmp<uint64_t> x_tuple, x_ord;
     Tmp<RecInfo> x_info;
-    uint64_t* r_tuple = l_tuple; uint64_t* r_ord = l_ord; RecInfo* r_info = l_info;
+    uint64_t* r_ord = l_ord; RecInfo* r_info = l_info;
+    TupleSrc T = local_src;
     if (W > 1) {
         Tmp<uint32_t> owner, owner_s, iota, perm;
         Tmp<uint64_t> s_tuple, s_ord;
@@ -271,7 +278,7 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
         if (Kl) {
             kb_permute_kernel<<<nblk(Kl), 256, 0, st>>>(perm, Kl, ord_base, read_base, l_ord, l_info, s_ord, s_info);
             LAUNCHED(c);
-            kb_permute_tuples_kernel<<<nblk(Kl * k), 256, 0, st>>>(perm, Kl * k, k, l_tuple, s_tuple);
+            kb_permute_tuples_kernel<<<nblk(Kl * k), 256, 0, st>>>(perm, Kl * k, local_src, s_tuple);
             LAUNCHED(c);
         }
         MDBG_CK(c, x_tuple.get(c->pool, K * k)); MDBG_CK(c, x_ord.get(c->pool, K)); MDBG_CK(c, x_info.get(c->pool, K));
@@ -282,17 +289,18 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
         RC(alltoallv(c, s_ord, send_cnt.data(), x_ord, recv_cnt.data(), 8));
         RC(alltoallv(c, s_info, send_cnt.data(), x_info, recv_cnt.data(), sizeof(RecInfo)));
         NCK(c, nccl().GroupEnd());
-        r_tuple = x_tuple; r_ord = x_ord; r_info = x_info;
-        l_tuple.reset(); l_ord.reset(); l_info.reset();
+        r_ord = x_ord; r_info = x_info;
+        T = TupleSrc{x_tuple.p, nullptr, nullptr, nullptr, k};
+        l_ord.reset(); l_info.reset(); wloc.reset();
     }
     G->n_kminmers = Ktot;
     const int ord_bits = std::max(1, log2_ceil(Ktot + 1));   // serial ordinals are < Ktot
-    l_fp.reset();
+    if (W > 1) l_fp.reset();
     MDBG_CK(c, cudaEventRecord(c->ev[6], st));
 
     // ---- K-C table + K-D sort by slot (retry with a new seed on a fingerprint collision) ---------
     uint32_t D = 0, S_local = 0, Q_local = 0;
-    Tmp<uint32_t> slot, first, iota, sslot, sj, seg_start, seg_index, solid_seg, nseq, seq_off;
+    Tmp<uint32_t> slot, first, sslot, sj, seg_start, seg_index, solid_seg, nseq, seq_off;
     Tmp<uint64_t> first_ord;
     Tmp<uint8_t> solid;
     const int cap_bits = std::max(12, log2_ceil(2 * std::max<uint64_t>(K, 1)));
@@ -300,24 +308,27 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
         Tmp<uint64_t> fp, keys;
         Tmp<uint8_t> head;
         const uint64_t cap = 1ull << cap_bits;
-        MDBG_CK(c, fp.get(c->pool, K)); MDBG_CK(c, iota.get(c->pool, K)); MDBG_CK(c, slot.get(c->pool, K));
+        if (W > 1) { MDBG_CK(c, fp.get(c->pool, K)); MDBG_CK(c, iota.get(c->pool, K)); }
+        MDBG_CK(c, slot.get(c->pool, K));
+        uint64_t* fpv = W == 1 ? l_fp.p : fp.p;   // one GPU: attempt 0 came out of kb_records
         MDBG_CK(c, keys.get(c->pool, cap)); MDBG_CK(c, first.get(c->pool, cap));
         MDBG_CK(c, sslot.get(c->pool, K)); MDBG_CK(c, sj.get(c->pool, K));
         MDBG_CK(c, head.get(c->pool, K)); MDBG_CK(c, seg_start.get(c->pool, K + 1));
         for (int attempt = 0;; attempt++) {
             if (attempt >= 8) { c->err = "fingerprint collisions persisted over 8 seeds"; return MDBG_ERR_RANGE; }
             c->tm.table_attempts = attempt + 1;
-            uint64_t seed = 0x7461626c65000000ull + 0x9e3779b97f4a7c15ull * (uint64_t)attempt;
-            uint64_t mask = ~0ull;
-            if (attempt == 0 && c->p.debug_fp_bits > 0 && c->p.debug_fp_bits < 64) mask = (1ull << c->p.debug_fp_bits) - 1;
-            kc_fp_kernel<<<nblk(K), 256, 0, st>>>(r_tuple, K, k, seed, mask, fp, iota);
-            LAUNCHED(c);
+            uint64_t seed = table_seed0 + 0x9e3779b97f4a7c15ull * (uint64_t)attempt;
+            uint64_t mask = attempt == 0 ? fp_mask0 : ~0ull;
+            if (W > 1 || attempt > 0) {
+                kc_fp_kernel<<<nblk(K), 256, 0, st>>>(T, K, seed, mask, fpv, iota);
+                LAUNCHED(c);
+            }
             MDBG_CK(c, cudaMemsetAsync(keys, 0xFF, cap * 8, st));
             MDBG_CK(c, cudaMemsetAsync(first, 0xFF, cap * 4, st));
             MDBG_CK(c, cudaMemsetAsync(&c->d_sc->v[1], 0, 8, st));
-            kc_insert_kernel<<<nblk(K * 4), 256, 0, st>>>(fp, K, keys, first, cap - 1, slot);
+            kc_insert_kernel<<<nblk(K * 4), 256, 0, st>>>(fpv, K, keys, first, cap - 1, slot);
             LAUNCHED(c);
-            kc_verify_kernel<<<nblk(K), 256, 0, st>>>(r_tuple, K, k, slot, first, &c->d_sc->v[1]);
+            kc_verify_kernel<<<nblk(K), 256, 0, st>>>(T, K, slot, first, &c->d_sc->v[1]);
             LAUNCHED(c);
             // K-D: stable sort by slot, segment heads (speculatively: the collision flag is read
             // together with the segment count, one host round trip for both)
@@ -336,16 +347,60 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
         D = (uint32_t)(c->h_sc->v[2] & 0xFFFFFFFFu);
     }
     MDBG_CK(c, cudaEventRecord(c->ev[7], st));   // ms_kc = table + sort by slot, ms_kd = reduce + nodes
-    slot.reset(); first.reset(); iota.reset(); sslot.reset();
+    slot.reset(); first.reset(); iota.reset(); sslot.reset(); l_fp.reset();
     MDBG_CK(c, first_ord.get(c->pool, D)); MDBG_CK(c, solid.get(c->pool, D)); MDBG_CK(c, nseq.get(c->pool, (uint64_t)D + 1));
-    MDBG_CK(c, seq_off.get(c->pool, (uint64_t)D + 1)); MDBG_CK(c, seg_index.get(c->pool, D)); MDBG_CK(c, solid_seg.get(c->pool, D));
-    Tmp<uint64_t> first_sorted;
-    MDBG_CK(c, first_sorted.get(c->pool, D));
+    MDBG_CK(c, seq_off.get(c->pool, (uint64_t)D + 1)); MDBG_CK(c, seg_index.get(c->pool, D));
     Tmp<uint8_t> counted;
     MDBG_CK(c, counted.get(c->pool, D));
     uint32_t Dc = D;   // tuples that are in the table (all of them without --bf)
+    uint64_t Dtot = 0, Stot = 0, Qtot = 0;
+    if (W == 1) {
+        // ---- one GPU: ordinals are local, so the node index and the place of a solid node in the
+        // ascending-index node list both come out of ONE prefix sum over ordinal space; nodes are
+        // written in place (no sort of first sightings, no binary searches, no sort of nodes)
+        Tmp<uint8_t> ord_flags;
+        Tmp<uint64_t> rank64;
+        MDBG_CK(c, ord_flags.get(c->pool, K + 1)); MDBG_CK(c, rank64.get(c->pool, K + 1));
+        if (D > 0) {
+            MDBG_CK(c, cudaMemsetAsync(ord_flags.p, 0, K + 1, st));
+            kd_segments_kernel<<<nblk(D), 256, 0, st>>>(seg_start, D, K, sj, r_ord, minab, bf, first_ord, counted, solid, nseq,
+                                                        ord_flags);
+            LAUNCHED(c);
+            RC(R.cub([&](void* t, size_t& b) {
+                cub::TransformInputIterator<uint64_t, FlagPairToU64, const uint8_t*> in(ord_flags.p, FlagPairToU64());
+                return cub::DeviceScan::ExclusiveSum(t, b, in, rank64.p, (uint32_t)(K + 1), st);
+            }));
+            MDBG_CK(c, cudaMemcpyAsync(&c->d_sc->v[3], rank64.p + K, 8, cudaMemcpyDeviceToDevice, st));
+            MDBG_CK(c, cudaMemsetAsync(&c->d_sc->v[4], 0, 8, st));
+            if (want_seqlines) {
+                MDBG_CK(c, cudaMemsetAsync(nseq.p + D, 0, 4, st));
+                RC(R.cub([&](void* t, size_t& b) { return cub::DeviceScan::ExclusiveSum(t, b, nseq.p, seq_off.p, D + 1, st); }));
+                MDBG_CK(c, cudaMemcpyAsync(&c->d_sc->v[4], seq_off.p + D, 4, cudaMemcpyDeviceToDevice, st));
+            }
+            RC(read_scalars(c));   // v[3] = tuples in the table | solid nodes << 32, v[4] = .sequences lines
+            Dc = (uint32_t)(c->h_sc->v[3] & 0xFFFFFFFFu);
+            S_local = (uint32_t)(c->h_sc->v[3] >> 32);
+            Q_local = (uint32_t)(c->h_sc->v[4] & 0xFFFFFFFFu);
+        }
+        Dtot = Dc; Stot = S_local; Qtot = Q_local;
+        G->n_distinct = Dtot; G->n_nodes = Stot; G->n_seqlines = want_seqlines ? Qtot : 0;
+        MDBG_CK(c, G->index.get(c->pool, Stot)); MDBG_CK(c, G->abundance.get(c->pool, Stot));
+        MDBG_CK(c, G->seqlen.get(c->pool, Stot)); MDBG_CK(c, G->shift.get(c->pool, 2 * Stot));
+        MDBG_CK(c, G->tuple.get(c->pool, Stot * k));
+        if (D > 0) {
+            NodeOut NO{G->index, G->abundance, G->seqlen, G->shift, G->tuple};
+            kd_nodes_direct_kernel<<<nblk(D), 256, 0, st>>>(D, minab, K, seg_start, sj, first_ord, counted, solid, rank64, T,
+                                                            r_ord, r_info, seg_index, NO);
+            LAUNCHED(c);
+        }
+        first_ord.reset(); solid.reset();
+    } else {
+    MDBG_CK(c, solid_seg.get(c->pool, D));
+    Tmp<uint64_t> first_sorted;
+    MDBG_CK(c, first_sorted.get(c->pool, D));
     if (D > 0) {
-        kd_segments_kernel<<<nblk(D), 256, 0, st>>>(seg_start, D, K, sj, r_ord, minab, bf, first_ord, counted, solid, nseq);
+        kd_segments_kernel<<<nblk(D), 256, 0, st>>>(seg_start, D, K, sj, r_ord, minab, bf, first_ord, counted, solid, nseq,
+                                                    nullptr);
         LAUNCHED(c);
         // sorted list of the index-consuming sightings (uncounted ones carry ORD_MASK and sort last)
         RC(R.cub([&](void* t, size_t& b) { return cub::DeviceRadixSort::SortKeys(t, b, first_ord.p, first_sorted.p, D, 0, bf ? 63 : ord_bits, st); }));
@@ -373,7 +428,6 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
     std::vector<uint64_t> allD;
     { uint64_t mine[3] = {Dc, S_local, Q_local}; RC(allgather_u64(c, mine, 3, allD)); }
     std::vector<uint64_t> dcnt(W), scnt(W), qcnt(W), loff(W + 1, 0);
-    uint64_t Dtot = 0, Stot = 0, Qtot = 0;
     for (int r = 0; r < W; r++) {
         dcnt[r] = allD[3 * r]; scnt[r] = allD[3 * r + 1]; qcnt[r] = allD[3 * r + 2];
         Dtot += dcnt[r]; Stot += scnt[r]; Qtot += qcnt[r];
@@ -404,35 +458,32 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
         Tmp<uint64_t> my_tuple, all_tuple;
         MDBG_CK(c, my_nodes.get(c->pool, S_local)); MDBG_CK(c, my_tuple.get(c->pool, (uint64_t)S_local * k));
         if (S_local > 0) {
-            kd_nodes_kernel<<<nblk(S_local), 256, 0, st>>>(S_local, k, minab, K, D, solid_seg, seg_start, sj, seg_index,
-                                                           r_tuple, r_ord, r_info, my_nodes, my_tuple);
+            kd_nodes_kernel<<<nblk(S_local), 256, 0, st>>>(S_local, minab, K, D, solid_seg, seg_start, sj, seg_index,
+                                                           T, r_ord, r_info, my_nodes, my_tuple);
             LAUNCHED(c);
         }
-        NodeRec* nodes_all = my_nodes; uint64_t* tuple_all = my_tuple;
-        if (W > 1) {
-            MDBG_CK(c, all_nodes.get(c->pool, Stot)); MDBG_CK(c, all_tuple.get(c->pool, Stot * k));
-            std::vector<uint64_t> tcnt(W);
-            for (int r = 0; r < W; r++) tcnt[r] = scnt[r] * k;
-            NCK(c, nccl().GroupStart());
-            RC(allgatherv(c, my_nodes, S_local, scnt, all_nodes, sizeof(NodeRec)));
-            RC(allgatherv(c, my_tuple, (uint64_t)S_local * k, tcnt, all_tuple, 8));
-            NCK(c, nccl().GroupEnd());
-            nodes_all = all_nodes; tuple_all = all_tuple;
-        }
+        MDBG_CK(c, all_nodes.get(c->pool, Stot)); MDBG_CK(c, all_tuple.get(c->pool, Stot * k));
+        std::vector<uint64_t> tcnt(W);
+        for (int r = 0; r < W; r++) tcnt[r] = scnt[r] * k;
+        NCK(c, nccl().GroupStart());
+        RC(allgatherv(c, my_nodes, S_local, scnt, all_nodes, sizeof(NodeRec)));
+        RC(allgatherv(c, my_tuple, (uint64_t)S_local * k, tcnt, all_tuple, 8));
+        NCK(c, nccl().GroupEnd());
         if (Stot > 0) {
             Tmp<uint32_t> nkey, nkey_s, nid, nid_s;
             MDBG_CK(c, nkey.get(c->pool, Stot)); MDBG_CK(c, nkey_s.get(c->pool, Stot));
             MDBG_CK(c, nid.get(c->pool, Stot)); MDBG_CK(c, nid_s.get(c->pool, Stot));
-            kd_node_keys_kernel<<<nblk(Stot), 256, 0, st>>>(nodes_all, (uint32_t)Stot, nkey, nid);
+            kd_node_keys_kernel<<<nblk(Stot), 256, 0, st>>>(all_nodes, (uint32_t)Stot, nkey, nid);
             LAUNCHED(c);
             RC(R.cub([&](void* t, size_t& b) {
                 return cub::DeviceRadixSort::SortPairs(t, b, nkey.p, nkey_s.p, nid.p, nid_s.p, (uint32_t)Stot, 0, idx_bits, st);
             }));
-            kd_unpack_nodes_kernel<<<nblk(Stot), 256, 0, st>>>(nodes_all, nid_s, (uint32_t)Stot, k, tuple_all, G->index,
+            kd_unpack_nodes_kernel<<<nblk(Stot), 256, 0, st>>>(all_nodes, nid_s, (uint32_t)Stot, k, all_tuple, G->index,
                                                                G->abundance, G->seqlen, G->shift, G->tuple);
             LAUNCHED(c);
         }
     }
+    }   // W > 1
     // .sequences lines of this owner, in ordinal (= emission) order
     G->n_seq_local = 0;
     if (want_seqlines) {
@@ -457,7 +508,7 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
     MDBG_CK(c, cudaEventRecord(c->ev[8], st));
     // free table-stage scratch before the edge stage
     nseq.reset(); seq_off.reset(); seg_index.reset(); solid_seg.reset(); seg_start.reset(); sj.reset();
-    x_tuple.reset(); x_ord.reset(); x_info.reset(); l_tuple.reset(); l_ord.reset(); l_info.reset();
+    x_tuple.reset(); x_ord.reset(); x_info.reset(); wloc.reset(); l_ord.reset(); l_info.reset();
 
     // ---- K-E: edges of this GPU's slice of the nodes ----------------------------------------------
     uint32_t E = 0;
@@ -477,37 +528,49 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
         RC(R.cub([&](void* t, size_t& b) {
             return cub::DeviceRadixSort::SortPairs(t, b, ekey.p, skey.p, eval.p, sval.p, E2, 0, 32, st);
         }));
-        Tmp<uint32_t> cnt_e, cnt_r, off_e, off_r;
-        MDBG_CK(c, cnt_e.get(c->pool, (uint64_t)q_n + 1)); MDBG_CK(c, cnt_r.get(c->pool, (uint64_t)q_n + 1));
-        MDBG_CK(c, off_e.get(c->pool, (uint64_t)q_n + 1)); MDBG_CK(c, off_r.get(c->pool, (uint64_t)q_n + 1));
-        MDBG_CK(c, cudaMemsetAsync(cnt_e.p + q_n, 0, 4, st));
-        MDBG_CK(c, cudaMemsetAsync(cnt_r.p + q_n, 0, 4, st));
+        Tmp<uint32_t> inv;
+        MDBG_CK(c, inv.get(c->pool, E2));
+        ke_inverse_kernel<<<nblk(E2), 256, 0, st>>>(sval, E2, inv);
+        LAUNCHED(c);
+        // The join decides every edge ONCE: kept edges / presimp removals are parked in fixed
+        // per-query slots together with their counts; one packed scan places them.  Only if some
+        // query outgrows its slots (flagged by the kernel) is the exact two-pass form run.
+        Tmp<uint64_t> cnt_q, off_q, cap_r;
+        Tmp<EdgeRec> cap_e;
+        MDBG_CK(c, cnt_q.get(c->pool, (uint64_t)q_n + 1)); MDBG_CK(c, off_q.get(c->pool, (uint64_t)q_n + 1));
+        MDBG_CK(c, cap_e.get(c->pool, (uint64_t)q_n * KE_CAP_E)); MDBG_CK(c, cap_r.get(c->pool, (uint64_t)q_n * KE_CAP_R));
+        MDBG_CK(c, cudaMemsetAsync(cnt_q.p + q_n, 0, 8, st));
+        MDBG_CK(c, cudaMemsetAsync(&c->d_sc->v[5], 0, 24, st));   // v[5] packed totals, v[6] overflow, v[7] kept edges
         uint32_t EP = 0, NR = 0;
+        bool overflow = false;
         if (q_n > 0) {
-            ke_join_kernel<false><<<nblk(q_n, 128), 128, 0, st>>>(NV, ekey, erev, skey, sval, presimp, q_lo, q_n, cnt_e, cnt_r,
-                                                                  nullptr, nullptr, nullptr, nullptr);
+            ke_join_kernel<0><<<nblk(q_n, 128), 128, 0, st>>>(NV, ekey, erev, skey, sval, inv, presimp, q_lo, q_n, cnt_q, nullptr,
+                                                              cap_e, cap_r, &c->d_sc->v[6]);
             LAUNCHED(c);
-            RC(R.cub([&](void* t, size_t& b) { return cub::DeviceScan::ExclusiveSum(t, b, cnt_e.p, off_e.p, q_n + 1, st); }));
-            RC(R.cub([&](void* t, size_t& b) { return cub::DeviceScan::ExclusiveSum(t, b, cnt_r.p, off_r.p, q_n + 1, st); }));
-            MDBG_CK(c, cudaMemcpyAsync(&c->h_sc->v[5], off_e.p + q_n, 4, cudaMemcpyDeviceToHost, st));
-            MDBG_CK(c, cudaMemcpyAsync(&c->h_sc->v[6], off_r.p + q_n, 4, cudaMemcpyDeviceToHost, st));
-            MDBG_CK(c, cudaStreamSynchronize(st));
+            RC(R.cub([&](void* t, size_t& b) { return cub::DeviceScan::ExclusiveSum(t, b, cnt_q.p, off_q.p, q_n + 1, st); }));
+            MDBG_CK(c, cudaMemcpyAsync(&c->d_sc->v[5], off_q.p + q_n, 8, cudaMemcpyDeviceToDevice, st));
+            RC(read_scalars(c));
             EP = (uint32_t)(c->h_sc->v[5] & 0xFFFFFFFFu);
-            NR = (uint32_t)(c->h_sc->v[6] & 0xFFFFFFFFu);
+            NR = (uint32_t)(c->h_sc->v[5] >> 32);
+            overflow = c->h_sc->v[6] != 0;
         }
         rem_local = presimp > 0.0f ? NR : 0;
         Tmp<EdgeRec> pend, kept;
         Tmp<uint64_t> removed;
         MDBG_CK(c, pend.get(c->pool, EP)); MDBG_CK(c, removed.get(c->pool, NR));
         if (EP > 0 || NR > 0) {
-            ke_join_kernel<true><<<nblk(q_n, 128), 128, 0, st>>>(NV, ekey, erev, skey, sval, presimp, q_lo, q_n, nullptr, nullptr,
-                                                                 off_e, off_r, pend, removed);
-            LAUNCHED(c);
-            if (EP > 0) {   // canonical order: nodes ascend already, sort each node's edges in place
-                ke_group_sort_kernel<<<nblk(q_n / 2), 256, 0, st>>>(pend, off_e, q_n / 2);
+            if (overflow) {
+                ke_join_kernel<1><<<nblk(q_n, 128), 128, 0, st>>>(NV, ekey, erev, skey, sval, inv, presimp, q_lo, q_n, nullptr,
+                                                                  off_q, pend, removed, nullptr);
+                LAUNCHED(c);
+                ke_group_sort_kernel<<<nblk(q_n / 2), 256, 0, st>>>(pend, off_q, q_n / 2);
+                LAUNCHED(c);
+            } else {   // canonical order: nodes ascend already, each node's edges are sorted while they move
+                ke_compact_kernel<<<nblk(q_n / 2), 256, 0, st>>>(cap_e, cap_r, cnt_q, off_q, q_n / 2, pend, removed);
                 LAUNCHED(c);
             }
         }
+        cap_e.reset(); cap_r.reset();
         // presimp removals of every GPU (an edge is dropped if it or its reverse was removed anywhere)
         std::vector<uint64_t> allNR;
         { uint64_t mine[1] = {NR}; RC(allgather_u64(c, mine, 1, allNR)); }

@@ -74,13 +74,32 @@ struct RecInfo {
 constexpr uint64_t ORD_REV = 1ull << 63;
 constexpr uint64_t ORD_MASK = ORD_REV - 1;
 
-// one thread per local k-min-mer ordinal g: orientation, ordinal, RecInfo, window location and (for
-// N > 1) the fingerprint that decides the owner.  The tuple itself is written by
-// kb_tuples_kernel, one thread per ELEMENT, so that the K x k x 8 bytes go out coalesced.
+// Where the canonical tuple of record j lives.  On the GPU that cut the windows a record is just a
+// window of the resident minimizer arena (wloc[j], read backwards when ord[j] says reversed): the
+// arena is ~2d x 8 bytes per base and stays in L2, so nothing is materialised.  After the exchange
+// (N > 1) the received tuples are a dense [K x k] array.
+struct TupleSrc {
+    const uint64_t* mat;    // [K * k] canonical tuples, or nullptr:
+    const uint64_t* hash;   //   arena hashes
+    const uint32_t* wloc;   //   [K] first arena element of the window
+    const uint64_t* ord;    //   [K] bit 63 = window is reversed
+    uint32_t k;
+    __device__ __forceinline__ void row(uint64_t j, const uint64_t*& p, int& step) const {
+        if (mat) { p = mat + j * k; step = 1; return; }
+        bool rv = (__ldg(ord + j) & ORD_REV) != 0;
+        p = hash + __ldg(wloc + j) + (rv ? k - 1 : 0);
+        step = rv ? -1 : 1;
+    }
+};
+
+// one thread per local k-min-mer ordinal g: orientation, ordinal, RecInfo, window location and a
+// fingerprint of the canonical tuple: fp_mode 1 = owner fingerprint (N > 1), 2 = table
+// fingerprint (masked, never KC_EMPTY; saves the separate kc_fp pass on one GPU), 0 = none.
 __global__ void kb_records_kernel(MinArena A, const uint64_t* __restrict__ kmer_off, uint64_t K, uint32_t k,
-                                  uint64_t seed, uint64_t ord_base, uint64_t read_base, int want_fp,
+                                  uint64_t seed, uint64_t fp_mask, uint64_t ord_base, uint64_t read_base, int fp_mode,
                                   uint32_t* __restrict__ wloc, uint64_t* __restrict__ ord,
-                                  RecInfo* __restrict__ info, uint64_t* __restrict__ fp) {
+                                  RecInfo* __restrict__ info, uint64_t* __restrict__ fp,
+                                  uint32_t* __restrict__ iota) {
     uint64_t g = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (g >= K) return;
     uint64_t r = owner_read(kmer_off, A.R, g);
@@ -89,11 +108,16 @@ __global__ void kb_records_kernel(MinArena A, const uint64_t* __restrict__ kmer_
     const uint64_t* h = A.hash + lo;
     const uint32_t* p = A.pos + lo;
     bool rv = window_reversed(h, k);
-    if (want_fp) {
+    if (fp_mode) {
         uint64_t f = fp_init(seed, k);
         for (uint32_t j = 0; j < k; j++) f = fp_mix(f, rv ? __ldg(h + k - 1 - j) : __ldg(h + j));
+        if (fp_mode == 2) {
+            f &= fp_mask;
+            if (f == KC_EMPTY) f = KC_EMPTY - 1;
+        }
         fp[g] = f;
     }
+    if (iota) iota[g] = (uint32_t)g;
     wloc[g] = (uint32_t)lo;
     ord[g] = (ord_base + g) | (rv ? ORD_REV : 0);
     RecInfo ri;
@@ -103,17 +127,6 @@ __global__ void kb_records_kernel(MinArena A, const uint64_t* __restrict__ kmer_
     ri.span = p[k - 1] - p[0];
     ri.read = read_base + r;
     info[g] = ri;
-}
-// canonical tuples, one thread per element (coalesced stores; the overlapping windows hit in L1/L2)
-__global__ void kb_tuples_kernel(const uint64_t* __restrict__ hash, const uint32_t* __restrict__ wloc,
-                                 const uint64_t* __restrict__ ord, uint64_t n_elem, uint32_t k,
-                                 uint64_t* __restrict__ tuple) {
-    uint64_t e = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (e >= n_elem) return;
-    uint64_t g = e / k;
-    uint32_t j = (uint32_t)(e - g * k);
-    bool rv = (__ldg(ord + g) & ORD_REV) != 0;
-    tuple[e] = __ldg(hash + __ldg(wloc + g) + (rv ? k - 1 - j : j));
 }
 
 // owner rank of a record: range partition on the fingerprint (mdbg_owner_of_fingerprint)
@@ -146,23 +159,27 @@ __global__ void kb_permute_kernel(const uint32_t* __restrict__ perm, uint64_t K,
     ri.read += read_add;
     info_o[j] = ri;
 }
-__global__ void kb_permute_tuples_kernel(const uint32_t* __restrict__ perm, uint64_t n_elem, uint32_t k,
-                                         const uint64_t* __restrict__ tuple, uint64_t* __restrict__ tuple_o) {
+// send-order tuples, one thread per ELEMENT (coalesced stores), read straight from the arena
+__global__ void kb_permute_tuples_kernel(const uint32_t* __restrict__ perm, uint64_t n_elem, TupleSrc T,
+                                         uint64_t* __restrict__ tuple_o) {
     uint64_t e = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (e >= n_elem) return;
-    uint64_t j = e / k;
-    uint32_t q = (uint32_t)(e - j * k);
-    tuple_o[e] = __ldg(tuple + (uint64_t)__ldg(perm + j) * k + q);
+    uint64_t j = e / T.k;
+    uint32_t q = (uint32_t)(e - j * T.k);
+    const uint64_t* p; int step;
+    T.row(__ldg(perm + j), p, step);
+    tuple_o[e] = __ldg(p + (int64_t)q * step);
 }
 
-// table fingerprint of the (already canonical) received tuples
-__global__ void kc_fp_kernel(const uint64_t* __restrict__ tuple, uint64_t K, uint32_t k, uint64_t seed,
-                             uint64_t fp_mask, uint64_t* __restrict__ fp, uint32_t* __restrict__ iota) {
+// table fingerprint of the canonical tuples
+__global__ void kc_fp_kernel(TupleSrc T, uint64_t K, uint64_t seed, uint64_t fp_mask, uint64_t* __restrict__ fp,
+                             uint32_t* __restrict__ iota) {
     uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (j >= K) return;
-    const uint64_t* t = tuple + j * k;
-    uint64_t f = fp_init(seed, k);
-    for (uint32_t q = 0; q < k; q++) f = fp_mix(f, __ldg(t + q));
+    const uint64_t* t; int step;
+    T.row(j, t, step);
+    uint64_t f = fp_init(seed, T.k);
+    for (uint32_t q = 0; q < T.k; q++) f = fp_mix(f, __ldg(t + (int64_t)q * step));
     f &= fp_mask;
     if (f == KC_EMPTY) f = KC_EMPTY - 1;
     fp[j] = f;
@@ -232,17 +249,17 @@ __global__ void kc_insert_kernel(const uint64_t* __restrict__ fp, uint64_t K, ui
 }
 
 // exactness: every record must carry the same TUPLE as the first record of its slot
-__global__ void kc_verify_kernel(const uint64_t* __restrict__ tuple, uint64_t K, uint32_t k,
-                                 const uint32_t* __restrict__ slot, const uint32_t* __restrict__ first,
-                                 unsigned long long* collisions) {
+__global__ void kc_verify_kernel(TupleSrc T, uint64_t K, const uint32_t* __restrict__ slot,
+                                 const uint32_t* __restrict__ first, unsigned long long* collisions) {
     uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (j >= K) return;
     uint32_t f = __ldg(first + __ldg(slot + j));
     if (f == j) return;
-    const uint64_t* a = tuple + j * k;
-    const uint64_t* b = tuple + (uint64_t)f * k;
+    const uint64_t *a, *b; int sa, sb;
+    T.row(j, a, sa);
+    T.row(f, b, sb);
     bool same = true;
-    for (uint32_t q = 0; q < k && same; q++) same = __ldg(a + q) == __ldg(b + q);
+    for (uint32_t q = 0; q < T.k && same; q++) same = __ldg(a + (int64_t)q * sa) == __ldg(b + (int64_t)q * sb);
     if (!same) atomicAdd(collisions, 1ull);
 }
 
@@ -264,19 +281,31 @@ __global__ void kd_segments_kernel(const uint32_t* __restrict__ seg_start, uint3
                                    const uint32_t* __restrict__ sj, const uint64_t* __restrict__ ord,
                                    uint32_t minab, uint32_t bf, uint64_t* __restrict__ first_ord,
                                    uint8_t* __restrict__ counted, uint8_t* __restrict__ solid,
-                                   uint32_t* __restrict__ nseq) {
+                                   uint32_t* __restrict__ nseq, uint8_t* __restrict__ ord_flags) {
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= D) return;
     uint32_t st = seg_start[s];
     uint32_t en = (s + 1 < D) ? seg_start[s + 1] : (uint32_t)K;
     uint32_t cnt = en - st;
     const bool in_table = !bf || cnt >= 2;
-    first_ord[s] = in_table ? (ord[sj[st + (bf ? 1 : 0)]] & ORD_MASK) : ORD_MASK;
+    const uint64_t fo = in_table ? (ord[sj[st + (bf ? 1 : 0)]] & ORD_MASK) : ORD_MASK;
+    first_ord[s] = fo;
     counted[s] = in_table ? 1 : 0;
     uint32_t ab = cnt & 0xFFFFu;
-    solid[s] = (minab == 1 || ab >= minab) ? 1 : 0;
+    const bool sol = (minab == 1 || ab >= minab);
+    solid[s] = sol ? 1 : 0;
     nseq[s] = cnt >= minab ? 1 + (cnt - minab) / 65536u : 0;
+    // one GPU: ordinals are local (< K), so "how many tuples were first seen earlier" is a prefix
+    // sum over ordinal space: bit 0 = this ordinal consumed a node index, bit 1 = ... of a solid node
+    if (ord_flags && in_table) ord_flags[fo] = (uint8_t)(1 | (sol ? 2 : 0));
 }
+
+// u8 flag pair -> packed u64 counters (low 32: index consumers, high 32: solid nodes) for ONE scan
+struct FlagPairToU64 {
+    __host__ __device__ __forceinline__ uint64_t operator()(uint8_t f) const {
+        return (uint64_t)(f & 1u) | ((uint64_t)((f >> 1) & 1u) << 32);
+    }
+};
 
 // node index = number of distinct tuples (on any GPU) first seen earlier: sum over the W sorted
 // first-sighting lists of lower_bound(first_ord)
@@ -297,15 +326,16 @@ __global__ void kd_index_kernel(const uint64_t* __restrict__ first_ord, uint32_t
 
 struct NodeRec { uint32_t index, seqlen; uint16_t abundance, shift0, shift1, pad; };
 
-// solid nodes of this owner (arbitrary order; sorted by index afterwards)
-__global__ void kd_nodes_kernel(uint32_t S, uint32_t k, uint32_t minab, uint64_t K, uint32_t D,
+// solid nodes of this owner (arbitrary order; sorted by index afterwards) -- N > 1
+__global__ void kd_nodes_kernel(uint32_t S, uint32_t minab, uint64_t K, uint32_t D,
                                 const uint32_t* __restrict__ solid_seg, const uint32_t* __restrict__ seg_start,
                                 const uint32_t* __restrict__ sj, const uint32_t* __restrict__ seg_index,
-                                const uint64_t* __restrict__ tuple, const uint64_t* __restrict__ ord,
+                                TupleSrc T, const uint64_t* __restrict__ ord,
                                 const RecInfo* __restrict__ info, NodeRec* __restrict__ node,
                                 uint64_t* __restrict__ node_tuple) {
     uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= S) return;
+    const uint32_t k = T.k;
     uint32_t s = solid_seg[n];
     uint32_t st = seg_start[s];
     uint32_t en = (s + 1 < D) ? seg_start[s + 1] : (uint32_t)K;
@@ -322,8 +352,46 @@ __global__ void kd_nodes_kernel(uint32_t S, uint32_t k, uint32_t minab, uint64_t
     o.shift1 = (uint16_t)(rv ? ri.d01 : ri.dlast);
     o.pad = 0;
     node[n] = o;
-    const uint64_t* t = tuple + (uint64_t)sj[st] * k;
-    for (uint32_t q = 0; q < k; q++) node_tuple[(uint64_t)n * k + q] = t[q];
+    const uint64_t* t; int step;
+    T.row(sj[st], t, step);
+    for (uint32_t q = 0; q < k; q++) node_tuple[(uint64_t)n * k + q] = t[(int64_t)q * step];
+}
+
+// One GPU: the exclusive scan of the ordinal flags gives, at a tuple's first sighting, its node
+// index (low half) and -- because index order IS first-sighting order -- the position of a solid
+// node in the ascending-index node list (high half): nodes are written in place, no sort.
+// One thread per distinct tuple; also leaves every tuple's index in seg_index (for .sequences).
+struct NodeOut { uint32_t* index; uint16_t* abundance; uint32_t* seqlen; uint16_t* shift; uint64_t* tuple; };
+__global__ void kd_nodes_direct_kernel(uint32_t D, uint32_t minab, uint64_t K,
+                                       const uint32_t* __restrict__ seg_start, const uint32_t* __restrict__ sj,
+                                       const uint64_t* __restrict__ first_ord, const uint8_t* __restrict__ counted,
+                                       const uint8_t* __restrict__ solid, const uint64_t* __restrict__ rank64,
+                                       TupleSrc T, const uint64_t* __restrict__ ord,
+                                       const RecInfo* __restrict__ info, uint32_t* __restrict__ seg_index,
+                                       NodeOut O) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= D) return;
+    if (!counted[s]) { seg_index[s] = 0xFFFFFFFFu; return; }
+    const uint64_t rk = rank64[first_ord[s]];
+    const uint32_t index = (uint32_t)rk, n = (uint32_t)(rk >> 32);
+    seg_index[s] = index;
+    if (!solid[s]) return;
+    const uint32_t k = T.k;
+    uint32_t st = seg_start[s];
+    uint32_t en = (s + 1 < D) ? seg_start[s + 1] : (uint32_t)K;
+    uint32_t cnt = en - st;
+    uint32_t rep_rank = (minab - 1) + 65536u * ((cnt - minab) / 65536u);  // last overwrite, main.rs:680-684
+    uint32_t j = sj[st + rep_rank];
+    bool rv = (ord[j] & ORD_REV) != 0;
+    RecInfo ri = info[j];
+    O.index[n] = index;
+    O.seqlen[n] = ri.span + 2;                                      // read_offsets.2, main.rs:778
+    O.abundance[n] = (uint16_t)(cnt & 0xFFFFu);
+    O.shift[2 * n] = (uint16_t)(rv ? ri.dlast : ri.d01);            // lowprec_shift, main.rs:675
+    O.shift[2 * n + 1] = (uint16_t)(rv ? ri.d01 : ri.dlast);
+    const uint64_t* t; int step;
+    T.row(sj[st], t, step);
+    for (uint32_t q = 0; q < k; q++) O.tuple[(uint64_t)n * k + q] = t[(int64_t)q * step];
 }
 
 struct SeqRec { uint64_t ord; uint32_t index, pad; uint64_t read, start, end, shift0, shift1; };
@@ -434,15 +502,25 @@ __device__ __forceinline__ bool eq_range(const uint64_t* a, int sa, const uint64
     return true;
 }
 
-// One thread per (n1, key) with key in [suffix_norm, prefix_norm] (main.rs:1050-1052).  WRITE=false
-// counts kept edges / presimp removals, WRITE=true emits them at the scanned offsets.
-template <bool WRITE>
+// position of every entry in the key-sorted list (so a query finds its bucket without a search)
+__global__ void ke_inverse_kernel(const uint32_t* __restrict__ sval, uint32_t n, uint32_t* __restrict__ inv) {
+    uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m < n) inv[sval[m]] = m;
+}
+
+// One thread per (n1, key) with key in [suffix_norm, prefix_norm] (main.rs:1050-1052).
+//   MODE 0 (capture): decide the edges once, park up to KE_CAP_E kept edges / KE_CAP_R presimp
+//          removals of the query in fixed slots, write the packed counts (edges | removals << 32);
+//          a query that needs more raises *overflow and the host falls back to MODE 1
+//   MODE 1 (write): emit at the scanned packed offsets (exact, any bucket size)
+constexpr uint32_t KE_CAP_E = 8, KE_CAP_R = 4;
+template <int MODE>
 __global__ void ke_join_kernel(NodeView N, const uint64_t* __restrict__ ekey, const uint8_t* __restrict__ erev,
                                const uint64_t* __restrict__ skey, const uint32_t* __restrict__ sval,
-                               float presimp, uint32_t q_lo, uint32_t q_n,
-                               uint32_t* __restrict__ cnt_edge, uint32_t* __restrict__ cnt_rem,
-                               const uint32_t* __restrict__ off_edge, const uint32_t* __restrict__ off_rem,
-                               EdgeRec* __restrict__ edges, uint64_t* __restrict__ removed) {
+                               const uint32_t* __restrict__ inv, float presimp, uint32_t q_lo, uint32_t q_n,
+                               uint64_t* __restrict__ cnt, const uint64_t* __restrict__ off,
+                               EdgeRec* __restrict__ edges, uint64_t* __restrict__ removed,
+                               unsigned long long* __restrict__ overflow) {
     // queries [q_lo, q_lo + q_n) of the 2S (n1, key) pairs: the slice of nodes this GPU emits edges for
     uint32_t qq = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t S = N.S, k = N.k, k1 = k - 1;
@@ -451,20 +529,19 @@ __global__ void ke_join_kernel(NodeView N, const uint64_t* __restrict__ ekey, co
     uint32_t n1 = q >> 1, which = q & 1;
     uint32_t qe = 2 * n1 + (which == 0 ? 1 : 0);  // which 0: suffix entry, 1: prefix entry
     uint64_t kf = ekey[qe];
-    // bucket [lo, hi) of equal fingerprints in the sorted entry list
-    uint32_t lo = 0, hi = 2 * S;
-    while (lo < hi) { uint32_t m = (lo + hi) >> 1; if (skey[m] < kf) lo = m + 1; else hi = m; }
-    uint32_t b0 = lo;
-    hi = 2 * S;
-    while (lo < hi) { uint32_t m = (lo + hi) >> 1; if (skey[m] <= kf) lo = m + 1; else hi = m; }
-    uint32_t b1 = lo;
+    // bucket [b0, b1) of equal fingerprints around the query's own entry in the sorted list
+    uint32_t b0 = inv[qe], b1 = b0 + 1;
+    while (b0 > 0 && skey[b0 - 1] == kf) b0--;
+    while (b1 < 2 * S && skey[b1] == kf) b1++;
     const uint64_t* t1 = N.tuple + (uint64_t)n1 * k;
     const uint64_t* qsub = t1 + (qe & 1);
     bool qrev = erev[qe];
     uint32_t ab1 = N.abundance[n1];
     // pass 0: number of potential edges and max abundance; pass 1: decide each edge
     uint32_t npot = 0, abmax = 0, ne = 0, nr = 0;
-    uint32_t oe = WRITE ? off_edge[qq] : 0, orr = WRITE ? off_rem[qq] : 0;
+    const uint64_t o64 = MODE == 1 ? off[qq] : 0;
+    const uint32_t oe = MODE == 1 ? (uint32_t)o64 : qq * KE_CAP_E;
+    const uint32_t orr = MODE == 1 ? (uint32_t)(o64 >> 32) : qq * KE_CAP_R;
     for (int pass = 0; pass < 2; pass++) {
         uint32_t abref = abmax < ab1 ? abmax : ab1;
         for (uint32_t e = b0; e < b1; e++) {
@@ -487,11 +564,11 @@ __global__ void ke_join_kernel(NodeView N, const uint64_t* __restrict__ ekey, co
                 if (!t[o]) continue;
                 if (pass == 0) { npot++; abmax = ab2 > abmax ? ab2 : abmax; continue; }
                 if (presimp > 0.0f && npot >= 2 && (float)ab2 < presimp * (float)abref) {  // main.rs:1086
-                    if (WRITE) removed[orr + nr] = ((uint64_t)N.index[n1] << 32) | N.index[n2];
+                    if (MODE == 1 || nr < KE_CAP_R) removed[orr + nr] = ((uint64_t)N.index[n1] << 32) | N.index[n2];
                     nr++;
                     continue;
                 }
-                if (WRITE) {
+                if (MODE == 1 || ne < KE_CAP_E) {
                     uint32_t sh = (o < 2) ? N.shift[2 * n1] : N.shift[2 * n1 + 1];
                     uint32_t a = N.seqlen[n1] - sh, b = N.seqlen[n2] - 1;  // main.rs:1091-1092
                     EdgeRec r;
@@ -504,7 +581,10 @@ __global__ void ke_join_kernel(NodeView N, const uint64_t* __restrict__ ekey, co
         }
         if (npot == 0) break;
     }
-    if (!WRITE) { cnt_edge[qq] = ne; cnt_rem[qq] = nr; }
+    if (MODE == 0) {
+        cnt[qq] = (uint64_t)ne | ((uint64_t)nr << 32);
+        if (ne > KE_CAP_E || nr > KE_CAP_R) atomicAdd(overflow, 1ull);
+    }
 }
 
 // The join emits the edges of node n1 contiguously and nodes in ascending index order, so the
@@ -516,16 +596,35 @@ __device__ __forceinline__ bool edge_less(const EdgeRec& a, const EdgeRec& b) {
     if (a.o2 != b.o2) return a.o2 < b.o2;
     return a.ov < b.ov;
 }
-__global__ void ke_group_sort_kernel(EdgeRec* __restrict__ edges, const uint32_t* __restrict__ off_edge, uint32_t n_nodes) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_nodes) return;
-    uint32_t lo = off_edge[2 * i], hi = off_edge[2 * i + 2];
+__device__ __forceinline__ void edge_group_sort(EdgeRec* __restrict__ edges, uint32_t lo, uint32_t hi) {
     for (uint32_t a = lo + 1; a < hi; a++) {
         EdgeRec x = edges[a];
         uint32_t b = a;
         while (b > lo && edge_less(x, edges[b - 1])) { edges[b] = edges[b - 1]; b--; }
         edges[b] = x;
     }
+}
+// after MODE 1: off = packed exclusive offsets per query (2 per node)
+__global__ void ke_group_sort_kernel(EdgeRec* __restrict__ edges, const uint64_t* __restrict__ off, uint32_t n_nodes) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    edge_group_sort(edges, (uint32_t)off[2 * i], (uint32_t)off[2 * i + 2]);
+}
+// after MODE 0 without overflow: move the parked edges / removals of a node's two queries to their
+// scanned places and sort the node's edges; one thread per node
+__global__ void ke_compact_kernel(const EdgeRec* __restrict__ cap_e, const uint64_t* __restrict__ cap_r,
+                                  const uint64_t* __restrict__ cnt, const uint64_t* __restrict__ off,
+                                  uint32_t n_nodes, EdgeRec* __restrict__ edges, uint64_t* __restrict__ removed) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    for (uint32_t w = 0; w < 2; w++) {
+        const uint32_t qq = 2 * i + w;
+        const uint64_t c = cnt[qq], o = off[qq];
+        const uint32_t ne = (uint32_t)c, nr = (uint32_t)(c >> 32), oe = (uint32_t)o, orr = (uint32_t)(o >> 32);
+        for (uint32_t t = 0; t < ne; t++) edges[oe + t] = cap_e[qq * KE_CAP_E + t];
+        for (uint32_t t = 0; t < nr; t++) removed[orr + t] = cap_r[qq * KE_CAP_R + t];
+    }
+    edge_group_sort(edges, (uint32_t)off[2 * i], (uint32_t)off[2 * i + 2]);
 }
 
 // keep[e] = 0 if (n1,n2) or (n2,n1) was presimp-removed (main.rs:1109)

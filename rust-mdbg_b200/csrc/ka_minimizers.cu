@@ -215,9 +215,17 @@ __device__ __forceinline__ uint64_t find_read(const uint64_t* __restrict__ read_
 }  // namespace
 
 // tile_lb[i] = first r in [0, R] with read_off[r] >= i*TILE; tile_lb[n_tiles] = R+1.
+// The same launch resets the batch's device counters (a kernel, not cudaMemsetAsync / an H2D copy:
+// those may be served by the copy engine and would queue behind the bulk upload that K-A is
+// supposed to overlap).
 __global__ void ka_tile_lb_kernel(const uint64_t* __restrict__ read_off, uint64_t R, uint64_t n_tiles,
-                                  uint64_t* __restrict__ tile_lb) {
+                                  uint64_t* __restrict__ tile_lb, KAInit I) {
     uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i == 0) {
+        *I.total_out = 0; *I.err_pos = ~0ull; *I.stage_counter = 0; *I.dense_tiles = 0;
+        for (uint32_t j = 0; j < I.n_counters; j++) I.counters[j] = 0;
+        if (I.zero64) *I.zero64 = 0;
+    }
     if (i > n_tiles) return;
     if (i == n_tiles) { tile_lb[i] = R + 1; return; }
     uint64_t target = i * (uint64_t)TILE;
@@ -692,20 +700,16 @@ __global__ void ka_finalize_kernel(const KAArgs A, const uint64_t* __restrict__ 
 }
 
 // ---- host launchers ------------------------------------------------------------------------
-cudaError_t ka_prepare(const KAArgs& A, cudaStream_t st, uint64_t* launches) {
+cudaError_t ka_prepare(const KAArgs& A, const KAInit& I, cudaStream_t st, uint64_t* launches) {
     uint64_t nt = A.n_tiles;
-    cudaError_t e = cudaMemsetAsync(A.stage_counter, 0, sizeof(unsigned long long), st);
-    if (e != cudaSuccess) return e;
     unsigned nb = (unsigned)((nt + 1 + 255) / 256);
-    ka_tile_lb_kernel<<<nb, 256, 0, st>>>(A.read_off, A.n_reads, nt, A.tile_lb);
+    ka_tile_lb_kernel<<<nb, 256, 0, st>>>(A.read_off, A.n_reads, nt, A.tile_lb, I);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }
 
 cudaError_t ka_launch(const KAArgs& A, int hpc, int grid, cudaStream_t st, uint64_t* launches) {
-    if (A.tile_end <= A.tile_begin) return cudaSuccess;
-    cudaError_t e = cudaMemsetAsync(A.tile_counter, 0, sizeof(uint32_t), st);
-    if (e != cudaSuccess) return e;
+    if (A.tile_end <= A.tile_begin) return cudaSuccess;   // A.tile_counter: zeroed by ka_prepare, one per launch
     uint64_t warps = A.tile_end - A.tile_begin;
     uint64_t need = (warps + NWARP - 1) / NWARP;
     unsigned g = (unsigned)(need < (uint64_t)grid ? need : (uint64_t)grid);

@@ -42,7 +42,13 @@ struct KAArgs {
     uint64_t tile_begin, tile_end;   // tiles handled by this launch (chunked, overlapped uploads)
 };
 // prepare: per-tile read lookup + counters; launch: tiles [A.tile_begin, A.tile_end); finalize: order
-cudaError_t ka_prepare(const KAArgs& A, cudaStream_t st, uint64_t* launches);
+// device counters reset by ka_prepare: the batch scalars, one tile counter per K-A launch of the
+// batch, and optionally one u64 (the first read offset of an empty arena)
+struct KAInit {
+    unsigned long long* total_out; unsigned long long* err_pos; unsigned long long* stage_counter;
+    unsigned int* dense_tiles; unsigned int* counters; uint32_t n_counters; uint64_t* zero64;
+};
+cudaError_t ka_prepare(const KAArgs& A, const KAInit& I, cudaStream_t st, uint64_t* launches);
 cudaError_t ka_launch(const KAArgs& A, int hpc, int grid, cudaStream_t st, uint64_t* launches);
 cudaError_t ka_finalize(const KAArgs& A, const uint64_t* tile_excl, cudaStream_t st, uint64_t* launches);
 int ka_max_blocks_per_sm(int hpc);

@@ -47,7 +47,7 @@ class CTimings(ctypes.Structure):
                                               "ms_d2h", "ms_total_push", "ms_total_finish")] + \
                [("launches_push", u64), ("launches_finish", u64), ("ka_launches", u64),
                 ("ka_ms_sum", ctypes.c_float), ("table_attempts", u32), ("ka_dense_tiles", u32),
-                ("ms_ka_kernel", ctypes.c_float)]
+                ("ms_ka_kernel", ctypes.c_float), ("ms_ka_start", ctypes.c_float)]
 
 
 class CSynth(ctypes.Structure):
