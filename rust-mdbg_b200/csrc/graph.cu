@@ -104,24 +104,6 @@ int allgather_u64(mdbg_ctx* c, const uint64_t* mine, int n, std::vector<uint64_t
     return MDBG_OK;
 }
 
-// variable all-to-all of `elem`-byte items: send_cnt[d] items to rank d (send buffer grouped by
-// destination), recv_cnt[s] items from rank s (receive buffer grouped by source)
-int alltoallv(mdbg_ctx* c, const void* send, const uint64_t* send_cnt, void* recv, const uint64_t* recv_cnt,
-              size_t elem) {
-    const int W = c->world;
-    NcclApi& N = nccl();
-    size_t so = 0, ro = 0;
-    NCK(c, N.GroupStart());
-    for (int p = 0; p < W; p++) {
-        if (send_cnt[p]) NCK(c, N.Send((const char*)send + so, send_cnt[p] * elem, ncclChar, p, (ncclComm_t)c->comm, c->st));
-        if (recv_cnt[p]) NCK(c, N.Recv((char*)recv + ro, recv_cnt[p] * elem, ncclChar, p, (ncclComm_t)c->comm, c->st));
-        so += send_cnt[p] * elem;
-        ro += recv_cnt[p] * elem;
-    }
-    NCK(c, N.GroupEnd());
-    return MDBG_OK;
-}
-
 // all-gather of variable-length arrays: every rank ends with the concatenation in rank order
 int allgatherv(mdbg_ctx* c, const void* mine, uint64_t my_cnt, const std::vector<uint64_t>& cnt, void* out,
                size_t elem) {
@@ -182,151 +164,119 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
     if (W > 1 && !c->comm) { c->err = "world > 1 but mdbg_comm_init was not called"; return MDBG_ERR_BAD_ARG; }
     if (c->M >= 0xFFFFFFF0ull) { c->err = "more than 2^32 minimizers on one GPU"; return MDBG_ERR_RANGE; }
     MDBG_CK(c, cudaEventRecord(c->ev[5], st));
+    // ---- the minimizer arena of the whole job ---------------------------------------------------
+    // N > 1: the per-GPU arenas (~2d x 12 bytes per base) are all-gathered, so every GPU sees every
+    // window of the job in serial order; nothing larger is ever exchanged.
     MinArena A{c->m_hash, c->m_pos, c->m_off, c->R};
-    const uint64_t nR = c->R;
+    Tmp<uint64_t> g_hash, g_off, d_rmap;
+    Tmp<uint32_t> g_pos;
+    const uint64_t* d_rpre = nullptr; const uint64_t* d_rbase = nullptr;
+    if (W > 1) {
+        std::vector<uint64_t> all;
+        uint64_t mine[3] = {c->M, c->R, c->read_base_set ? c->read_base : ~0ull};
+        RC(allgather_u64(c, mine, 3, all));
+        std::vector<uint64_t> mcnt(W), rcnt(W), rmap(3 * (size_t)W + 2, 0);   // rpre[W+1] | mpre[W+1] | rbase[W]
+        uint64_t* rpre = rmap.data(); uint64_t* mpre = rpre + W + 1; uint64_t* rbase = mpre + W + 1;
+        for (int r = 0; r < W; r++) {
+            mcnt[r] = all[3 * r]; rcnt[r] = all[3 * r + 1];
+            mpre[r + 1] = mpre[r] + mcnt[r]; rpre[r + 1] = rpre[r] + rcnt[r];
+            rbase[r] = all[3 * r + 2] != ~0ull ? all[3 * r + 2] : rpre[r];
+        }
+        const uint64_t Mtot = mpre[W], Rtot = rpre[W];
+        if (Mtot >= 0xFFFFFFF0ull) { c->err = "more than 2^32 minimizers in the job"; return MDBG_ERR_RANGE; }
+        MDBG_CK(c, g_hash.get(c->pool, Mtot)); MDBG_CK(c, g_pos.get(c->pool, Mtot)); MDBG_CK(c, g_off.get(c->pool, Rtot + 1));
+        MDBG_CK(c, d_rmap.get(c->pool, rmap.size()));
+        MDBG_CK(c, cudaMemcpyAsync(d_rmap, rmap.data(), rmap.size() * 8, cudaMemcpyHostToDevice, st));
+        NCK(c, nccl().GroupStart());
+        RC(allgatherv(c, c->m_hash, c->M, mcnt, g_hash, 8));
+        RC(allgatherv(c, c->m_pos, c->M, mcnt, g_pos, 4));
+        RC(allgatherv(c, c->m_off, c->R, rcnt, g_off, 8));
+        NCK(c, nccl().GroupEnd());
+        d_rpre = d_rmap.p; d_rbase = d_rmap.p + 2 * (W + 1);
+        kb_rebase_off_kernel<<<nblk(Rtot + 1), 256, 0, st>>>(g_off, Rtot, d_rpre, d_rmap.p + (W + 1), (uint32_t)W);
+        LAUNCHED(c);
+        A = MinArena{g_hash, g_pos, g_off, Rtot};
+    }
+    const uint64_t nR = A.R;
 
     // ---- K-B: records -------------------------------------------------------------------------
     Tmp<uint64_t> cnt, kmer_off;
     MDBG_CK(c, cnt.get(c->pool, nR + 1));
     MDBG_CK(c, kmer_off.get(c->pool, nR + 1));
-    uint64_t Kl = 0;  // local sightings
-    if (nR > 0 && c->M > 0) {
-        kb_count_kernel<<<nblk(nR + 1), 256, 0, st>>>(c->m_off, nR, k, cnt);
+    uint64_t Ktot = 0;  // sightings of the whole job (serial ordinals are 0 .. Ktot-1)
+    if (nR > 0) {
+        kb_count_kernel<<<nblk(nR + 1), 256, 0, st>>>(A.off, nR, k, cnt);
         LAUNCHED(c);
         RC(R.cub([&](void* t, size_t& b) { return cub::DeviceScan::ExclusiveSum(t, b, cnt.p, kmer_off.p, nR + 1, st); }));
         MDBG_CK(c, cudaMemcpyAsync(&c->h_sc->v[0], kmer_off.p + nR, 8, cudaMemcpyDeviceToHost, st));
         MDBG_CK(c, cudaStreamSynchronize(st));
-        Kl = c->h_sc->v[0];
+        Ktot = c->h_sc->v[0];
     }
-    if (Kl >= 0x7FFFFFF0ull) { c->err = "more than 2^31 k-min-mers on one GPU"; return MDBG_ERR_RANGE; }
-    // Records are produced with LOCAL ordinals / read indices; with N > 1 the global bases are
-    // added when the records are packed for sending (they come out of the same all-gather as the
-    // exchange counts, one host round trip for both).
-    uint64_t Ktot = Kl;
-    Tmp<uint64_t> l_ord, l_fp;
-    Tmp<RecInfo> l_info;
+    if (Ktot >= 0x7FFFFFF0ull) { c->err = "more than 2^31 k-min-mers in the job"; return MDBG_ERR_RANGE; }
+    G->n_kminmers = Ktot;
+    const int ord_bits = std::max(1, log2_ceil(Ktot + 1));   // serial ordinals are < Ktot
+    // records this GPU owns: all of them on one GPU; with N > 1 the windows whose tuple fingerprint
+    // falls into this rank's range (every copy of a tuple meets on one owner), in ordinal order
+    uint64_t K = Ktot;
+    Tmp<uint32_t> own_g;
+    if (W > 1 && Ktot > 0) {
+        Tmp<uint8_t> own;
+        MDBG_CK(c, own.get(c->pool, Ktot)); MDBG_CK(c, own_g.get(c->pool, Ktot));
+        kb_own_kernel<<<nblk(Ktot), 256, 0, st>>>(A, kmer_off, Ktot, k, 0x6d64626700000000ull, (uint32_t)W, (uint32_t)rank, own);
+        LAUNCHED(c);
+        RC(R.cub([&](void* t, size_t& b) {
+            return cub::DeviceSelect::Flagged(t, b, cub::CountingInputIterator<uint32_t>(0), own.p, own_g.p,
+                                              (uint32_t*)&c->d_sc->v[0], (uint32_t)Ktot, st);
+        }));
+        RC(read_scalars(c));
+        K = c->h_sc->v[0] & 0xFFFFFFFFu;
+    }
+    Tmp<uint64_t> r_ord_t, fp;
+    Tmp<RecInfo> r_info_t;
     Tmp<uint32_t> wloc, iota;
-    MDBG_CK(c, l_ord.get(c->pool, Kl));
-    MDBG_CK(c, l_info.get(c->pool, Kl));
-    MDBG_CK(c, l_fp.get(c->pool, Kl));
-    MDBG_CK(c, wloc.get(c->pool, Kl));
-    if (W == 1) MDBG_CK(c, iota.get(c->pool, Kl));
-    // The canonical tuples are NOT materialised on the GPU that cut the windows: a record is a
-    // window of the (L2-resident) minimizer arena, read through TupleSrc.  On one GPU the same
-    // pass also computes the table fingerprint of the first seed.
+    MDBG_CK(c, r_ord_t.get(c->pool, K)); MDBG_CK(c, r_info_t.get(c->pool, K)); MDBG_CK(c, fp.get(c->pool, K));
+    MDBG_CK(c, wloc.get(c->pool, K)); MDBG_CK(c, iota.get(c->pool, K));
+    // The canonical tuples are never materialised: a record is a window of the (L2-resident)
+    // arena, read through TupleSrc.  The same pass computes the table fingerprint of the first seed.
     const uint64_t table_seed0 = 0x7461626c65000000ull;
     uint64_t fp_mask0 = ~0ull;
     if (c->p.debug_fp_bits > 0 && c->p.debug_fp_bits < 64) fp_mask0 = (1ull << c->p.debug_fp_bits) - 1;
-    if (Kl) {
-        kb_records_kernel<<<nblk(Kl), 256, 0, st>>>(A, kmer_off, Kl, k, W == 1 ? table_seed0 : 0x6d64626700000000ull,
-                                                    fp_mask0, 0, W == 1 ? c->read_base : 0, W == 1 ? 2 : 1, wloc, l_ord,
-                                                    l_info, l_fp, W == 1 ? iota.p : nullptr);
+    if (K) {
+        kb_records_kernel<<<nblk(K), 256, 0, st>>>(A, kmer_off, K, k, W > 1 ? own_g.p : nullptr, table_seed0, fp_mask0, d_rpre,
+                                                   d_rbase, (uint32_t)W, c->read_base, wloc, r_ord_t, r_info_t, fp, iota);
         LAUNCHED(c);
     }
-    const TupleSrc local_src{nullptr, c->m_hash, wloc.p, l_ord.p, k};
-    cnt.reset();
-    kmer_off.reset();
-
-    // ---- exchange: all copies of a tuple meet on the owner of its fingerprint range -------------
-    uint64_t K = Kl;  // records this GPU owns
-    Tmp<uint64_t> x_tuple, x_ord;
-    Tmp<RecInfo> x_info;
-    uint64_t* r_ord = l_ord; RecInfo* r_info = l_info;
-    TupleSrc T = local_src;
-    if (W > 1) {
-        Tmp<uint32_t> owner, owner_s, iota, perm;
-        Tmp<uint64_t> s_tuple, s_ord;
-        Tmp<RecInfo> s_info;
-        Tmp<unsigned long long> d_start;
-        MDBG_CK(c, owner.get(c->pool, Kl)); MDBG_CK(c, owner_s.get(c->pool, Kl));
-        MDBG_CK(c, iota.get(c->pool, Kl)); MDBG_CK(c, perm.get(c->pool, Kl));
-        MDBG_CK(c, s_tuple.get(c->pool, Kl * k)); MDBG_CK(c, s_ord.get(c->pool, Kl)); MDBG_CK(c, s_info.get(c->pool, Kl));
-        MDBG_CK(c, d_start.get(c->pool, W + 1));
-        if (Kl) {
-            kb_owner_kernel<<<nblk(Kl), 256, 0, st>>>(l_fp, Kl, (uint32_t)W, owner, iota);
-            LAUNCHED(c);
-            RC(R.cub([&](void* t, size_t& b) {   // stable: ordinal order is kept inside every destination
-                return cub::DeviceRadixSort::SortPairs(t, b, owner.p, owner_s.p, iota.p, perm.p, (uint32_t)Kl, 0,
-                                                       std::max(1, log2_ceil(W)), st);
-            }));
-        }
-        kb_owner_counts_kernel<<<nblk(Kl + 1), 256, 0, st>>>(owner_s, Kl, (uint32_t)W, d_start);
-        LAUNCHED(c);
-        std::vector<unsigned long long> h_start(W + 1);
-        MDBG_CK(c, cudaMemcpyAsync(h_start.data(), d_start, (W + 1) * 8, cudaMemcpyDeviceToHost, st));
-        MDBG_CK(c, cudaStreamSynchronize(st));
-        std::vector<uint64_t> mine(W + 2), mat;
-        mine[0] = Kl; mine[1] = c->R;
-        for (int p = 0; p < W; p++) mine[2 + p] = h_start[p + 1] - h_start[p];
-        RC(allgather_u64(c, mine.data(), W + 2, mat));
-        const size_t row = (size_t)W + 2;
-        uint64_t ord_base = 0, read_base = 0;
-        Ktot = 0;
-        for (int r = 0; r < W; r++) {
-            if (r < rank) { ord_base += mat[r * row]; read_base += mat[r * row + 1]; }
-            Ktot += mat[r * row];
-        }
-        if (c->read_base_set) read_base = c->read_base;
-        std::vector<uint64_t> send_cnt(W), recv_cnt(W);
-        K = 0;
-        for (int p = 0; p < W; p++) {
-            send_cnt[p] = mine[2 + p];
-            recv_cnt[p] = mat[p * row + 2 + rank];
-            K += recv_cnt[p];
-        }
-        if (K >= 0x7FFFFFF0ull) { c->err = "more than 2^31 k-min-mers owned by one GPU"; return MDBG_ERR_RANGE; }
-        if (Kl) {
-            kb_permute_kernel<<<nblk(Kl), 256, 0, st>>>(perm, Kl, ord_base, read_base, l_ord, l_info, s_ord, s_info);
-            LAUNCHED(c);
-            kb_permute_tuples_kernel<<<nblk(Kl * k), 256, 0, st>>>(perm, Kl * k, local_src, s_tuple);
-            LAUNCHED(c);
-        }
-        MDBG_CK(c, x_tuple.get(c->pool, K * k)); MDBG_CK(c, x_ord.get(c->pool, K)); MDBG_CK(c, x_info.get(c->pool, K));
-        std::vector<uint64_t> sc_t(W), rc_t(W);
-        for (int p = 0; p < W; p++) { sc_t[p] = send_cnt[p] * k; rc_t[p] = recv_cnt[p] * k; }
-        NCK(c, nccl().GroupStart());   // ONE fused all-to-all for the three record arrays
-        RC(alltoallv(c, s_tuple, sc_t.data(), x_tuple, rc_t.data(), 8));
-        RC(alltoallv(c, s_ord, send_cnt.data(), x_ord, recv_cnt.data(), 8));
-        RC(alltoallv(c, s_info, send_cnt.data(), x_info, recv_cnt.data(), sizeof(RecInfo)));
-        NCK(c, nccl().GroupEnd());
-        r_ord = x_ord; r_info = x_info;
-        T = TupleSrc{x_tuple.p, nullptr, nullptr, nullptr, k};
-        l_ord.reset(); l_info.reset(); wloc.reset();
-    }
-    G->n_kminmers = Ktot;
-    const int ord_bits = std::max(1, log2_ceil(Ktot + 1));   // serial ordinals are < Ktot
-    if (W > 1) l_fp.reset();
+    const uint64_t* r_ord = r_ord_t; const RecInfo* r_info = r_info_t;
+    const TupleSrc T{A.hash, wloc.p, r_ord_t.p, k};
+    cnt.reset(); kmer_off.reset(); own_g.reset();
     MDBG_CK(c, cudaEventRecord(c->ev[6], st));
 
     // ---- K-C table + K-D sort by slot (retry with a new seed on a fingerprint collision) ---------
-    uint32_t D = 0, S_local = 0, Q_local = 0;
-    Tmp<uint32_t> slot, first, sslot, sj, seg_start, seg_index, solid_seg, nseq, seq_off;
+    uint32_t D = 0, Q_local = 0;
+    Tmp<uint32_t> slot, first, sslot, sj, seg_start, seg_index, nseq, seq_off;
     Tmp<uint64_t> first_ord;
     Tmp<uint8_t> solid;
     const int cap_bits = std::max(12, log2_ceil(2 * std::max<uint64_t>(K, 1)));
     if (K > 0) {
-        Tmp<uint64_t> fp, keys;
+        Tmp<uint64_t> keys;
         Tmp<uint8_t> head;
         const uint64_t cap = 1ull << cap_bits;
-        if (W > 1) { MDBG_CK(c, fp.get(c->pool, K)); MDBG_CK(c, iota.get(c->pool, K)); }
         MDBG_CK(c, slot.get(c->pool, K));
-        uint64_t* fpv = W == 1 ? l_fp.p : fp.p;   // one GPU: attempt 0 came out of kb_records
         MDBG_CK(c, keys.get(c->pool, cap)); MDBG_CK(c, first.get(c->pool, cap));
         MDBG_CK(c, sslot.get(c->pool, K)); MDBG_CK(c, sj.get(c->pool, K));
         MDBG_CK(c, head.get(c->pool, K)); MDBG_CK(c, seg_start.get(c->pool, K + 1));
         for (int attempt = 0;; attempt++) {
             if (attempt >= 8) { c->err = "fingerprint collisions persisted over 8 seeds"; return MDBG_ERR_RANGE; }
             c->tm.table_attempts = attempt + 1;
-            uint64_t seed = table_seed0 + 0x9e3779b97f4a7c15ull * (uint64_t)attempt;
-            uint64_t mask = attempt == 0 ? fp_mask0 : ~0ull;
-            if (W > 1 || attempt > 0) {
-                kc_fp_kernel<<<nblk(K), 256, 0, st>>>(T, K, seed, mask, fpv, iota);
+            if (attempt > 0) {   // attempt 0 came out of kb_records
+                uint64_t seed = table_seed0 + 0x9e3779b97f4a7c15ull * (uint64_t)attempt;
+                kc_fp_kernel<<<nblk(K), 256, 0, st>>>(T, K, seed, ~0ull, fp, iota);
                 LAUNCHED(c);
             }
             MDBG_CK(c, cudaMemsetAsync(keys, 0xFF, cap * 8, st));
             MDBG_CK(c, cudaMemsetAsync(first, 0xFF, cap * 4, st));
             MDBG_CK(c, cudaMemsetAsync(&c->d_sc->v[1], 0, 8, st));
-            kc_insert_kernel<<<nblk(K * 4), 256, 0, st>>>(fpv, K, keys, first, cap - 1, slot);
+            kc_insert_kernel<<<nblk(K * 4), 256, 0, st>>>(fp, K, keys, first, cap - 1, slot);
             LAUNCHED(c);
             kc_verify_kernel<<<nblk(K), 256, 0, st>>>(T, K, slot, first, &c->d_sc->v[1]);
             LAUNCHED(c);
@@ -347,143 +297,83 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
         D = (uint32_t)(c->h_sc->v[2] & 0xFFFFFFFFu);
     }
     MDBG_CK(c, cudaEventRecord(c->ev[7], st));   // ms_kc = table + sort by slot, ms_kd = reduce + nodes
-    slot.reset(); first.reset(); iota.reset(); sslot.reset(); l_fp.reset();
+    slot.reset(); first.reset(); iota.reset(); sslot.reset(); fp.reset();
     MDBG_CK(c, first_ord.get(c->pool, D)); MDBG_CK(c, solid.get(c->pool, D)); MDBG_CK(c, nseq.get(c->pool, (uint64_t)D + 1));
     MDBG_CK(c, seq_off.get(c->pool, (uint64_t)D + 1)); MDBG_CK(c, seg_index.get(c->pool, D));
     Tmp<uint8_t> counted;
     MDBG_CK(c, counted.get(c->pool, D));
-    uint32_t Dc = D;   // tuples that are in the table (all of them without --bf)
     uint64_t Dtot = 0, Stot = 0, Qtot = 0;
-    if (W == 1) {
-        // ---- one GPU: ordinals are local, so the node index and the place of a solid node in the
-        // ascending-index node list both come out of ONE prefix sum over ordinal space; nodes are
-        // written in place (no sort of first sightings, no binary searches, no sort of nodes)
+    {
+        // ---- node index and node placement from ONE prefix sum over ordinal space -----------------
+        // Every distinct tuple marks the ordinal of its first sighting (bit 0: it consumed a node
+        // index, bit 1: it is a solid node).  N > 1: the flag arrays are summed over the GPUs (an
+        // ordinal belongs to one tuple, hence one owner).  The exclusive scan then holds, at that
+        // ordinal, the tuple's node index and the place of the node in the ascending-index list:
+        // no sort of first sightings, no binary searches, no sort of nodes.
         Tmp<uint8_t> ord_flags;
         Tmp<uint64_t> rank64;
-        MDBG_CK(c, ord_flags.get(c->pool, K + 1)); MDBG_CK(c, rank64.get(c->pool, K + 1));
+        MDBG_CK(c, ord_flags.get(c->pool, Ktot + 1)); MDBG_CK(c, rank64.get(c->pool, Ktot + 1));
+        MDBG_CK(c, cudaMemsetAsync(ord_flags.p, 0, Ktot + 1, st));
+        MDBG_CK(c, cudaMemsetAsync(&c->d_sc->v[3], 0, 16, st));
         if (D > 0) {
-            MDBG_CK(c, cudaMemsetAsync(ord_flags.p, 0, K + 1, st));
             kd_segments_kernel<<<nblk(D), 256, 0, st>>>(seg_start, D, K, sj, r_ord, minab, bf, first_ord, counted, solid, nseq,
                                                         ord_flags);
             LAUNCHED(c);
-            RC(R.cub([&](void* t, size_t& b) {
-                cub::TransformInputIterator<uint64_t, FlagPairToU64, const uint8_t*> in(ord_flags.p, FlagPairToU64());
-                return cub::DeviceScan::ExclusiveSum(t, b, in, rank64.p, (uint32_t)(K + 1), st);
-            }));
-            MDBG_CK(c, cudaMemcpyAsync(&c->d_sc->v[3], rank64.p + K, 8, cudaMemcpyDeviceToDevice, st));
-            MDBG_CK(c, cudaMemsetAsync(&c->d_sc->v[4], 0, 8, st));
-            if (want_seqlines) {
-                MDBG_CK(c, cudaMemsetAsync(nseq.p + D, 0, 4, st));
-                RC(R.cub([&](void* t, size_t& b) { return cub::DeviceScan::ExclusiveSum(t, b, nseq.p, seq_off.p, D + 1, st); }));
-                MDBG_CK(c, cudaMemcpyAsync(&c->d_sc->v[4], seq_off.p + D, 4, cudaMemcpyDeviceToDevice, st));
-            }
-            RC(read_scalars(c));   // v[3] = tuples in the table | solid nodes << 32, v[4] = .sequences lines
-            Dc = (uint32_t)(c->h_sc->v[3] & 0xFFFFFFFFu);
-            S_local = (uint32_t)(c->h_sc->v[3] >> 32);
-            Q_local = (uint32_t)(c->h_sc->v[4] & 0xFFFFFFFFu);
         }
-        Dtot = Dc; Stot = S_local; Qtot = Q_local;
+        if (W > 1) NCK(c, nccl().AllReduce(ord_flags.p, ord_flags.p, Ktot + 1, ncclUint8, ncclSum, (ncclComm_t)c->comm, st));
+        RC(R.cub([&](void* t, size_t& b) {
+            cub::TransformInputIterator<uint64_t, FlagPairToU64, const uint8_t*> in(ord_flags.p, FlagPairToU64());
+            return cub::DeviceScan::ExclusiveSum(t, b, in, rank64.p, (uint32_t)(Ktot + 1), st);
+        }));
+        MDBG_CK(c, cudaMemcpyAsync(&c->d_sc->v[3], rank64.p + Ktot, 8, cudaMemcpyDeviceToDevice, st));
+        if (want_seqlines && D > 0) {
+            MDBG_CK(c, cudaMemsetAsync(nseq.p + D, 0, 4, st));
+            RC(R.cub([&](void* t, size_t& b) { return cub::DeviceScan::ExclusiveSum(t, b, nseq.p, seq_off.p, D + 1, st); }));
+            MDBG_CK(c, cudaMemcpyAsync(&c->d_sc->v[4], seq_off.p + D, 4, cudaMemcpyDeviceToDevice, st));
+        }
+        RC(read_scalars(c));   // v[3] = tuples in the table | solid nodes << 32 (job-wide), v[4] = own .sequences lines
+        Dtot = c->h_sc->v[3] & 0xFFFFFFFFu;
+        Stot = c->h_sc->v[3] >> 32;
+        Q_local = (uint32_t)(c->h_sc->v[4] & 0xFFFFFFFFu);
+        Qtot = Q_local;
+        if (W > 1 && want_seqlines) {
+            std::vector<uint64_t> allQ;
+            uint64_t mineq[1] = {Q_local};
+            RC(allgather_u64(c, mineq, 1, allQ));
+            Qtot = 0;
+            for (int r = 0; r < W; r++) Qtot += allQ[r];
+        }
+        if (Stot >= 0x7FFFFFF0ull) { c->err = "more than 2^31 nodes"; return MDBG_ERR_RANGE; }
         G->n_distinct = Dtot; G->n_nodes = Stot; G->n_seqlines = want_seqlines ? Qtot : 0;
-        MDBG_CK(c, G->index.get(c->pool, Stot)); MDBG_CK(c, G->abundance.get(c->pool, Stot));
+        // node arrays: every GPU writes the nodes it owns at their final places; N > 1: the arrays
+        // (zero elsewhere) are summed so that every GPU holds all nodes for the edge stage
+        const uint64_t Sp = Stot + (Stot & 1);   // u16 arrays are reduced as u32 words
+        MDBG_CK(c, G->index.get(c->pool, Stot)); MDBG_CK(c, G->abundance.get(c->pool, Sp));
         MDBG_CK(c, G->seqlen.get(c->pool, Stot)); MDBG_CK(c, G->shift.get(c->pool, 2 * Stot));
         MDBG_CK(c, G->tuple.get(c->pool, Stot * k));
+        if (W > 1 && Stot > 0) {
+            MDBG_CK(c, cudaMemsetAsync(G->index.p, 0, Stot * 4, st)); MDBG_CK(c, cudaMemsetAsync(G->abundance.p, 0, Sp * 2, st));
+            MDBG_CK(c, cudaMemsetAsync(G->seqlen.p, 0, Stot * 4, st)); MDBG_CK(c, cudaMemsetAsync(G->shift.p, 0, Stot * 4, st));
+            MDBG_CK(c, cudaMemsetAsync(G->tuple.p, 0, Stot * k * 8, st));
+        }
         if (D > 0) {
             NodeOut NO{G->index, G->abundance, G->seqlen, G->shift, G->tuple};
             kd_nodes_direct_kernel<<<nblk(D), 256, 0, st>>>(D, minab, K, seg_start, sj, first_ord, counted, solid, rank64, T,
                                                             r_ord, r_info, seg_index, NO);
             LAUNCHED(c);
         }
+        if (W > 1 && Stot > 0) {
+            ncclComm_t cm = (ncclComm_t)c->comm;
+            NCK(c, nccl().GroupStart());
+            NCK(c, nccl().AllReduce(G->index.p, G->index.p, Stot, ncclUint32, ncclSum, cm, st));
+            NCK(c, nccl().AllReduce(G->abundance.p, G->abundance.p, Sp / 2, ncclUint32, ncclSum, cm, st));
+            NCK(c, nccl().AllReduce(G->seqlen.p, G->seqlen.p, Stot, ncclUint32, ncclSum, cm, st));
+            NCK(c, nccl().AllReduce(G->shift.p, G->shift.p, Stot, ncclUint32, ncclSum, cm, st));
+            NCK(c, nccl().AllReduce(G->tuple.p, G->tuple.p, Stot * k, ncclUint64, ncclSum, cm, st));
+            NCK(c, nccl().GroupEnd());
+        }
         first_ord.reset(); solid.reset();
-    } else {
-    MDBG_CK(c, solid_seg.get(c->pool, D));
-    Tmp<uint64_t> first_sorted;
-    MDBG_CK(c, first_sorted.get(c->pool, D));
-    if (D > 0) {
-        kd_segments_kernel<<<nblk(D), 256, 0, st>>>(seg_start, D, K, sj, r_ord, minab, bf, first_ord, counted, solid, nseq,
-                                                    nullptr);
-        LAUNCHED(c);
-        // sorted list of the index-consuming sightings (uncounted ones carry ORD_MASK and sort last)
-        RC(R.cub([&](void* t, size_t& b) { return cub::DeviceRadixSort::SortKeys(t, b, first_ord.p, first_sorted.p, D, 0, bf ? 63 : ord_bits, st); }));
-        if (bf) {
-            Tmp<uint32_t> cidx;
-            MDBG_CK(c, cidx.get(c->pool, D));
-            RC(R.cub([&](void* t, size_t& b) {
-                return cub::DeviceSelect::Flagged(t, b, cub::CountingInputIterator<uint32_t>(0), counted.p, cidx.p,
-                                                  (uint32_t*)&c->d_sc->v[8], D, st);
-            }));
-        }
-        RC(R.cub([&](void* t, size_t& b) {
-            return cub::DeviceSelect::Flagged(t, b, cub::CountingInputIterator<uint32_t>(0), solid.p, solid_seg.p,
-                                              (uint32_t*)&c->d_sc->v[3], D, st);
-        }));
-        MDBG_CK(c, cudaMemsetAsync(nseq.p + D, 0, 4, st));
-        RC(R.cub([&](void* t, size_t& b) { return cub::DeviceScan::ExclusiveSum(t, b, nseq.p, seq_off.p, D + 1, st); }));
-        MDBG_CK(c, cudaMemcpyAsync(&c->d_sc->v[4], seq_off.p + D, 4, cudaMemcpyDeviceToDevice, st));
-        RC(read_scalars(c));   // v[3] = solid count, v[4] = .sequences lines, v[8] = tuples in the table (--bf)
-        if (bf) Dc = (uint32_t)(c->h_sc->v[8] & 0xFFFFFFFFu);
-        S_local = (uint32_t)(c->h_sc->v[3] & 0xFFFFFFFFu);
-        Q_local = (uint32_t)(c->h_sc->v[4] & 0xFFFFFFFFu);
     }
-    // node index: first sightings of every GPU, sorted per GPU
-    std::vector<uint64_t> allD;
-    { uint64_t mine[3] = {Dc, S_local, Q_local}; RC(allgather_u64(c, mine, 3, allD)); }
-    std::vector<uint64_t> dcnt(W), scnt(W), qcnt(W), loff(W + 1, 0);
-    for (int r = 0; r < W; r++) {
-        dcnt[r] = allD[3 * r]; scnt[r] = allD[3 * r + 1]; qcnt[r] = allD[3 * r + 2];
-        Dtot += dcnt[r]; Stot += scnt[r]; Qtot += qcnt[r];
-        loff[r + 1] = loff[r] + dcnt[r];
-    }
-    if (Dtot >= 0xFFFFFFF0ull) { c->err = "more than 2^32 distinct k-min-mers"; return MDBG_ERR_RANGE; }
-    const int idx_bits = std::max(1, log2_ceil(Dtot + 1));   // node indices are < Dtot
-    G->n_distinct = Dtot; G->n_nodes = Stot; G->n_seqlines = want_seqlines ? Qtot : 0;
-    {
-        Tmp<uint64_t> all_first, d_loff;
-        MDBG_CK(c, all_first.get(c->pool, Dtot)); MDBG_CK(c, d_loff.get(c->pool, W + 1));
-        RC(allgatherv(c, first_sorted, Dc, dcnt, all_first, 8));
-        MDBG_CK(c, cudaMemcpyAsync(d_loff, loff.data(), (W + 1) * 8, cudaMemcpyHostToDevice, st));
-        if (D > 0) {
-            kd_index_kernel<<<nblk(D), 256, 0, st>>>(first_ord, D, all_first, d_loff, (uint32_t)W, seg_index);
-            LAUNCHED(c);
-        }
-    }
-    first_sorted.reset(); first_ord.reset(); solid.reset();
-
-    // solid nodes of this owner -> all GPUs, ascending index
-    MDBG_CK(c, G->index.get(c->pool, Stot)); MDBG_CK(c, G->abundance.get(c->pool, Stot));
-    MDBG_CK(c, G->seqlen.get(c->pool, Stot)); MDBG_CK(c, G->shift.get(c->pool, 2 * Stot));
-    MDBG_CK(c, G->tuple.get(c->pool, Stot * k));
-    if (Stot >= 0x7FFFFFF0ull) { c->err = "more than 2^31 nodes"; return MDBG_ERR_RANGE; }
-    {
-        Tmp<NodeRec> my_nodes, all_nodes;
-        Tmp<uint64_t> my_tuple, all_tuple;
-        MDBG_CK(c, my_nodes.get(c->pool, S_local)); MDBG_CK(c, my_tuple.get(c->pool, (uint64_t)S_local * k));
-        if (S_local > 0) {
-            kd_nodes_kernel<<<nblk(S_local), 256, 0, st>>>(S_local, minab, K, D, solid_seg, seg_start, sj, seg_index,
-                                                           T, r_ord, r_info, my_nodes, my_tuple);
-            LAUNCHED(c);
-        }
-        MDBG_CK(c, all_nodes.get(c->pool, Stot)); MDBG_CK(c, all_tuple.get(c->pool, Stot * k));
-        std::vector<uint64_t> tcnt(W);
-        for (int r = 0; r < W; r++) tcnt[r] = scnt[r] * k;
-        NCK(c, nccl().GroupStart());
-        RC(allgatherv(c, my_nodes, S_local, scnt, all_nodes, sizeof(NodeRec)));
-        RC(allgatherv(c, my_tuple, (uint64_t)S_local * k, tcnt, all_tuple, 8));
-        NCK(c, nccl().GroupEnd());
-        if (Stot > 0) {
-            Tmp<uint32_t> nkey, nkey_s, nid, nid_s;
-            MDBG_CK(c, nkey.get(c->pool, Stot)); MDBG_CK(c, nkey_s.get(c->pool, Stot));
-            MDBG_CK(c, nid.get(c->pool, Stot)); MDBG_CK(c, nid_s.get(c->pool, Stot));
-            kd_node_keys_kernel<<<nblk(Stot), 256, 0, st>>>(all_nodes, (uint32_t)Stot, nkey, nid);
-            LAUNCHED(c);
-            RC(R.cub([&](void* t, size_t& b) {
-                return cub::DeviceRadixSort::SortPairs(t, b, nkey.p, nkey_s.p, nid.p, nid_s.p, (uint32_t)Stot, 0, idx_bits, st);
-            }));
-            kd_unpack_nodes_kernel<<<nblk(Stot), 256, 0, st>>>(all_nodes, nid_s, (uint32_t)Stot, k, all_tuple, G->index,
-                                                               G->abundance, G->seqlen, G->shift, G->tuple);
-            LAUNCHED(c);
-        }
-    }
-    }   // W > 1
     // .sequences lines of this owner, in ordinal (= emission) order
     G->n_seq_local = 0;
     if (want_seqlines) {
@@ -507,8 +397,8 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
     }
     MDBG_CK(c, cudaEventRecord(c->ev[8], st));
     // free table-stage scratch before the edge stage
-    nseq.reset(); seq_off.reset(); seg_index.reset(); solid_seg.reset(); seg_start.reset(); sj.reset();
-    x_tuple.reset(); x_ord.reset(); x_info.reset(); wloc.reset(); l_ord.reset(); l_info.reset();
+    nseq.reset(); seq_off.reset(); seg_index.reset(); seg_start.reset(); sj.reset();
+    wloc.reset(); r_ord_t.reset(); r_info_t.reset(); g_hash.reset(); g_pos.reset(); g_off.reset();
 
     // ---- K-E: edges of this GPU's slice of the nodes ----------------------------------------------
     uint32_t E = 0;

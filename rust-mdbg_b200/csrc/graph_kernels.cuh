@@ -74,101 +74,92 @@ struct RecInfo {
 constexpr uint64_t ORD_REV = 1ull << 63;
 constexpr uint64_t ORD_MASK = ORD_REV - 1;
 
-// Where the canonical tuple of record j lives.  On the GPU that cut the windows a record is just a
-// window of the resident minimizer arena (wloc[j], read backwards when ord[j] says reversed): the
-// arena is ~2d x 8 bytes per base and stays in L2, so nothing is materialised.  After the exchange
-// (N > 1) the received tuples are a dense [K x k] array.
+// Where the canonical tuple of record j lives: nowhere of its own.  A record is a window of the
+// minimizer arena (wloc[j], read backwards when ord[j] says reversed); the arena is ~2d x 12 bytes
+// per base and stays in L2, so the K x k x 8 bytes of tuples are never materialised.  With N GPUs
+// the arena is the all-gathered arena of the whole job, so this also holds for the owner of a
+// tuple whose sightings came from other GPUs.
 struct TupleSrc {
-    const uint64_t* mat;    // [K * k] canonical tuples, or nullptr:
-    const uint64_t* hash;   //   arena hashes
-    const uint32_t* wloc;   //   [K] first arena element of the window
-    const uint64_t* ord;    //   [K] bit 63 = window is reversed
+    const uint64_t* hash;   // arena hashes
+    const uint32_t* wloc;   // [K] first arena element of the window
+    const uint64_t* ord;    // [K] bit 63 = window is reversed
     uint32_t k;
     __device__ __forceinline__ void row(uint64_t j, const uint64_t*& p, int& step) const {
-        if (mat) { p = mat + j * k; step = 1; return; }
         bool rv = (__ldg(ord + j) & ORD_REV) != 0;
         p = hash + __ldg(wloc + j) + (rv ? k - 1 : 0);
         step = rv ? -1 : 1;
     }
 };
 
-// one thread per local k-min-mer ordinal g: orientation, ordinal, RecInfo, window location and a
-// fingerprint of the canonical tuple: fp_mode 1 = owner fingerprint (N > 1), 2 = table
-// fingerprint (masked, never KC_EMPTY; saves the separate kc_fp pass on one GPU), 0 = none.
+// N > 1, after the arenas were all-gathered: the per-rank read offsets become offsets into the
+// concatenated arena.  rpre = prefix of reads per rank [W+1], mpre = prefix of minimizers [W+1].
+__global__ void kb_rebase_off_kernel(uint64_t* __restrict__ off, uint64_t R, const uint64_t* __restrict__ rpre,
+                                     const uint64_t* __restrict__ mpre, uint32_t world) {
+    uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (r > R) return;
+    if (r == R) { off[R] = mpre[world]; return; }
+    uint32_t w = 0;
+    while (w + 1 < world && rpre[w + 1] <= r) w++;
+    off[r] += mpre[w];
+}
+
+// N > 1: own[g] = 1 if this GPU owns the tuple of window g (range partition on the tuple
+// fingerprint, mdbg_owner_of_fingerprint).  Every GPU scans all windows of the job -- two passes
+// over an L2-resident arena -- instead of shipping K x k x 8 bytes of tuples through an all-to-all.
+__global__ void kb_own_kernel(MinArena A, const uint64_t* __restrict__ kmer_off, uint64_t K, uint32_t k,
+                              uint64_t seed, uint32_t world, uint32_t rank, uint8_t* __restrict__ own) {
+    uint64_t g = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (g >= K) return;
+    uint64_t r = owner_read(kmer_off, A.R, g);
+    uint64_t lo = __ldg(A.off + r) + (g - __ldg(kmer_off + r));
+    const uint64_t* h = A.hash + lo;
+    bool rv = window_reversed(h, k);
+    uint64_t f = fp_init(seed, k);
+    for (uint32_t j = 0; j < k; j++) f = fp_mix(f, rv ? __ldg(h + k - 1 - j) : __ldg(h + j));
+    own[g] = (uint32_t)__umul64hi(f, (uint64_t)world) == rank ? 1 : 0;
+}
+
+// One thread per record j of this GPU (window g = own[j], or j itself on one GPU): orientation,
+// ordinal (= g: windows are numbered in serial (read, i) order over the whole job), RecInfo, window
+// location and the table fingerprint of the first seed (masked, never KC_EMPTY).
+//   read id: reads of rank w are numbered rbase[w] + (r - rpre[w])  (one GPU: base0 + r)
 __global__ void kb_records_kernel(MinArena A, const uint64_t* __restrict__ kmer_off, uint64_t K, uint32_t k,
-                                  uint64_t seed, uint64_t fp_mask, uint64_t ord_base, uint64_t read_base, int fp_mode,
+                                  const uint32_t* __restrict__ own, uint64_t seed, uint64_t fp_mask,
+                                  const uint64_t* __restrict__ rpre, const uint64_t* __restrict__ rbase,
+                                  uint32_t world, uint64_t base0,
                                   uint32_t* __restrict__ wloc, uint64_t* __restrict__ ord,
                                   RecInfo* __restrict__ info, uint64_t* __restrict__ fp,
                                   uint32_t* __restrict__ iota) {
-    uint64_t g = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (g >= K) return;
+    uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (j >= K) return;
+    uint64_t g = own ? (uint64_t)__ldg(own + j) : j;
     uint64_t r = owner_read(kmer_off, A.R, g);
     uint64_t i = g - __ldg(kmer_off + r);
     uint64_t lo = __ldg(A.off + r) + i;
     const uint64_t* h = A.hash + lo;
     const uint32_t* p = A.pos + lo;
     bool rv = window_reversed(h, k);
-    if (fp_mode) {
-        uint64_t f = fp_init(seed, k);
-        for (uint32_t j = 0; j < k; j++) f = fp_mix(f, rv ? __ldg(h + k - 1 - j) : __ldg(h + j));
-        if (fp_mode == 2) {
-            f &= fp_mask;
-            if (f == KC_EMPTY) f = KC_EMPTY - 1;
-        }
-        fp[g] = f;
+    uint64_t f = fp_init(seed, k);
+    for (uint32_t q = 0; q < k; q++) f = fp_mix(f, rv ? __ldg(h + k - 1 - q) : __ldg(h + q));
+    f &= fp_mask;
+    if (f == KC_EMPTY) f = KC_EMPTY - 1;
+    fp[j] = f;
+    iota[j] = (uint32_t)j;
+    wloc[j] = (uint32_t)lo;
+    ord[j] = g | (rv ? ORD_REV : 0);
+    uint64_t read = base0 + r;
+    if (world > 1) {
+        uint32_t w = 0;
+        while (w + 1 < world && __ldg(rpre + w + 1) <= r) w++;
+        read = __ldg(rbase + w) + (r - __ldg(rpre + w));
     }
-    if (iota) iota[g] = (uint32_t)g;
-    wloc[g] = (uint32_t)lo;
-    ord[g] = (ord_base + g) | (rv ? ORD_REV : 0);
     RecInfo ri;
     ri.p0 = p[0];
     ri.d01 = p[1] - p[0];
     ri.dlast = p[k - 1] - p[k - 2];
     ri.span = p[k - 1] - p[0];
-    ri.read = read_base + r;
-    info[g] = ri;
-}
-
-// owner rank of a record: range partition on the fingerprint (mdbg_owner_of_fingerprint)
-__global__ void kb_owner_kernel(const uint64_t* __restrict__ fp, uint64_t K, uint32_t world,
-                                uint32_t* __restrict__ owner, uint32_t* __restrict__ iota) {
-    uint64_t g = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (g >= K) return;
-    owner[g] = (uint32_t)__umul64hi(fp[g], (uint64_t)world);
-    iota[g] = (uint32_t)g;
-}
-// owner_sorted is ascending: cnt[w] = #records of owner w (one thread per boundary)
-__global__ void kb_owner_counts_kernel(const uint32_t* __restrict__ owner_sorted, uint64_t K, uint32_t world,
-                                       unsigned long long* __restrict__ start /* [world+1] */) {
-    uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (j > K) return;
-    uint32_t cur = j < K ? owner_sorted[j] : world;
-    uint32_t prev = j > 0 ? owner_sorted[j - 1] : 0;
-    if (j == 0) { for (uint32_t w = 0; w <= cur && w <= world; w++) start[w] = 0; }
-    else for (uint32_t w = prev + 1; w <= cur && w <= world; w++) start[w] = j;
-}
-// gather records into send order: ord / info per record, tuples per ELEMENT (coalesced stores)
-__global__ void kb_permute_kernel(const uint32_t* __restrict__ perm, uint64_t K, uint64_t ord_add, uint64_t read_add,
-                                  const uint64_t* __restrict__ ord, const RecInfo* __restrict__ info,
-                                  uint64_t* __restrict__ ord_o, RecInfo* __restrict__ info_o) {
-    uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (j >= K) return;
-    uint32_t g = perm[j];
-    ord_o[j] = ord[g] + ord_add;      // local -> global serial ordinal (bit 63 keeps the reversed flag)
-    RecInfo ri = info[g];
-    ri.read += read_add;
-    info_o[j] = ri;
-}
-// send-order tuples, one thread per ELEMENT (coalesced stores), read straight from the arena
-__global__ void kb_permute_tuples_kernel(const uint32_t* __restrict__ perm, uint64_t n_elem, TupleSrc T,
-                                         uint64_t* __restrict__ tuple_o) {
-    uint64_t e = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (e >= n_elem) return;
-    uint64_t j = e / T.k;
-    uint32_t q = (uint32_t)(e - j * T.k);
-    const uint64_t* p; int step;
-    T.row(__ldg(perm + j), p, step);
-    tuple_o[e] = __ldg(p + (int64_t)q * step);
+    ri.read = read;
+    info[j] = ri;
 }
 
 // table fingerprint of the canonical tuples
@@ -295,9 +286,10 @@ __global__ void kd_segments_kernel(const uint32_t* __restrict__ seg_start, uint3
     const bool sol = (minab == 1 || ab >= minab);
     solid[s] = sol ? 1 : 0;
     nseq[s] = cnt >= minab ? 1 + (cnt - minab) / 65536u : 0;
-    // one GPU: ordinals are local (< K), so "how many tuples were first seen earlier" is a prefix
-    // sum over ordinal space: bit 0 = this ordinal consumed a node index, bit 1 = ... of a solid node
-    if (ord_flags && in_table) ord_flags[fo] = (uint8_t)(1 | (sol ? 2 : 0));
+    // "how many tuples were first seen earlier" is a prefix sum over ordinal space: bit 0 = this
+    // ordinal consumed a node index, bit 1 = ... of a solid node (N > 1: the flag arrays of the
+    // GPUs are summed, every ordinal belongs to one tuple and so to one owner)
+    if (in_table) ord_flags[fo] = (uint8_t)(1 | (sol ? 2 : 0));
 }
 
 // u8 flag pair -> packed u64 counters (low 32: index consumers, high 32: solid nodes) for ONE scan
@@ -307,60 +299,11 @@ struct FlagPairToU64 {
     }
 };
 
-// node index = number of distinct tuples (on any GPU) first seen earlier: sum over the W sorted
-// first-sighting lists of lower_bound(first_ord)
-__global__ void kd_index_kernel(const uint64_t* __restrict__ first_ord, uint32_t D,
-                                const uint64_t* __restrict__ all_first, const uint64_t* __restrict__ list_off,
-                                uint32_t world, uint32_t* __restrict__ index) {
-    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= D) return;
-    uint64_t x = first_ord[s], acc = 0;
-    for (uint32_t w = 0; w < world; w++) {
-        uint64_t lo = list_off[w], hi = list_off[w + 1];
-        const uint64_t base = lo;
-        while (lo < hi) { uint64_t m = (lo + hi) >> 1; if (__ldg(all_first + m) < x) lo = m + 1; else hi = m; }
-        acc += lo - base;
-    }
-    index[s] = (uint32_t)acc;
-}
-
-struct NodeRec { uint32_t index, seqlen; uint16_t abundance, shift0, shift1, pad; };
-
-// solid nodes of this owner (arbitrary order; sorted by index afterwards) -- N > 1
-__global__ void kd_nodes_kernel(uint32_t S, uint32_t minab, uint64_t K, uint32_t D,
-                                const uint32_t* __restrict__ solid_seg, const uint32_t* __restrict__ seg_start,
-                                const uint32_t* __restrict__ sj, const uint32_t* __restrict__ seg_index,
-                                TupleSrc T, const uint64_t* __restrict__ ord,
-                                const RecInfo* __restrict__ info, NodeRec* __restrict__ node,
-                                uint64_t* __restrict__ node_tuple) {
-    uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= S) return;
-    const uint32_t k = T.k;
-    uint32_t s = solid_seg[n];
-    uint32_t st = seg_start[s];
-    uint32_t en = (s + 1 < D) ? seg_start[s + 1] : (uint32_t)K;
-    uint32_t cnt = en - st;
-    uint32_t rep_rank = (minab - 1) + 65536u * ((cnt - minab) / 65536u);  // last overwrite, main.rs:680-684
-    uint32_t j = sj[st + rep_rank];
-    bool rv = (ord[j] & ORD_REV) != 0;
-    RecInfo ri = info[j];
-    NodeRec o;
-    o.index = seg_index[s];
-    o.seqlen = ri.span + 2;                                   // read_offsets.2, main.rs:778
-    o.abundance = (uint16_t)(cnt & 0xFFFFu);
-    o.shift0 = (uint16_t)(rv ? ri.dlast : ri.d01);            // lowprec_shift, main.rs:675
-    o.shift1 = (uint16_t)(rv ? ri.d01 : ri.dlast);
-    o.pad = 0;
-    node[n] = o;
-    const uint64_t* t; int step;
-    T.row(sj[st], t, step);
-    for (uint32_t q = 0; q < k; q++) node_tuple[(uint64_t)n * k + q] = t[(int64_t)q * step];
-}
-
-// One GPU: the exclusive scan of the ordinal flags gives, at a tuple's first sighting, its node
+// The exclusive scan of the (job-wide) ordinal flags gives, at a tuple's first sighting, its node
 // index (low half) and -- because index order IS first-sighting order -- the position of a solid
-// node in the ascending-index node list (high half): nodes are written in place, no sort.
-// One thread per distinct tuple; also leaves every tuple's index in seg_index (for .sequences).
+// node in the ascending-index node list (high half): nodes are written in place, no sort, no
+// binary searches.  One thread per distinct tuple of this GPU; also leaves every tuple's index in
+// seg_index (for .sequences).
 struct NodeOut { uint32_t* index; uint16_t* abundance; uint32_t* seqlen; uint16_t* shift; uint64_t* tuple; };
 __global__ void kd_nodes_direct_kernel(uint32_t D, uint32_t minab, uint64_t K,
                                        const uint32_t* __restrict__ seg_start, const uint32_t* __restrict__ sj,
@@ -424,25 +367,6 @@ __global__ void kd_seqlines_kernel(uint32_t D, uint64_t K, uint32_t minab, uint3
     }
 }
 
-__global__ void kd_unpack_nodes_kernel(const NodeRec* __restrict__ rec, const uint32_t* __restrict__ perm, uint32_t S,
-                                       uint32_t k, const uint64_t* __restrict__ tuple_in, uint32_t* __restrict__ index,
-                                       uint16_t* __restrict__ abundance, uint32_t* __restrict__ seqlen,
-                                       uint16_t* __restrict__ shift, uint64_t* __restrict__ tuple_out) {
-    uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= S) return;
-    uint32_t src = perm[n];
-    NodeRec r = rec[src];
-    index[n] = r.index; abundance[n] = r.abundance; seqlen[n] = r.seqlen;
-    shift[2 * n] = r.shift0; shift[2 * n + 1] = r.shift1;
-    for (uint32_t q = 0; q < k; q++) tuple_out[(uint64_t)n * k + q] = tuple_in[(uint64_t)src * k + q];
-}
-__global__ void kd_node_keys_kernel(const NodeRec* __restrict__ rec, uint32_t S, uint32_t* __restrict__ key,
-                                    uint32_t* __restrict__ iota) {
-    uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= S) return;
-    key[n] = rec[n].index;
-    iota[n] = n;
-}
 __global__ void kd_seq_keys_kernel(const SeqRec* __restrict__ rec, uint32_t Q, uint64_t* __restrict__ key,
                                    uint32_t* __restrict__ iota) {
     uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
