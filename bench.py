@@ -166,7 +166,7 @@ def main():
                "e2e": {"value": v, "unit": "Gbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                "note": "CPU restatement of the reference algorithm in its thread structure (oracle/); the Rust "
                        "binary cannot be built in this image (no cargo/rustc)"}
-        print(json.dumps(out))
+        _emit(json.dumps(out))
         return 0
 
     # ------------------------------------------------------------------ our arm (GPU)
@@ -345,7 +345,7 @@ def main():
                "counts": {k_: int(v_) for k_, v_ in stats.items()}}
         if multik is not None:
             out["multik"] = multik
-        print(json.dumps(out))
+        _emit(json.dumps(out))
     ctx.device_free(d_bases); ctx.device_free(d_off)
     ctx.close()
     if dist is not None:
@@ -353,5 +353,17 @@ def main():
     return 0
 
 
+def _emit(line):
+    """The one JSON line goes to the REAL stdout; see __main__."""
+    os.write(_REAL_STDOUT, (line + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
 if __name__ == "__main__":
+    # Anything native libraries print on fd 1 (e.g. "NCCL version ..." under NCCL_DEBUG=VERSION)
+    # is sent to stderr, so that stdout carries exactly one JSON line.
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     sys.exit(main())

@@ -197,8 +197,9 @@ int mdbg_sync(mdbg_ctx* ctx);
 /* write >= L2-size bytes so the next timed iteration starts from a cold L2 */
 int mdbg_flush_l2(mdbg_ctx* ctx);
 
-/* ---- multi-GPU (one process per GPU; reads sharded by record; NCCL all-to-all by
- *      fingerprint prefix) --------------------------------------------------- */
+/* ---- multi-GPU (one process per GPU; reads sharded by record; the minimizer arenas are
+ *      all-gathered over NCCL and every tuple is counted on the owner of its fingerprint
+ *      range) ------------------------------------------------------------------ */
 #define MDBG_NCCL_ID_BYTES 128
 int mdbg_nccl_unique_id(uint8_t id[MDBG_NCCL_ID_BYTES]);             /* rank 0, then broadcast */
 int mdbg_comm_init(mdbg_ctx* ctx, const uint8_t id[MDBG_NCCL_ID_BYTES], int rank, int world);

@@ -5,17 +5,18 @@
 // sightings (u16), seqlen/shift/sequence from the minabund-th sighting.
 //
 // One code path for 1 and N GPUs (one process per GPU, NCCL over NVLink):
-//   1. every k-min-mer sighting becomes a RECORD {canonical tuple, global ordinal, RecInfo}
-//   2. N > 1: records are range-partitioned by tuple fingerprint and exchanged with ONE
-//      all-to-all (grouped ncclSend/ncclRecv), so every copy of a tuple meets on one owner;
-//      records arrive grouped by source rank = ascending global ordinal
+//   1. N > 1: the minimizer arenas (~12 B x 2d per base) are all-gathered, so every GPU sees every
+//      window of the job in serial order; nothing larger is exchanged
+//   2. every k-min-mer sighting this GPU owns (N > 1: tuple fingerprint in this rank's range, so
+//      every copy of a tuple meets on one owner) becomes a RECORD {window location, ordinal,
+//      RecInfo}; the canonical tuple is read from the arena, never materialised
 //   3. owner: open-address table (fingerprint placed, tuple verified), stable radix sort by slot,
 //      segmented reduce -> abundance / first sighting / representative sighting
-//   4. node index = number of distinct tuples first seen earlier anywhere: the owners all-gather
-//      their sorted first-sighting ordinals and sum W lower_bounds
-//   5. solid nodes are all-gathered (small: ~2d nodes per genome base); every GPU builds the
-//      (k-1)-mer entry index and emits the edges of its slice of the nodes; presimp removals are
-//      all-gathered before the final filter
+//   4. node index and node placement = ONE exclusive scan over ordinal space of the
+//      first-sighting flags (summed over the GPUs with one all-reduce)
+//   5. every GPU writes its nodes at their final places, the node arrays are all-reduced; every
+//      GPU builds the (k-1)-mer entry index and emits the edges of its slice of the nodes; presimp
+//      removals are all-gathered before the final filter
 #include <cuda_runtime.h>
 
 #include <algorithm>
