@@ -11,7 +11,7 @@ HDR := $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh include/*.h)
 
 CLI := rust-mdbg_b200/rust-mdbg
 
-all: $(OUT) $(CLI) oracle
+all: $(OUT) $(CLI) oracle model model
 
 $(CLI): rust-mdbg_b200/cli/rust_mdbg_main.cpp include/mdbg.h $(OUT)
 	g++ -O2 -std=c++17 -Wall -o $@ $< -Lrust-mdbg_b200 -lmdbg_b200 -lz -Wl,-rpath,'$$ORIGIN'
@@ -28,8 +28,14 @@ $(OUT): $(OBJ)
 oracle:
 	$(MAKE) -C oracle
 
+# CPU model of the bit-sliced K-A kernel body (test infrastructure, see tests/model/)
+MODEL := tests/model/libka_bitslice_model.so
+model: $(MODEL)
+$(MODEL): tests/model/ka_bitslice_model.cpp $(HDR)
+	g++ -O2 -std=c++17 -fPIC -Wall -Wno-unknown-pragmas -pthread -I/usr/local/cuda/include -shared -o $@ $<
+
 clean:
 	rm -f $(CSRC)/*.o $(CSRC)/*.log $(OUT) $(CLI)
 	$(MAKE) -C oracle clean
 
-.PHONY: all oracle clean
+.PHONY: all oracle model clean

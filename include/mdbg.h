@@ -54,7 +54,11 @@ typedef struct {
                                 enters the table at its SECOND sighting (index order = second
                                 sightings, "nodes before filter" = tuples seen >= 2 times);
                                 ignored when min_abundance == 1, as in the reference            */
-    uint32_t reserved[6];
+    uint32_t ka_variant;     /* K-A kernel: 0 = library default (env MDBG_KA_VARIANT=classic|bitslice
+                                overrides), 1 = classic (ka_minimizers_kernel), 2 = bit-sliced
+                                (ka_bitslice_kernel) where (l, density) allow it, classic elsewhere;
+                                results are identical, only the speed differs                    */
+    uint32_t reserved[5];
 } mdbg_params;
 
 typedef struct mdbg_ctx mdbg_ctx;
@@ -159,6 +163,8 @@ typedef struct {
     uint32_t ka_dense_tiles;                   /* tiles that took the exact (dense) path     */
     float ms_ka_kernel;                        /* ka_minimizers_kernel alone (last push)     */
     float ms_ka_start;                         /* push start -> first K-A work on the stream  */
+    uint32_t ka_variant_used;                  /* 1 classic, 2 bit-sliced (last push)          */
+    uint32_t ka_dirty_tiles;                   /* bit-sliced: tiles handed to the classic kernel */
 } mdbg_timings;
 int mdbg_get_timings(mdbg_ctx* ctx, mdbg_timings* out);
 void* mdbg_stream(mdbg_ctx* ctx);              /* the cudaStream_t all kernels run on        */

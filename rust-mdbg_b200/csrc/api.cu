@@ -103,6 +103,21 @@ int mdbg_ctx_create(const mdbg_params* p, mdbg_ctx** out) {
     int per_sm = ka_max_blocks_per_sm(p->hpc);
     if (per_sm < 1) per_sm = 1;
     c->ka_grid = c->num_sms * per_sm;
+    // K-A variant: the bit-sliced kernel is taken only where it is instantiated (l, density); the
+    // classic kernel stays the exact path for everything else and for the tiles it hands over.
+    uint32_t variant = p->ka_variant;
+    if (variant == 0) {
+        const char* e = getenv("MDBG_KA_VARIANT");
+        if (e && !strcmp(e, "bitslice")) variant = 2;
+        else variant = 1;
+    }
+    if (variant > 2) { g_create_err = "bad ka_variant"; mdbg_ctx_destroy(c); return MDBG_ERR_BAD_ARG; }
+    c->ka_bs = (variant == 2) && ka_bs_supported(p->l, c->bound);
+    if (c->ka_bs) {
+        int bs_per_sm = ka_bs_max_blocks_per_sm(p->l, p->hpc);
+        if (bs_per_sm < 1) { g_create_err = "bit-sliced K-A kernel does not fit this device"; mdbg_ctx_destroy(c); return MDBG_ERR_CUDA; }
+        c->ka_bs_grid = c->num_sms * bs_per_sm;
+    }
     memset(&c->tm, 0, sizeof(c->tm));
     *out = c;
     return MDBG_OK;
@@ -202,12 +217,14 @@ static int run_ka(mdbg_ctx* c, const uint8_t* d_bases, const uint64_t* d_read_of
 
     uint64_t n_tiles = std::max<uint64_t>(1, (B + KA_TILE - 1) / KA_TILE);
     Tmp<uint64_t> tile_cnt, tile_soff, tile_excl, tile_lb, stage_hash;
-    Tmp<uint32_t> stage_pos, chunk_cnt;
+    Tmp<uint32_t> stage_pos, chunk_cnt, dirty_list;
     Tmp<uint8_t> scan_tmp;
     MDBG_CK(c, tile_cnt.get(c->pool, n_tiles));
     MDBG_CK(c, tile_soff.get(c->pool, n_tiles));
     MDBG_CK(c, tile_excl.get(c->pool, n_tiles));
     MDBG_CK(c, tile_lb.get(c->pool, n_tiles + 1));
+    const bool bs = c->ka_bs && n_tiles < 0xFFFFFFFFull;
+    if (bs) MDBG_CK(c, dirty_list.get(c->pool, n_tiles));
     size_t scan_bytes = 0;
     MDBG_CK(c, cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, tile_cnt.p, tile_excl.p, n_tiles, c->st));
     MDBG_CK(c, scan_tmp.get(c->pool, scan_bytes + 256));
@@ -220,9 +237,11 @@ static int run_ka(mdbg_ctx* c, const uint8_t* d_bases, const uint64_t* d_read_of
         // an H2D copy here may be served by the copy engine and then queues behind the bulk upload
         // of mdbg_push_reads, which serialises K-A after the copy instead of under it.
         const size_t n_launch = (plan && attempt == 0) ? plan->size() : 1;
-        MDBG_CK(c, chunk_cnt.get(c->pool, n_launch));
+        // counters: one tile/group counter per K-A launch, then (bit-sliced) the length of the dirty
+        // list and the tile counter of the classic kernel's pass over that list
+        MDBG_CK(c, chunk_cnt.get(c->pool, n_launch + 2));
         KAInit I{&c->d_sc->total_out, &c->d_sc->err_pos, &c->d_sc->stage_counter, &c->d_sc->dense_tiles,
-                 chunk_cnt.p, (uint32_t)n_launch, fresh_arena ? c->m_off : nullptr};
+                 chunk_cnt.p, (uint32_t)n_launch + 2, fresh_arena ? c->m_off : nullptr};
         KAArgs A{};
         A.bases = d_bases; A.read_off = d_read_off; A.n_reads = R; A.n_bases = B;
         A.l = c->p.l; A.bound = c->bound; A.fc = c->fc; A.force_dense = 0;
@@ -233,6 +252,15 @@ static int run_ka(mdbg_ctx* c, const uint8_t* d_bases, const uint64_t* d_read_of
         A.stage_hash = stage_hash; A.stage_pos = stage_pos; A.stage_cap = stage_cap;
         A.stage_counter = &c->d_sc->stage_counter; A.tile_cnt = tile_cnt; A.tile_soff = tile_soff;
         A.tile_lb = tile_lb; A.n_tiles = n_tiles;
+        A.dirty_out = &c->d_sc->v[11];
+        if (bs) {
+            A.dirty_list = dirty_list; A.dirty_n = chunk_cnt.p + n_launch;
+            // tiles per claim: enough groups for ~8 claims per resident warp, at most 8 tiles
+            uint64_t warps = (uint64_t)c->ka_bs_grid * (KA_THREADS / 32);
+            uint64_t g = n_tiles / (warps * 8 + 1);
+            A.bs_group = (uint32_t)std::min<uint64_t>(8, std::max<uint64_t>(1, g));
+            if (const char* e = getenv("MDBG_BS_GROUP")) { long v = atol(e); if (v >= 1 && v <= 64) A.bs_group = (uint32_t)v; }
+        }
         MDBG_CK(c, cudaEventRecord(c->ev[0], c->st));
         MDBG_CK(c, ka_prepare(A, I, c->st, &c->tm.launches_push));
         if (plan && attempt == 0) {
@@ -241,12 +269,20 @@ static int run_ka(mdbg_ctx* c, const uint8_t* d_bases, const uint64_t* d_read_of
             for (const KaChunk& ch : *plan) {
                 if (ch.wait) MDBG_CK(c, cudaStreamWaitEvent(c->st, ch.wait, 0));
                 A.tile_begin = tb; A.tile_end = ch.tile_end; A.tile_counter = chunk_cnt.p + li++;
-                MDBG_CK(c, ka_launch(A, c->p.hpc, c->ka_grid, c->st, &c->tm.launches_push));
+                if (bs) MDBG_CK(c, ka_bs_launch(A, c->p.hpc, c->ka_bs_grid, c->st, &c->tm.launches_push));
+                else MDBG_CK(c, ka_launch(A, c->p.hpc, c->ka_grid, c->st, &c->tm.launches_push));
                 tb = ch.tile_end;
             }
         } else {
             A.tile_begin = 0; A.tile_end = n_tiles; A.tile_counter = chunk_cnt.p;
-            MDBG_CK(c, ka_launch(A, c->p.hpc, c->ka_grid, c->st, &c->tm.launches_push));
+            if (bs) MDBG_CK(c, ka_bs_launch(A, c->p.hpc, c->ka_bs_grid, c->st, &c->tm.launches_push));
+            else MDBG_CK(c, ka_launch(A, c->p.hpc, c->ka_grid, c->st, &c->tm.launches_push));
+        }
+        if (bs) {   // the tiles the bit-sliced kernel handed over (N, long homopolymers, ...): exact kernel
+            A.tile_list = dirty_list; A.tile_list_n = chunk_cnt.p + n_launch; A.tile_counter = chunk_cnt.p + n_launch + 1;
+            int lg = (int)std::min<uint64_t>((uint64_t)c->ka_grid, (n_tiles + (KA_THREADS / 32) - 1) / (KA_THREADS / 32));
+            MDBG_CK(c, ka_launch_list(A, c->p.hpc, lg, c->st, &c->tm.launches_push));
+            A.tile_list = nullptr; A.tile_list_n = nullptr;
         }
         MDBG_CK(c, cudaEventRecord(c->ev[16], c->st));
         MDBG_CK(c, cub::DeviceScan::ExclusiveSum(scan_tmp.p, scan_bytes, tile_cnt.p, tile_excl.p, n_tiles, c->st));
@@ -262,6 +298,8 @@ static int run_ka(mdbg_ctx* c, const uint8_t* d_bases, const uint64_t* d_read_of
         c->tm.ka_ms_sum += ms;
         c->tm.ka_launches += 1;
         c->tm.ka_dense_tiles = c->h_sc->dense_tiles;
+        c->tm.ka_variant_used = bs ? 2 : 1;
+        c->tm.ka_dirty_tiles = (uint32_t)c->h_sc->v[11];
         if (c->h_sc->err_pos != ~0ull) {
             char buf[160];
             snprintf(buf, sizeof buf, "Non-ACGTN nucleotide encountered! (batch byte offset %llu)", c->h_sc->err_pos);

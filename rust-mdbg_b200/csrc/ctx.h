@@ -71,6 +71,8 @@ struct mdbg_ctx {
     uint64_t bound = 0;
     mdbg::FilterConsts fc{};
     int device = 0, num_sms = 0, ka_grid = 0;
+    bool ka_bs = false;                             // bit-sliced K-A variant selected and applicable
+    int ka_bs_grid = 0;
     cudaStream_t st = nullptr;
     cudaStream_t st_copy = nullptr;                 // uploads overlapped with K-A
     std::vector<cudaEvent_t> copy_ev;

@@ -264,8 +264,14 @@ __global__ void __launch_bounds__(KA_THREADS, MDBG_KA_MIN_BLOCKS) ka_minimizers_
         }
         for (int i = tid; i < WORDS; i += NT) sm.bitmap[i] = 0;
         __syncwarp();
-        const uint64_t tile = A.tile_begin + sm.tile;
-        if (tile >= A.tile_end) break;
+        uint64_t tile;
+        if (A.tile_list) {             // list mode: the tiles the bit-sliced variant handed over
+            if (sm.tile >= *A.tile_list_n) break;
+            tile = A.tile_list[sm.tile];
+        } else {
+            tile = A.tile_begin + sm.tile;
+            if (tile >= A.tile_end) break;
+        }
         const int64_t t0 = (int64_t)tile * TILE;
         const int64_t t1 = (t0 + TILE < B) ? t0 + TILE : B;
         const int64_t w0 = t0 - PRE;
@@ -692,6 +698,7 @@ __global__ void ka_finalize_kernel(const KAArgs A, const uint64_t* __restrict__ 
         }
         if (warp + 1 == A.n_tiles && lane == 0) *A.total_out = A.out_base + tile_excl[warp] + cnt;
     }
+    if (gtid == 0 && A.dirty_out) *A.dirty_out = A.dirty_n ? *A.dirty_n : 0;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t r = gtid; r <= A.n_reads; r += stride) {
         uint64_t v = A.out_read_off[A.read_base + r];
@@ -715,6 +722,14 @@ cudaError_t ka_launch(const KAArgs& A, int hpc, int grid, cudaStream_t st, uint6
     unsigned g = (unsigned)(need < (uint64_t)grid ? need : (uint64_t)grid);
     if (hpc) ka_minimizers_kernel<true><<<g, KA_THREADS, 0, st>>>(A);
     else ka_minimizers_kernel<false><<<g, KA_THREADS, 0, st>>>(A);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t ka_launch_list(const KAArgs& A, int hpc, int grid, cudaStream_t st, uint64_t* launches) {
+    if (!A.tile_list || !A.tile_list_n || grid < 1) return cudaErrorInvalidValue;
+    if (hpc) ka_minimizers_kernel<true><<<grid, KA_THREADS, 0, st>>>(A);
+    else ka_minimizers_kernel<false><<<grid, KA_THREADS, 0, st>>>(A);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

@@ -40,6 +40,14 @@ struct KAArgs {
     unsigned int* tile_counter;
     uint64_t n_tiles;
     uint64_t tile_begin, tile_end;   // tiles handled by this launch (chunked, overlapped uploads)
+    // list mode of ka_minimizers_kernel: process tile_list[0 .. *tile_list_n) instead of a range
+    const uint32_t* tile_list;
+    const unsigned int* tile_list_n;
+    // bit-sliced variant (ka_bitslice.cu): tiles it cannot take are appended here
+    uint32_t* dirty_list;
+    unsigned int* dirty_n;
+    unsigned long long* dirty_out;   // ka_finalize_kernel copies *dirty_n here (host mailbox)
+    uint32_t bs_group;           // consecutive tiles claimed by a warp at a time
 };
 // prepare: per-tile read lookup + counters; launch: tiles [A.tile_begin, A.tile_end); finalize: order
 // device counters reset by ka_prepare: the batch scalars, one tile counter per K-A launch of the
@@ -52,5 +60,13 @@ cudaError_t ka_prepare(const KAArgs& A, const KAInit& I, cudaStream_t st, uint64
 cudaError_t ka_launch(const KAArgs& A, int hpc, int grid, cudaStream_t st, uint64_t* launches);
 cudaError_t ka_finalize(const KAArgs& A, const uint64_t* tile_excl, cudaStream_t st, uint64_t* launches);
 int ka_max_blocks_per_sm(int hpc);
+// list mode: A.tile_list / A.tile_list_n set; the grid is sized by the caller (the list length lives
+// on the device)
+cudaError_t ka_launch_list(const KAArgs& A, int hpc, int grid, cudaStream_t st, uint64_t* launches);
+
+// ---- K-A, bit-sliced variant (ka_bitslice.cu) -----------------------------------------------
+bool ka_bs_supported(uint32_t l, uint64_t bound);
+cudaError_t ka_bs_launch(const KAArgs& A, int hpc, int grid, cudaStream_t st, uint64_t* launches);
+int ka_bs_max_blocks_per_sm(uint32_t l, int hpc);
 
 }  // namespace mdbg

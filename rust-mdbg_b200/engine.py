@@ -11,15 +11,17 @@ class Params:
     """The members of the reference's `Params` (src/main.rs:92-114) the hot path reads."""
 
     def __init__(self, k=10, l=12, density=0.10, min_abundance=2, presimp=0.01, hpc=True,
-                 device=0, debug_fp_bits=0, bf=False):
+                 device=0, debug_fp_bits=0, bf=False, ka_variant=0):
         # defaults as in src/main.rs:437-450 (k=10, l=12, density=0.10, minabund=2, presimp=0.01)
         self.k, self.l, self.density = int(k), int(l), float(density)
         self.min_abundance, self.presimp, self.hpc = int(min_abundance), float(presimp), bool(hpc)
         self.device, self.debug_fp_bits, self.bf = int(device), int(debug_fp_bits), bool(bf)
+        self.ka_variant = {"default": 0, "classic": 1, "bitslice": 2}.get(ka_variant, ka_variant)
 
     def c(self):
         return CParams(self.k, self.l, self.density, self.min_abundance, self.presimp,
-                       1 if self.hpc else 0, self.device, 0, self.debug_fp_bits, 1 if self.bf else 0)
+                       1 if self.hpc else 0, self.device, 0, self.debug_fp_bits, 1 if self.bf else 0,
+                       int(self.ka_variant))
 
 
 class Graph:

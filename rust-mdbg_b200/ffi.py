@@ -29,7 +29,7 @@ class MdbgError(RuntimeError):
 class CParams(ctypes.Structure):
     _fields_ = [("k", u32), ("l", u32), ("density", ctypes.c_double), ("min_abundance", u32),
                 ("presimp", ctypes.c_float), ("hpc", i32), ("device", i32), ("keep_bases", i32),
-                ("debug_fp_bits", u32), ("bf", u32), ("reserved", u32 * 6)]
+                ("debug_fp_bits", u32), ("bf", u32), ("ka_variant", u32), ("reserved", u32 * 5)]
 
 
 class CGraph(ctypes.Structure):
@@ -47,7 +47,8 @@ class CTimings(ctypes.Structure):
                                               "ms_d2h", "ms_total_push", "ms_total_finish")] + \
                [("launches_push", u64), ("launches_finish", u64), ("ka_launches", u64),
                 ("ka_ms_sum", ctypes.c_float), ("table_attempts", u32), ("ka_dense_tiles", u32),
-                ("ms_ka_kernel", ctypes.c_float), ("ms_ka_start", ctypes.c_float)]
+                ("ms_ka_kernel", ctypes.c_float), ("ms_ka_start", ctypes.c_float),
+                ("ka_variant_used", u32), ("ka_dirty_tiles", u32)]
 
 
 class CSynth(ctypes.Structure):
