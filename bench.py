@@ -133,6 +133,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="ecoli50x", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ka-variant", default="default", choices=["default", "classic", "bitslice"],
+                    help="K-A kernel (mdbg_params.ka_variant); default = the library's choice")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--sweep-k", default="", help="comma list of k: also time finish() per k over the resident "
                     "minimizers (BASELINE config 5, the multi-k idea of utils/multik)")
@@ -198,7 +200,7 @@ def main():
         return float(t.item())
 
     P = m.Params(k=wl["k"], l=wl["l"], density=wl["density"], min_abundance=MIN_ABUNDANCE, presimp=PRESIMP,
-                 device=local_rank)
+                 device=local_rank, ka_variant=args.ka_variant)
     ctx = m.Context(P)
     if world > 1:
         ids = [m.nccl_unique_id() if rank == 0 else None]
@@ -254,11 +256,13 @@ def main():
     if os.path.exists(tp):
         try:
             tj = json.load(open(tp))
-            if tj.get("workload") == args.workload:
+            if tj.get("workload") == args.workload and int(tm.get("ka_variant_used", 1)) == int(tj.get("ka_variant", 1)):
                 traffic = tj.get("dram_bytes_per_launch")
         except Exception:
             pass
-    roofline = {"kernel": "ka_minimizers_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    ka_variant = {1: "classic", 2: "bitslice"}.get(int(tm.get("ka_variant_used", 1)), "classic")
+    roofline = {"kernel": "ka_bitslice_kernel" if ka_variant == "bitslice" else "ka_minimizers_kernel",
+                "ka_variant": ka_variant, "ka_dirty_tiles": int(tm.get("ka_dirty_tiles", 0)), "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": ka_avg_ms,
                 "share_of_step": ka_avg_ms / (dev_ms / steps)}

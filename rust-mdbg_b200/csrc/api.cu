@@ -261,6 +261,13 @@ static int run_ka(mdbg_ctx* c, const uint8_t* d_bases, const uint64_t* d_read_of
             A.bs_group = (uint32_t)std::min<uint64_t>(8, std::max<uint64_t>(1, g));
             if (const char* e = getenv("MDBG_BS_GROUP")) { long v = atol(e); if (v >= 1 && v <= 64) A.bs_group = (uint32_t)v; }
         }
+        Tmp<uint32_t> dbg;
+        const char* dbg_path = bs ? getenv("MDBG_BS_DEBUG_DUMP") : nullptr;
+        if (dbg_path) {
+            MDBG_CK(c, dbg.get(c->pool, n_tiles * 8));
+            MDBG_CK(c, cudaMemsetAsync(dbg.p, 0xFF, n_tiles * 8 * sizeof(uint32_t), c->st));
+            A.dbg = dbg.p;
+        }
         MDBG_CK(c, cudaEventRecord(c->ev[0], c->st));
         MDBG_CK(c, ka_prepare(A, I, c->st, &c->tm.launches_push));
         if (plan && attempt == 0) {
@@ -298,6 +305,18 @@ static int run_ka(mdbg_ctx* c, const uint8_t* d_bases, const uint64_t* d_read_of
         c->tm.ka_ms_sum += ms;
         c->tm.ka_launches += 1;
         c->tm.ka_dense_tiles = c->h_sc->dense_tiles;
+        if (dbg_path) {   // test hook: per-tile state of the bit-sliced kernel + its raw tile counts
+            std::vector<uint32_t> hd(n_tiles * 8);
+            std::vector<uint64_t> hc(n_tiles);
+            MDBG_CK(c, cudaMemcpy(hd.data(), dbg.p, hd.size() * 4, cudaMemcpyDeviceToHost));
+            MDBG_CK(c, cudaMemcpy(hc.data(), tile_cnt.p, hc.size() * 8, cudaMemcpyDeviceToHost));
+            if (FILE* f = fopen(dbg_path, "wb")) {
+                fwrite(&n_tiles, 8, 1, f);
+                fwrite(hd.data(), 4, hd.size(), f);
+                fwrite(hc.data(), 8, hc.size(), f);
+                fclose(f);
+            }
+        }
         c->tm.ka_variant_used = bs ? 2 : 1;
         c->tm.ka_dirty_tiles = (uint32_t)c->h_sc->v[11];
         if (c->h_sc->err_pos != ~0ull) {

@@ -406,6 +406,11 @@ BS_DEV void process_tile(const KAArgs& A, WarpSmem& sm, const CtaTables& ct, con
         A.dirty_list[di] = (uint32_t)tile;
     }
 
+    if (A.dbg && lane == 0) {          // per-tile state for the emulator-vs-GPU comparison
+        uint32_t* d = A.dbg + tile * 8;
+        d[0] = Ctile; d[1] = Ctotal; d[2] = (sm.flags & 1u) | (tile_bad ? 2u : 0u) | (dirty ? 4u : 0u);
+        d[3] = sm.qn; d[4] = dirty ? 0u : sm.u.post.accpre[NW]; d[5] = sm.CA[0]; d[6] = sm.CB[0]; d[7] = sm.mraw[0];
+    }
     // ---- what the tile below needs to know about this one --------------------------------------
     if (lane == 0) {
         Carry cy;

@@ -54,15 +54,22 @@ MDBG_HD uint32_t fsl(uint32_t lo, uint32_t hi, uint32_t s) {
 MDBG_HD uint32_t low_mask(uint32_t n) { return n >= 32u ? 0xFFFFFFFFu : ((1u << n) - 1u); }
 
 // ---- seeds by 2-bit code ------------------------------------------------------------------
-constexpr uint64_t seed_fwd(uint32_t code) { return code == 0 ? NT_A : code == 1 ? NT_C : code == 2 ? NT_T : NT_G; }
-constexpr uint64_t seed_rc(uint32_t code) { return code == 0 ? NT_T : code == 1 ? NT_G : code == 2 ? NT_A : NT_C; }
+// (constexpr functions are __host__ only for nvcc unless marked: called from device code unmarked
+// they compile -- inside templates even without a diagnostic -- but to garbage)
+#if defined(__CUDACC__)
+#define MDBG_HDC __host__ __device__ constexpr
+#else
+#define MDBG_HDC constexpr
+#endif
+MDBG_HDC uint64_t seed_fwd(uint32_t code) { return code == 0 ? NT_A : code == 1 ? NT_C : code == 2 ? NT_T : NT_G; }
+MDBG_HDC uint64_t seed_rc(uint32_t code) { return code == 0 ? NT_T : code == 1 ? NT_G : code == 2 ? NT_A : NT_C; }
 // truth table of bit q (mod 64) of the seed over the code (index = code = b<<1 | a)
-constexpr uint32_t tt_fwd(int q) {
+MDBG_HDC uint32_t tt_fwd(int q) {
     const int s = ((q % 64) + 64) % 64;
     return (uint32_t)(((seed_fwd(0) >> s) & 1u) | (((seed_fwd(1) >> s) & 1u) << 1) |
                       (((seed_fwd(2) >> s) & 1u) << 2) | (((seed_fwd(3) >> s) & 1u) << 3));
 }
-constexpr uint32_t tt_rc(int q) {
+MDBG_HDC uint32_t tt_rc(int q) {
     const int s = ((q % 64) + 64) % 64;
     return (uint32_t)(((seed_rc(0) >> s) & 1u) | (((seed_rc(1) >> s) & 1u) << 1) |
                       (((seed_rc(2) >> s) & 1u) << 2) | (((seed_rc(3) >> s) & 1u) << 3));

@@ -48,6 +48,7 @@ struct KAArgs {
     unsigned int* dirty_n;
     unsigned long long* dirty_out;   // ka_finalize_kernel copies *dirty_n here (host mailbox)
     uint32_t bs_group;           // consecutive tiles claimed by a warp at a time
+    uint32_t* dbg;               // optional: 8 words of per-tile state (tests / MDBG_BS_DEBUG_DUMP)
 };
 // prepare: per-tile read lookup + counters; launch: tiles [A.tile_begin, A.tile_end); finalize: order
 // device counters reset by ka_prepare: the batch scalars, one tile counter per K-A launch of the

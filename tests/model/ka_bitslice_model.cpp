@@ -97,7 +97,7 @@ int bs_model_run(const uint8_t* bases, const uint64_t* read_off, uint64_t R, uin
                  int hpc, uint32_t group, int n_warps, uint64_t tile_begin, uint64_t tile_end_or_0,
                  uint64_t* tile_cnt, uint64_t* tile_soff, uint64_t* stage_hash, uint32_t* stage_pos,
                  uint64_t stage_cap, uint64_t* out_read_off, uint32_t* dirty_list, uint32_t* dirty_n,
-                 uint64_t* stage_total) {
+                 uint64_t* stage_total, uint32_t* dbg) {
     if (!bs::supported(l, bound)) return -1;
     const uint64_t n_tiles = std::max<uint64_t>(1, (B + KA_TILE - 1) / KA_TILE);
     std::vector<uint64_t> tile_lb(n_tiles + 1);
@@ -118,7 +118,7 @@ int bs_model_run(const uint8_t* bases, const uint64_t* read_off, uint64_t R, uin
     A.stage_counter = &stage_counter; A.tile_cnt = tile_cnt; A.tile_soff = tile_soff;
     A.tile_lb = tile_lb.data(); A.tile_counter = &tile_counter; A.n_tiles = n_tiles;
     A.tile_begin = tile_begin; A.tile_end = tile_end_or_0 ? tile_end_or_0 : n_tiles;
-    A.dirty_list = dirty_list; A.dirty_n = &dn; A.bs_group = group;
+    A.dirty_list = dirty_list; A.dirty_n = &dn; A.bs_group = group; A.dbg = dbg;
     switch (l) {
         case 10: hpc ? run_warps<10, true>(A, n_warps) : run_warps<10, false>(A, n_warps); break;
         case 12: hpc ? run_warps<12, true>(A, n_warps) : run_warps<12, false>(A, n_warps); break;

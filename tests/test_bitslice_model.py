@@ -22,7 +22,7 @@ def model():
     vp, u64, u32 = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32
     L.bs_model_run.restype = ctypes.c_int
     L.bs_model_run.argtypes = [vp, vp, u64, u64, u32, u64, ctypes.c_int, u32, ctypes.c_int, u64, u64,
-                               vp, vp, vp, vp, u64, vp, vp, vp, vp]
+                               vp, vp, vp, vp, u64, vp, vp, vp, vp, vp]
     L.bs_model_filter.restype = u32
     L.bs_model_filter.argtypes = [u32] * 5
     L.bs_model_exact.restype = u64
@@ -111,7 +111,7 @@ def run_model(model, oracle, seqs, l, d, hpc=True, group=4, n_warps=1, max_dirty
     bb = bases if B else np.zeros(1, np.uint8)
     rc = model.bs_model_run(bb.ctypes.data, off.ctypes.data, R, B, l, bound, int(hpc), group, n_warps, 0, 0,
                             tile_cnt.ctypes.data, tile_soff.ctypes.data, sh.ctypes.data, sp.ctypes.data, cap,
-                            oro.ctypes.data, dl.ctypes.data, ctypes.byref(dn), ctypes.byref(st))
+                            oro.ctypes.data, dl.ctypes.data, ctypes.byref(dn), ctypes.byref(st), None)
     assert rc == 0
     dirty = set(int(x) for x in dl[:dn.value])
     assert len(dirty) == dn.value
