@@ -54,8 +54,8 @@ typedef struct {
                                 enters the table at its SECOND sighting (index order = second
                                 sightings, "nodes before filter" = tuples seen >= 2 times);
                                 ignored when min_abundance == 1, as in the reference            */
-    uint32_t ka_variant;     /* K-A kernel: 0 = library default (env MDBG_KA_VARIANT=classic|bitslice
-                                overrides), 1 = classic (ka_minimizers_kernel), 2 = bit-sliced
+    uint32_t ka_variant;     /* K-A kernel: 0 = library default (= 2; env MDBG_KA_VARIANT=classic
+                                selects 1), 1 = classic (ka_minimizers_kernel), 2 = bit-sliced
                                 (ka_bitslice_kernel) where (l, density) allow it, classic elsewhere;
                                 results are identical, only the speed differs                    */
     uint32_t reserved[5];

@@ -108,8 +108,7 @@ int mdbg_ctx_create(const mdbg_params* p, mdbg_ctx** out) {
     uint32_t variant = p->ka_variant;
     if (variant == 0) {
         const char* e = getenv("MDBG_KA_VARIANT");
-        if (e && !strcmp(e, "bitslice")) variant = 2;
-        else variant = 1;
+        variant = (e && !strcmp(e, "classic")) ? 1 : 2;
     }
     if (variant > 2) { g_create_err = "bad ka_variant"; mdbg_ctx_destroy(c); return MDBG_ERR_BAD_ARG; }
     c->ka_bs = (variant == 2) && ka_bs_supported(p->l, c->bound);
