@@ -116,6 +116,15 @@ int mdbg_ctx_create(const mdbg_params* p, mdbg_ctx** out) {
         int bs_per_sm = ka_bs_max_blocks_per_sm(p->l, p->hpc);
         if (bs_per_sm < 1) { g_create_err = "bit-sliced K-A kernel does not fit this device"; mdbg_ctx_destroy(c); return MDBG_ERR_CUDA; }
         c->ka_bs_grid = c->num_sms * bs_per_sm;
+        std::vector<unsigned char> tab(KA_BS_TABLE_BYTES);
+        ka_bs_tables(tab.data());
+        e = cudaMalloc(&c->ka_bs_t4, KA_BS_TABLE_BYTES);
+        if (e == cudaSuccess) e = cudaMemcpy(c->ka_bs_t4, tab.data(), KA_BS_TABLE_BYTES, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            g_create_err = std::string("CUDA init failed: ") + cudaGetErrorString(e);
+            mdbg_ctx_destroy(c);
+            return MDBG_ERR_CUDA;
+        }
     }
     memset(&c->tm, 0, sizeof(c->tm));
     *out = c;
@@ -133,6 +142,7 @@ void mdbg_ctx_destroy(mdbg_ctx* c) {
     if (c->m_pos) cudaFree(c->m_pos);
     if (c->m_off) cudaFree(c->m_off);
     if (c->l2_flush) cudaFree(c->l2_flush);
+    if (c->ka_bs_t4) cudaFree(c->ka_bs_t4);
     if (c->d_sc) cudaFree(c->d_sc);
     if (c->h_sc) cudaFreeHost(c->h_sc);
     for (int i = 0; i < 24; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -254,6 +264,7 @@ static int run_ka(mdbg_ctx* c, const uint8_t* d_bases, const uint64_t* d_read_of
         A.dirty_out = &c->d_sc->v[11];
         if (bs) {
             A.dirty_list = dirty_list; A.dirty_n = chunk_cnt.p + n_launch;
+            A.bs_t4 = reinterpret_cast<const bs::T4Entry*>(c->ka_bs_t4);
             // tiles per claim: enough groups for ~8 claims per resident warp, at most 8 tiles
             uint64_t warps = (uint64_t)c->ka_bs_grid * (KA_THREADS / 32);
             uint64_t g = n_tiles / (warps * 8 + 1);

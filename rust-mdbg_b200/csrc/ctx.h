@@ -73,6 +73,7 @@ struct mdbg_ctx {
     int device = 0, num_sms = 0, ka_grid = 0;
     bool ka_bs = false;                             // bit-sliced K-A variant selected and applicable
     int ka_bs_grid = 0;
+    void* ka_bs_t4 = nullptr;                       // device copy of the 4-base ntHash tables
     cudaStream_t st = nullptr;
     cudaStream_t st_copy = nullptr;                 // uploads overlapped with K-A
     std::vector<cudaEvent_t> copy_ev;

@@ -1,8 +1,8 @@
 // ka_bitslice.cu -- K-A, bit-sliced variant: the kernel wrapper and its launcher.
 //
 // The algorithm is in ka_bitslice_body.h (one warp per tile, 32 HPC positions per instruction) and
-// ka_bitslice_math.h; this file only provides the shared memory, the 4-base hash tables and the
-// dispatch over the instantiated (l, hpc) pairs.  Roofline: HBM; algorithmic bytes as for
+// ka_bitslice_math.h; this file only provides the shared memory, the 4-base hash tables (host side) and
+// the dispatch over the instantiated (l, hpc) pairs.  Roofline: HBM; algorithmic bytes as for
 // ka_minimizers_kernel (1 B read per base + 12 B written per minimizer).
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -17,7 +17,6 @@ constexpr int BS_WARPS = KA_THREADS / 32;
 constexpr int BS_T = 8;                 // top bits tested by the filter: bound < 2^56
 
 struct __align__(16) BsCta {
-    bs::CtaTables ct;
     bs::WarpSmem w[BS_WARPS];
 };
 
@@ -25,9 +24,8 @@ template <int L, bool HPC>
 __global__ void __launch_bounds__(KA_THREADS) ka_bitslice_kernel(const KAArgs A) {
     extern __shared__ __align__(16) unsigned char bs_smem_raw[];
     BsCta& cs = *reinterpret_cast<BsCta*>(bs_smem_raw);
-    for (int i = threadIdx.x; i < 256; i += KA_THREADS) cs.ct.t4[i] = bs::t4_make((uint32_t)i);
-    __syncthreads();                    // the only CTA-wide barrier: warps are independent from here on
-    bs::warp_loop<L, BS_T, HPC>(A, cs.w[threadIdx.x >> 5], cs.ct, (int)(threadIdx.x & 31));
+    // warps are independent: no CTA-wide barrier anywhere
+    bs::warp_loop<L, BS_T, HPC>(A, cs.w[threadIdx.x >> 5], (int)(threadIdx.x & 31));
 }
 
 template <int L, bool HPC>
@@ -54,6 +52,12 @@ int occupancy_one() {
 }  // namespace
 
 bool ka_bs_supported(uint32_t l, uint64_t bound) { return bs::supported(l, bound); }
+
+void ka_bs_tables(void* host_out) {
+    static_assert(sizeof(bs::T4Entry) == 16, "table entry layout");
+    bs::T4Entry* t = reinterpret_cast<bs::T4Entry*>(host_out);
+    for (uint32_t i = 0; i < 256; i++) t[i] = bs::t4_make(i);
+}
 
 // Tiles [A.tile_begin, A.tile_end) in groups of A.bs_group; dirty tiles are appended to A.dirty_list.
 cudaError_t ka_bs_launch(const KAArgs& A, int hpc, int grid, cudaStream_t st, uint64_t* launches) {

@@ -5,7 +5,8 @@
 // tile protocol (4 KiB tiles on absolute offsets, per-tile count + slice of the staging arrays,
 // ka_finalize_kernel restores the global order), but the work per base is ~3.5x smaller:
 //
-//   P1  stage the tile (coalesced 128-bit loads -> padded rows, one row of 128 bytes per lane);
+//   P1  stage the tile (cp.async 16-byte chunks -> padded rows, one row of 128 bytes per lane); the
+//       copy of tile n+1 is issued as soon as the rows of tile n are dead and lands under P4..P6;
 //   P2  ASCII -> two bit planes, 4 bases per multiply (ka_bitslice_math.h), alphabet check;
 //   P3  run starts = plane word XOR itself shifted by one (32 bases per instruction), read starts
 //       forced; the planes are compacted by the run mask (parallel-suffix compress) and appended to
@@ -44,7 +45,8 @@ constexpr int ROWS = 33;               // 32 rows of 128 bytes + the look-ahead 
 constexpr int RSTRIDE = 144;           // row pitch: conflict-free LDS.128 with one row per lane
 constexpr int CW = 136;                // words of an HPC bit stream: 4096 + 32 bits, + reach of the filter
 constexpr int NW = 128;                // run-mask words of a tile
-constexpr int QCAP = 128;              // candidate queue (expected ~25 per tile at T = 8)
+constexpr int QCAP = 64;               // candidate queue (expected ~25 per tile at T = 8)
+constexpr int HALO_RUNS = 16;          // look-ahead kept by a top tile (>= l-1 for every instantiated l)
 constexpr uint32_t Q_DROP = 0xFFFFFFFFu;
 
 struct Carry {                         // the first HPC bases of tile t+1, seen from tile t
@@ -54,36 +56,26 @@ struct Carry {                         // the first HPC bases of tile t+1, seen 
     uint32_t ok;                       // cnt >= l-1, or the data ends inside these cnt runs
 };
 
-struct Post {                          // lives in the raw rows once the planes are built
-    uint64_t hq[QCAP];                 // exact hash of an accepted candidate
-    uint32_t queue[QCAP];              // HPC position of a candidate; Q_DROP once rejected
-    uint32_t qpos[QCAP];               // raw position inside its read
-    uint32_t ACC[CW];                  // accepted windows, HPC space
-    uint32_t accpre[CW];               // exclusive popcount prefix of ACC
-};
-
 struct __align__(16) WarpSmem {
-    union {
-        uint8_t raw[ROWS * RSTRIDE];
-        Post post;
-    } u;
+    uint8_t raw[ROWS * RSTRIDE];       // the staged tile; refilled for the NEXT tile while P4..P6 run
     uint32_t CA[CW], CB[CW];           // HPC string of the tile (+ look-ahead), 1 bit per base and plane
-    uint32_t RS[CW];                   // HPC positions that start a read
+    uint32_t RS[CW];                   // HPC positions that start a read; after P5: popcount prefix of ACC
+    uint32_t ACC[CW];                  // P3: forced run starts (read starts), raw space; P5/P6: accepted windows
     uint32_t mraw[NW];                 // run starts, raw space
     uint32_t cpre[NW + 1];             // HPC position of the first run of every raw word
+    union {
+        struct { uint32_t ca[NW], cb[NW]; } t;                                   // P3: compacted plane words
+        struct { uint64_t hq[QCAP]; uint32_t queue[QCAP], qpos[QCAP]; } q;      // P4..P6: candidates
+    } u;
     Carry carry;
     uint32_t qn;
     uint32_t flags;                    // look-ahead verdict of the tile (bit 0: unusable)
     uint32_t hcnt;
     unsigned long long base;
 };
-static_assert(sizeof(Post) <= 32 * RSTRIDE, "post-phase arrays must not reach the look-ahead row");
+static_assert(sizeof(uint32_t) * 4 * CW % 16 == 0, "CA..ACC are cleared with 128-bit stores");
 
-struct CtaTables {
-    T4Entry t4[256];
-};
-
-// ---- warp primitives: the real ones under nvcc, emulated ones (tests/model/warp_emu.h) under g++ ----
+// ---- warp primitives: the real ones under nvcc, emulated ones (tests/model/) under g++ -------------
 #if defined(__CUDACC__)
 #define BS_DEV __device__ __forceinline__
 BS_DEV uint32_t bs_shfl(uint32_t v, int src) { return __shfl_sync(0xffffffffu, v, src); }
@@ -95,7 +87,20 @@ BS_DEV uint32_t bs_atomic_add_s(uint32_t* p, uint32_t v) { return atomicAdd(p, v
 BS_DEV uint32_t bs_atomic_add_g32(unsigned int* p, uint32_t v) { return atomicAdd(p, v); }
 BS_DEV unsigned long long bs_atomic_add_g64(unsigned long long* p, unsigned long long v) { return atomicAdd(p, v); }
 BS_DEV uint64_t bs_ldg64(const uint64_t* p) { return __ldg(p); }
-BS_DEV uint4 bs_ldg128(const uint8_t* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+BS_DEV T4Entry bs_ldg_t4(const T4Entry* p) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+    T4Entry e;
+    e.f = ((uint64_t)v.y << 32) | v.x;
+    e.r = ((uint64_t)v.w << 32) | v.z;
+    return e;
+}
+// 16 bytes global -> shared without a register round trip (LDGSTS); completion: bs_stage_wait()
+BS_DEV void bs_cp_async16(uint8_t* dst_smem, const uint8_t* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src)
+                 : "memory");
+}
+BS_DEV void bs_stage_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+BS_DEV void bs_stage_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 #else
 #define BS_DEV inline
 uint32_t bs_shfl(uint32_t v, int src);
@@ -107,7 +112,10 @@ uint32_t bs_atomic_add_s(uint32_t* p, uint32_t v);
 uint32_t bs_atomic_add_g32(unsigned int* p, uint32_t v);
 unsigned long long bs_atomic_add_g64(unsigned long long* p, unsigned long long v);
 inline uint64_t bs_ldg64(const uint64_t* p) { return *p; }
-inline uint4 bs_ldg128(const uint8_t* p) { uint4 v; __builtin_memcpy(&v, p, 16); return v; }
+inline T4Entry bs_ldg_t4(const T4Entry* p) { return *p; }
+inline void bs_cp_async16(uint8_t* dst, const uint8_t* src) { __builtin_memcpy(dst, src, 16); }
+inline void bs_stage_commit() {}
+inline void bs_stage_wait() {}
 #endif
 
 // last r in [lo, hi) with read_off[r] <= p   (read_off[lo] <= p guaranteed)
@@ -137,10 +145,75 @@ BS_DEV void gather32(const uint8_t* p, uint32_t& A, uint32_t& B, BadAcc& acc) {
     bad_accumulate(acc, v1.x); bad_accumulate(acc, v1.y); bad_accumulate(acc, v1.z); bad_accumulate(acc, v1.w);
 }
 
-// One tile.  `top`: the tile above it is not part of this warp's group (look-ahead from the halo row).
+// The tiles of one warp, in the order it walks them: groups of S consecutive tiles claimed from an
+// atomic counter, each group from its top tile down.
+struct TileIter {
+    uint64_t tile, tlo;
+    bool valid, top;
+};
+BS_DEV void iter_claim(const KAArgs& A, TileIter& it, const int lane) {
+    const uint64_t S = A.bs_group ? A.bs_group : 1;
+    const uint64_t ngroups = (A.tile_end - A.tile_begin + S - 1) / S;
+    uint32_t g = 0;
+    if (lane == 0) g = bs_atomic_add_g32(A.tile_counter, 1u);
+    g = bs_shfl(g, 0);
+    it.valid = (uint64_t)g < ngroups;
+    if (it.valid) {
+        it.tlo = A.tile_begin + (uint64_t)g * S;
+        const uint64_t thi = (it.tlo + S < A.tile_end) ? it.tlo + S : A.tile_end;
+        it.tile = thi - 1;
+        it.top = true;
+    }
+}
+BS_DEV void iter_next(const KAArgs& A, TileIter& it, const int lane) {
+    if (it.tile > it.tlo) { it.tile--; it.top = false; }
+    else iter_claim(A, it, lane);
+}
+
+// P1: start copying a tile (and the look-ahead row of a top tile) into the warp's rows.  Whole
+// 16-byte chunks inside the batch go global -> shared asynchronously; the ragged end of the batch is
+// written with ordinary stores, padded with 'A' (never a run start, see the limit mask).
+BS_DEV void stage_issue(const KAArgs& A, WarpSmem& sm, const int lane, const uint64_t tile, const bool top) {
+    const uint8_t* gb = A.bases;
+    const int64_t B = (int64_t)A.n_bases;
+    const int64_t t0 = (int64_t)tile * TILE;
+    const int nchunks = (top ? ROWS : ROWS - 1) * 8;
+    if (t0 + (int64_t)nchunks * 16 <= B) {
+        const uint8_t* src = gb + t0 + lane * 16;
+        uint8_t* dst = sm.raw + (lane >> 3) * RSTRIDE + (lane & 7) * 16;   // chunk q = lane + 32 i -> row 4 i + (lane >> 3)
+#pragma unroll
+        for (int i = 0; i < 8; i++) bs_cp_async16(dst + i * 4 * RSTRIDE, src + i * 512);
+        if (top && lane < 8) bs_cp_async16(sm.raw + 32 * RSTRIDE + lane * 16, gb + t0 + TILE + lane * 16);
+    } else {
+        for (int q = lane; q < nchunks; q += 32) {
+            const int64_t gp = t0 + (int64_t)q * 16;
+            uint8_t* dst = sm.raw + (q >> 3) * RSTRIDE + (q & 7) * 16;
+            if (gp + 16 <= B) {
+                bs_cp_async16(dst, gb + gp);
+            } else {
+                uint32_t t[4];
+                for (int wq = 0; wq < 4; wq++) {
+                    uint32_t x = 0;
+                    for (int j = 0; j < 4; j++) {
+                        const int64_t pos = gp + wq * 4 + j;
+                        x |= (uint32_t)(pos < B ? gb[pos] : (uint8_t)'A') << (8 * j);
+                    }
+                    t[wq] = x;
+                }
+                uint4 v;
+                v.x = t[0]; v.y = t[1]; v.z = t[2]; v.w = t[3];
+                *reinterpret_cast<uint4*>(dst) = v;
+            }
+        }
+    }
+    bs_stage_commit();
+}
+
+// One tile.  Its bytes were requested by stage_issue(); `next` is the tile this warp takes afterwards:
+// its bytes are requested as soon as this tile's rows are no longer needed (they arrive while P4..P6 run).
 template <int L, int T, bool HPC>
-BS_DEV void process_tile(const KAArgs& A, WarpSmem& sm, const CtaTables& ct, const int lane,
-                         const uint64_t tile, const bool top) {
+BS_DEV void process_tile(const KAArgs& A, WarpSmem& sm, const int lane, const uint64_t tile, const bool top,
+                         const TileIter& next) {
     const uint8_t* gb = A.bases;
     const int64_t B = (int64_t)A.n_bases;
     const int64_t t0 = (int64_t)tile * TILE;
@@ -150,83 +223,56 @@ BS_DEV void process_tile(const KAArgs& A, WarpSmem& sm, const CtaTables& ct, con
     const uint64_t rhi = lbn < A.n_reads ? lbn : A.n_reads;   // exclusive
     constexpr uint32_t LM = (1u << L) - 1u;
 
-    // ---- P1: stage ------------------------------------------------------------------------
-    for (int i = lane; i < CW; i += 32) { sm.CA[i] = 0; sm.CB[i] = 0; sm.RS[i] = 0; }
-    const int nchunks = (top ? ROWS : ROWS - 1) * 8;
-    for (int q = lane; q < nchunks; q += 32) {
-        const int64_t gp = t0 + (int64_t)q * 16;
-        uint4 v;
-        if (gp + 16 <= B) {
-            v = bs_ldg128(gb + gp);
-        } else {                       // past the end of the batch: 'A' (never a run start, see the limit mask)
-            uint32_t t[4];
-            for (int wq = 0; wq < 4; wq++) {
-                uint32_t x = 0;
-                for (int j = 0; j < 4; j++) {
-                    const int64_t pos = gp + wq * 4 + j;
-                    x |= (uint32_t)(pos < B ? gb[pos] : (uint8_t)'A') << (8 * j);
-                }
-                t[wq] = x;
-            }
-            v.x = t[0]; v.y = t[1]; v.z = t[2]; v.w = t[3];
-        }
-        *reinterpret_cast<uint4*>(sm.u.raw + (q >> 3) * RSTRIDE + (q & 7) * 16) = v;
+    // ---- clear the bit streams; read starts -> forced run starts (raw space, in ACC) ---------------
+    {
+        uint4 z;
+        z.x = 0; z.y = 0; z.z = 0; z.w = 0;
+        uint4* p = reinterpret_cast<uint4*>(sm.CA);                  // CA, CB, RS, ACC are contiguous
+        for (int i = lane; i < CW; i += 32) p[i] = z;
+        if (lane == 0) sm.qn = 0;
     }
     const uint32_t preb = (t0 > 0 && vt > 0) ? (uint32_t)gb[t0 - 1] : 0u;   // the byte before the tile
     bs_syncwarp();
+    // the first base of a read starts a run whatever precedes it (read.rs:157 works per read)
+    for (uint64_t r = lb + lane; r < lbn; r += 32) {
+        const int64_t x = (int64_t)bs_ldg64(A.read_off + r) - t0;
+        if (x < TILE) bs_atomic_or_s(sm.ACC + (x >> 5), 1u << (x & 31));
+    }
+    bs_stage_wait();                   // this lane's part of the tile has landed ...
+    bs_syncwarp();                     // ... and everybody else's
 
-    // ---- P2: planes + alphabet ------------------------------------------------------------
-    uint32_t PA[4], PB[4], M[4];
+    // ---- P2 + P3: planes, alphabet, run starts, compaction (one raw word of 32 bases at a time) ----
     BadAcc bacc{0, 0, 0};
+    uint32_t tot = 0, tail;
     {
-        const uint8_t* row = sm.u.raw + lane * RSTRIDE;
-#pragma unroll
-        for (int n = 0; n < 4; n++) gather32(row + 32 * n, PA[n], PB[n], bacc);
+        const uint8_t* row = sm.raw + lane * RSTRIDE;
+        const uint32_t prevb = lane ? (uint32_t)sm.raw[(lane - 1) * RSTRIDE + 127] : preb;
+        const bool prev_ok = is_acgt(prevb);        // N / nothing before the tile: a run starts
+        uint32_t pa = (prevb >> 1) & 1u, pb = (prevb >> 2) & 1u;
+#pragma unroll 1
+        for (int n = 0; n < 4; n++) {
+            const int idx = lane * 4 + n;
+            uint32_t PA, PB;
+            gather32(row + 32 * n, PA, PB, bacc);
+            uint32_t m = HPC ? ((PA ^ ((PA << 1) | pa)) | (PB ^ ((PB << 1) | pb))) : 0xFFFFFFFFu;
+            if (n == 0 && !prev_ok) m |= 1u;
+            m |= sm.ACC[idx];
+            sm.ACC[idx] = 0;
+            if (vt < TILE) {           // last tile of the batch: nothing starts at or after byte vt
+                const int nv = vt - (lane * 128 + 32 * n);
+                m &= nv >= 32 ? 0xFFFFFFFFu : (nv > 0 ? low_mask((uint32_t)nv) : 0u);
+            }
+            pa = PA >> 31; pb = PB >> 31;
+            if (HPC) pext_pair(m, PA, PB); else { PA &= m; PB &= m; }
+            sm.mraw[idx] = m;
+            sm.u.t.ca[idx] = PA;
+            sm.u.t.cb[idx] = PB;
+            tot += popc32(m);
+        }
+        tail = pa | (pb << 1);                       // code of this lane's last base
     }
     const bool tile_bad = bs_any(bad_of(bacc) != 0);
-
-    // ---- P3: run starts, compaction ---------------------------------------------------------
-    const uint32_t tail = (PA[3] >> 31) | ((PB[3] >> 31) << 1);   // code of this lane's last base
-    uint32_t up = bs_shfl_up(tail, 1);
     const uint32_t tail31 = bs_shfl(tail, 31);
-    bool force_first = false;
-    if (lane == 0) {
-        if (is_acgt(preb)) up = (preb >> 1) & 3u; else force_first = true;   // N / nothing before: a run starts
-    }
-    if (HPC) {
-        uint32_t pa = up & 1u, pb = up >> 1;
-#pragma unroll
-        for (int n = 0; n < 4; n++) {
-            M[n] = (PA[n] ^ ((PA[n] << 1) | pa)) | (PB[n] ^ ((PB[n] << 1) | pb));
-            pa = PA[n] >> 31; pb = PB[n] >> 31;
-        }
-        if (force_first) M[0] |= 1u;
-    } else {
-#pragma unroll
-        for (int n = 0; n < 4; n++) M[n] = 0xFFFFFFFFu;
-    }
-    // the first base of a read starts a run whatever precedes it (read.rs:157 works per read)
-    for (uint64_t r = lb; r < lbn; r++) {
-        const int64_t x = (int64_t)bs_ldg64(A.read_off + r) - t0;
-        if (x < TILE && (x >> 7) == lane) {
-            const uint32_t bit = 1u << (x & 31);
-            const int n = (int)(x >> 5) & 3;
-            if (n == 0) M[0] |= bit;
-            if (n == 1) M[1] |= bit;
-            if (n == 2) M[2] |= bit;
-            if (n == 3) M[3] |= bit;
-        }
-    }
-    if (vt < TILE) {                   // last tile of the batch: nothing starts at or after byte vt
-#pragma unroll
-        for (int n = 0; n < 4; n++) {
-            const int nv = vt - (lane * 128 + 32 * n);
-            M[n] &= nv >= 32 ? 0xFFFFFFFFu : (nv > 0 ? low_mask((uint32_t)nv) : 0u);
-        }
-    }
-    uint32_t c[4], tot = 0;
-#pragma unroll
-    for (int n = 0; n < 4; n++) { c[n] = popc32(M[n]); tot += c[n]; }
     uint32_t inc = tot;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -236,14 +282,13 @@ BS_DEV void process_tile(const KAArgs& A, WarpSmem& sm, const CtaTables& ct, con
     const uint32_t Ctile = bs_shfl(inc, 31);       // runs (HPC bases) owned by the tile
     {
         uint32_t o = inc - tot;
-#pragma unroll
+#pragma unroll 1
         for (int n = 0; n < 4; n++) {
-            uint32_t ca = PA[n], cb = PB[n];
-            if (HPC) pext_pair(M[n], ca, cb); else { ca &= M[n]; cb &= M[n]; }
-            sm.mraw[lane * 4 + n] = M[n];
-            sm.cpre[lane * 4 + n] = o;
-            if (c[n]) { put_bits(sm.CA, o, ca); put_bits(sm.CB, o, cb); }
-            o += c[n];
+            const int idx = lane * 4 + n;
+            const uint32_t c = popc32(sm.mraw[idx]);
+            sm.cpre[idx] = o;
+            if (c) { put_bits(sm.CA, o, sm.u.t.ca[idx]); put_bits(sm.CB, o, sm.u.t.cb[idx]); }
+            o += c;
         }
         if (lane == 31) sm.cpre[NW] = o;
     }
@@ -253,9 +298,10 @@ BS_DEV void process_tile(const KAArgs& A, WarpSmem& sm, const CtaTables& ct, con
         if (t0 + TILE < B) {
             if (top) {
                 BadAcc hacc{0, 0, 0};
-                gather32(sm.u.raw + 32 * RSTRIDE, ha, hb, hacc);
+                uint32_t xa, xb;
+                gather32(sm.raw + 32 * RSTRIDE, xa, xb, hacc);
                 const int64_t left = B - (t0 + TILE);
-                uint32_t hm = HPC ? ((ha ^ ((ha << 1) | (tail31 & 1u))) | (hb ^ ((hb << 1) | (tail31 >> 1)))) : 0xFFFFFFFFu;
+                uint32_t hm = HPC ? ((xa ^ ((xa << 1) | (tail31 & 1u))) | (xb ^ ((xb << 1) | (tail31 >> 1)))) : 0xFFFFFFFFu;
                 uint32_t hs = 0;
                 uint64_t r = lbn;
                 int guard = 0;
@@ -266,13 +312,22 @@ BS_DEV void process_tile(const KAArgs& A, WarpSmem& sm, const CtaTables& ct, con
                 }
                 if (guard >= 64) unusable = 1;
                 hm |= hs;
-                if (left < 32) { hm &= low_mask((uint32_t)left); hs &= low_mask((uint32_t)left); }
+                if (left < 32) hm &= low_mask((uint32_t)left);
                 if (bad_of(hacc) != 0) unusable = 1;   // conservative: the filler past the batch end is 'A'
-                hcnt = popc32(hm);
-                uint32_t zero = 0;
-                if (HPC) { pext_pair(hm, ha, hb); pext_pair(hm, hs, zero); } else { ha &= hm; hb &= hm; }
-                hrs = hs;
-                if (!(hcnt >= (uint32_t)(L - 1) || left <= 32)) unusable = 1;
+                const uint32_t runs = popc32(hm);
+                while (hm && hcnt < (uint32_t)HALO_RUNS) {   // the first runs, one at a time (top tiles only)
+#if defined(__CUDA_ARCH__)
+                    const uint32_t k = (uint32_t)__ffs((int)hm) - 1u;
+#else
+                    const uint32_t k = (uint32_t)__builtin_ctz(hm);
+#endif
+                    hm &= hm - 1u;
+                    ha |= ((xa >> k) & 1u) << hcnt;
+                    hb |= ((xb >> k) & 1u) << hcnt;
+                    hrs |= ((hs >> k) & 1u) << hcnt;
+                    hcnt++;
+                }
+                if (!(hcnt >= (uint32_t)(L - 1) || (left <= 32 && hcnt == runs))) unusable = 1;
             } else {
                 const Carry cy = sm.carry;
                 ha = cy.a; hb = cy.b; hrs = cy.rs; hcnt = cy.cnt;
@@ -284,10 +339,9 @@ BS_DEV void process_tile(const KAArgs& A, WarpSmem& sm, const CtaTables& ct, con
         }
         sm.hcnt = hcnt;
         sm.flags = unusable;
-        sm.qn = 0;
     }
-    bs_syncwarp();                     // raw rows are dead from here on: Post may be written
-    for (int i = lane; i < CW; i += 32) sm.u.post.ACC[i] = 0;
+    bs_syncwarp();                     // the rows are dead from here on ...
+    if (next.valid) stage_issue(A, sm, lane, next.tile, next.top);   // ... refill them for the next tile
     // read starts of this tile in HPC space
     for (uint64_t r = lb + lane; r < lbn; r += 32) {
         const int64_t x = (int64_t)bs_ldg64(A.read_off + r) - t0;
@@ -299,6 +353,7 @@ BS_DEV void process_tile(const KAArgs& A, WarpSmem& sm, const CtaTables& ct, con
     const uint32_t Ctotal = Ctile + sm.hcnt;
     bool dirty = tile_bad || (sm.flags & 1u);
     bs_syncwarp();
+    const uint32_t rs0 = sm.RS[0];     // for the tile below (RS is recycled after P5)
 
     // ---- P4: filter -------------------------------------------------------------------------
     if (!dirty) {
@@ -319,7 +374,7 @@ BS_DEV void process_tile(const KAArgs& A, WarpSmem& sm, const CtaTables& ct, con
 #endif
                 cand &= cand - 1u;
                 const uint32_t qi = bs_atomic_add_s(&sm.qn, 1u);
-                if (qi < (uint32_t)QCAP) sm.u.post.queue[qi] = s + k;
+                if (qi < (uint32_t)QCAP) sm.u.q.queue[qi] = s + k;
             }
         }
         bs_syncwarp();
@@ -330,15 +385,15 @@ BS_DEV void process_tile(const KAArgs& A, WarpSmem& sm, const CtaTables& ct, con
     if (!dirty) {
         const uint32_t qn = sm.qn;
         for (uint32_t qi = lane; qi < qn; qi += 32) {
-            const uint32_t p = sm.u.post.queue[qi];
-            sm.u.post.queue[qi] = Q_DROP;
+            const uint32_t p = sm.u.q.queue[qi];
+            sm.u.q.queue[qi] = Q_DROP;
             if (p + (uint32_t)L > Ctotal) continue;             // fewer than l runs left in the data
             const uint32_t w = p >> 5, sh = p & 31u;
             const uint32_t rsb = fsr(sm.RS[w], sm.RS[w + 1], sh);
             if ((rsb >> 1) & (LM >> 1)) continue;               // a read starts inside the window
             const uint32_t av = fsr(sm.CA[w], sm.CA[w + 1], sh) & LM;
             const uint32_t bv = fsr(sm.CB[w], sm.CB[w + 1], sh) & LM;
-            const uint64_t h = exact_hash<L>(av, bv, ct.t4);
+            const uint64_t h = exact_hash<L>(av, bv, A.bs_t4);
             if (h > A.bound) continue;
             // raw position of the window's first run: last raw word whose first run is at or before p
             uint32_t lo = 0, hi = NW;
@@ -349,19 +404,20 @@ BS_DEV void process_tile(const KAArgs& A, WarpSmem& sm, const CtaTables& ct, con
             const uint32_t x = lo * 32u + select_bit(sm.mraw[lo], p - sm.cpre[lo]);
             const int64_t p0 = t0 + (int64_t)x;
             const uint64_t r = find_read(A.read_off, rlo, rhi, p0);
-            bs_atomic_or_s(sm.u.post.ACC + w, 1u << sh);
-            sm.u.post.queue[qi] = p;
-            sm.u.post.hq[qi] = h;
-            sm.u.post.qpos[qi] = (uint32_t)(p0 - (int64_t)bs_ldg64(A.read_off + r));
+            bs_atomic_or_s(sm.ACC + w, 1u << sh);
+            sm.u.q.queue[qi] = p;
+            sm.u.q.hq[qi] = h;
+            sm.u.q.qpos[qi] = (uint32_t)(p0 - (int64_t)bs_ldg64(A.read_off + r));
         }
         bs_syncwarp();
     }
 
     // ---- P6: ranks, reservation, emission ---------------------------------------------------
+    uint32_t* accpre = sm.RS;          // RS is not read any more
     if (!dirty) {
         uint32_t wv[4], cnt = 0;
 #pragma unroll
-        for (int i = 0; i < 4; i++) { wv[i] = sm.u.post.ACC[lane * 4 + i]; cnt += popc32(wv[i]); }
+        for (int i = 0; i < 4; i++) { wv[i] = sm.ACC[lane * 4 + i]; cnt += popc32(wv[i]); }
         uint32_t sc = cnt;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -371,8 +427,8 @@ BS_DEV void process_tile(const KAArgs& A, WarpSmem& sm, const CtaTables& ct, con
         const uint32_t total = bs_shfl(sc, 31);
         uint32_t ex = sc - cnt;
 #pragma unroll
-        for (int i = 0; i < 4; i++) { sm.u.post.accpre[lane * 4 + i] = ex; ex += popc32(wv[i]); }
-        if (lane == 31) sm.u.post.accpre[NW] = total;            // ACC[NW] stays 0
+        for (int i = 0; i < 4; i++) { accpre[lane * 4 + i] = ex; ex += popc32(wv[i]); }
+        if (lane == 31) accpre[NW] = total;                      // ACC[NW] stays 0
         if (lane == 0) {
             const unsigned long long sb = bs_atomic_add_g64(A.stage_counter, (unsigned long long)total);
             sm.base = sb;
@@ -386,19 +442,19 @@ BS_DEV void process_tile(const KAArgs& A, WarpSmem& sm, const CtaTables& ct, con
             uint32_t rank = total;
             if (x < vt) {
                 const uint32_t comp = sm.cpre[x >> 5] + popc32(sm.mraw[x >> 5] & low_mask((uint32_t)(x & 31)));
-                rank = sm.u.post.accpre[comp >> 5] + popc32(sm.u.post.ACC[comp >> 5] & low_mask(comp & 31u));
+                rank = accpre[comp >> 5] + popc32(sm.ACC[comp >> 5] & low_mask(comp & 31u));
             }
             A.out_read_off[A.read_base + r] = ((uint64_t)tile << 32) | rank;   // fixed up by ka_finalize_kernel
         }
         const uint32_t qn = sm.qn;
         for (uint32_t qi = lane; qi < qn; qi += 32) {
-            const uint32_t p = sm.u.post.queue[qi];
+            const uint32_t p = sm.u.q.queue[qi];
             if (p == Q_DROP) continue;
-            const uint32_t rank = sm.u.post.accpre[p >> 5] + popc32(sm.u.post.ACC[p >> 5] & low_mask(p & 31u));
+            const uint32_t rank = accpre[p >> 5] + popc32(sm.ACC[p >> 5] & low_mask(p & 31u));
             const uint64_t o = obase + rank;
             if (o < A.stage_cap) {
-                A.stage_hash[o] = sm.u.post.hq[qi];
-                A.stage_pos[o] = sm.u.post.qpos[qi];
+                A.stage_hash[o] = sm.u.q.hq[qi];
+                A.stage_pos[o] = sm.u.q.qpos[qi];
             }
         }
     } else if (lane == 0) {
@@ -406,18 +462,18 @@ BS_DEV void process_tile(const KAArgs& A, WarpSmem& sm, const CtaTables& ct, con
         A.dirty_list[di] = (uint32_t)tile;
     }
 
-    if (A.dbg && lane == 0) {          // per-tile state for the emulator-vs-GPU comparison
-        uint32_t* d = A.dbg + tile * 8;
-        d[0] = Ctile; d[1] = Ctotal; d[2] = (sm.flags & 1u) | (tile_bad ? 2u : 0u) | (dirty ? 4u : 0u);
-        d[3] = sm.qn; d[4] = dirty ? 0u : sm.u.post.accpre[NW]; d[5] = sm.CA[0]; d[6] = sm.CB[0]; d[7] = sm.mraw[0];
-    }
-    // ---- what the tile below needs to know about this one --------------------------------------
     if (lane == 0) {
+        if (A.dbg) {                   // per-tile state for the emulator-vs-GPU comparison
+            uint32_t* d = A.dbg + tile * 8;
+            d[0] = Ctile; d[1] = Ctotal; d[2] = (sm.flags & 1u) | (tile_bad ? 2u : 0u) | (dirty ? 4u : 0u);
+            d[3] = sm.qn; d[4] = dirty ? 0u : accpre[NW]; d[5] = sm.CA[0]; d[6] = sm.CB[0]; d[7] = sm.mraw[0];
+        }
+        // what the tile below needs to know about this one
         Carry cy;
         cy.cnt = Ctile < 32u ? Ctile : 32u;
         cy.a = sm.CA[0] & low_mask(cy.cnt);
         cy.b = sm.CB[0] & low_mask(cy.cnt);
-        cy.rs = sm.RS[0] & low_mask(cy.cnt);
+        cy.rs = rs0 & low_mask(cy.cnt);
         cy.bad = tile_bad ? 1u : 0u;
         cy.ok = (cy.cnt >= (uint32_t)(L - 1) || (Ctile == cy.cnt && t0 + TILE >= B)) ? 1u : 0u;
         sm.carry = cy;
@@ -425,20 +481,19 @@ BS_DEV void process_tile(const KAArgs& A, WarpSmem& sm, const CtaTables& ct, con
     bs_syncwarp();
 }
 
-// The persistent loop of one warp: claim a group of A.bs_group consecutive tiles, walk it top down.
+// The persistent loop of one warp.
 template <int L, int T, bool HPC>
-BS_DEV void warp_loop(const KAArgs& A, WarpSmem& sm, const CtaTables& ct, const int lane) {
-    const uint64_t S = A.bs_group ? A.bs_group : 1;
-    const uint64_t ntl = A.tile_end - A.tile_begin;
-    const uint64_t ngroups = (ntl + S - 1) / S;
+BS_DEV void warp_loop(const KAArgs& A, WarpSmem& sm, const int lane) {
+    TileIter it;
+    iter_claim(A, it, lane);
+    if (!it.valid) return;
+    stage_issue(A, sm, lane, it.tile, it.top);
     for (;;) {
-        uint32_t g = 0;
-        if (lane == 0) g = bs_atomic_add_g32(A.tile_counter, 1u);
-        g = bs_shfl(g, 0);
-        if ((uint64_t)g >= ngroups) break;
-        const uint64_t tlo = A.tile_begin + (uint64_t)g * S;
-        const uint64_t thi = (tlo + S < A.tile_end) ? tlo + S : A.tile_end;
-        for (uint64_t tile = thi; tile-- > tlo;) process_tile<L, T, HPC>(A, sm, ct, lane, tile, tile + 1 == thi);
+        const uint64_t tile = it.tile;
+        const bool top = it.top;
+        iter_next(A, it, lane);
+        process_tile<L, T, HPC>(A, sm, lane, tile, top, it);
+        if (!it.valid) break;
     }
 }
 

@@ -7,6 +7,8 @@
 
 namespace mdbg {
 
+namespace bs { struct T4Entry; }
+
 // ---- K-A (ka_minimizers.cu) ----------------------------------------------------------------
 constexpr int KA_THREADS = 128;                // CTA size: 4 independent warps
 constexpr int KA_SEG = 128;                    // bytes walked by one thread
@@ -48,6 +50,7 @@ struct KAArgs {
     unsigned int* dirty_n;
     unsigned long long* dirty_out;   // ka_finalize_kernel copies *dirty_n here (host mailbox)
     uint32_t bs_group;           // consecutive tiles claimed by a warp at a time
+    const bs::T4Entry* bs_t4;    // 256 x 16 B: 4-base ntHash tables (ka_bs_tables), device memory
     uint32_t* dbg;               // optional: 8 words of per-tile state (tests / MDBG_BS_DEBUG_DUMP)
 };
 // prepare: per-tile read lookup + counters; launch: tiles [A.tile_begin, A.tile_end); finalize: order
@@ -67,6 +70,8 @@ cudaError_t ka_launch_list(const KAArgs& A, int hpc, int grid, cudaStream_t st, 
 
 // ---- K-A, bit-sliced variant (ka_bitslice.cu) -----------------------------------------------
 bool ka_bs_supported(uint32_t l, uint64_t bound);
+constexpr size_t KA_BS_TABLE_BYTES = 256 * 16;
+void ka_bs_tables(void* host_out);           // fills KA_BS_TABLE_BYTES (host); the caller uploads them
 cudaError_t ka_bs_launch(const KAArgs& A, int hpc, int grid, cudaStream_t st, uint64_t* launches);
 int ka_bs_max_blocks_per_sm(uint32_t l, int hpc);
 

@@ -63,8 +63,6 @@ using namespace mdbg;
 
 template <int L, bool HPC>
 static void run_warps(const KAArgs& A, int n_warps) {
-    bs::CtaTables* ct = new bs::CtaTables();
-    for (uint32_t i = 0; i < 256; i++) ct->t4[i] = bs::t4_make(i);
     std::vector<std::thread> th;
     std::vector<WarpEmu*> warps;
     std::vector<bs::WarpSmem*> smems;
@@ -79,13 +77,12 @@ static void run_warps(const KAArgs& A, int n_warps) {
             th.emplace_back([=, &A]() {
                 g_warp = we;
                 g_lane = lane;
-                bs::warp_loop<L, 8, HPC>(A, *sm, *ct, lane);
+                bs::warp_loop<L, 8, HPC>(A, *sm, lane);
             });
     }
     for (auto& t : th) t.join();
     for (auto* we : warps) { pthread_barrier_destroy(&we->bar); delete we; }
     for (auto* sm : smems) free(sm);
-    delete ct;
 }
 
 extern "C" {
@@ -119,6 +116,9 @@ int bs_model_run(const uint8_t* bases, const uint64_t* read_off, uint64_t R, uin
     A.tile_lb = tile_lb.data(); A.tile_counter = &tile_counter; A.n_tiles = n_tiles;
     A.tile_begin = tile_begin; A.tile_end = tile_end_or_0 ? tile_end_or_0 : n_tiles;
     A.dirty_list = dirty_list; A.dirty_n = &dn; A.bs_group = group; A.dbg = dbg;
+    static bs::T4Entry t4[256];
+    for (uint32_t i = 0; i < 256; i++) t4[i] = bs::t4_make(i);
+    A.bs_t4 = t4;
     switch (l) {
         case 10: hpc ? run_warps<10, true>(A, n_warps) : run_warps<10, false>(A, n_warps); break;
         case 12: hpc ? run_warps<12, true>(A, n_warps) : run_warps<12, false>(A, n_warps); break;
