@@ -6,7 +6,8 @@ CSRC := rust-mdbg_b200/csrc
 OUT := rust-mdbg_b200/libmdbg_b200.so
 CU := $(wildcard $(CSRC)/*.cu)
 CPP := $(wildcard $(CSRC)/*.cpp)
-OBJ := $(CU:.cu=.o) $(CPP:.cpp=.o)
+CC := $(wildcard $(CSRC)/*.cc)
+OBJ := $(CU:.cu=.o) $(CPP:.cpp=.o) $(CC:.cc=.o)
 HDR := $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh include/*.h)
 
 CLI := rust-mdbg_b200/rust-mdbg
@@ -21,6 +22,10 @@ $(CSRC)/%.o: $(CSRC)/%.cu $(HDR)
 
 $(CSRC)/%.o: $(CSRC)/%.cpp $(HDR)
 	$(NVCC) $(NVFLAGS) -x cu -c $< -o $@ 2> $@.ptxas.log || (cat $@.ptxas.log; exit 1)
+
+# host-only sources (SIMD intrinsics): plain g++
+$(CSRC)/%.o: $(CSRC)/%.cc $(HDR)
+	g++ -O3 -std=c++17 -mssse3 -fPIC -Wall -pthread -c $< -o $@
 
 $(OUT): $(OBJ)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) -ldl -lz -lpthread

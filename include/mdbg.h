@@ -165,6 +165,8 @@ typedef struct {
     float ms_ka_start;                         /* push start -> first K-A work on the stream  */
     uint32_t ka_variant_used;                  /* 1 classic, 2 bit-sliced (last push)          */
     uint32_t ka_dirty_tiles;                   /* bit-sliced: tiles handed to the classic kernel */
+    uint32_t upload_packed;                    /* last mdbg_push_reads: 1 = bases crossed PCIe as 2-bit planes */
+    uint32_t upload_ascii_tiles;               /* ... of which 4 KiB tiles sent as ASCII (bytes outside ACGT)  */
 } mdbg_timings;
 int mdbg_get_timings(mdbg_ctx* ctx, mdbg_timings* out);
 void* mdbg_stream(mdbg_ctx* ctx);              /* the cudaStream_t all kernels run on        */
@@ -222,6 +224,16 @@ int mdbg_write_gfa(const mdbg_graph* g, const char* path);                   /* 
  * the HOST copies of the reads in global read order.                                       */
 int mdbg_write_sequences(const mdbg_graph* g, const uint8_t* bases, const uint64_t* read_off,
                          const char* path, int lz4_frame);
+
+/* ---- host ingest: 2-bit packing for the 4:1 upload (reference side: the reads the
+ *      parser hands to Read::extract, main.rs:163-178,830-839) ----------------------------------
+ * mdbg_push_reads packs host buffers like this itself (MDBG_UPLOAD=ascii turns it off); the entry
+ * point is public for hosts that pack while they parse.  planes[2w], planes[2w+1] = bit 1 and bit 2
+ * of the 32 bases [32w, 32w+32) (A 00, C 01, T 10, G 11; bases past n_bases read as A); bad_tiles[t]
+ * (may be NULL) is set to 1 when the 4096-base tile t holds a byte outside ACGT -- such tiles must
+ * travel as ASCII.  threads <= 1: on the calling thread.                                        */
+int mdbg_pack_bases_host(const uint8_t* bases, uint64_t n_bases, uint32_t* planes, uint8_t* bad_tiles,
+                         int threads);
 
 #ifdef __cplusplus
 }

@@ -11,7 +11,11 @@
 #include <string>
 #include <vector>
 
+#include <functional>
+#include <thread>
+
 #include "ctx.h"
+#include "pack_host.h"
 
 using namespace mdbg;
 
@@ -126,6 +130,10 @@ int mdbg_ctx_create(const mdbg_params* p, mdbg_ctx** out) {
             return MDBG_ERR_CUDA;
         }
     }
+    {   // host buffers travel 4:1 packed (pack_host.cc) unless MDBG_UPLOAD=ascii
+        const char* e = getenv("MDBG_UPLOAD");
+        c->upload_packed = !(e && !strcmp(e, "ascii"));
+    }
     memset(&c->tm, 0, sizeof(c->tm));
     *out = c;
     return MDBG_OK;
@@ -143,6 +151,8 @@ void mdbg_ctx_destroy(mdbg_ctx* c) {
     if (c->m_off) cudaFree(c->m_off);
     if (c->l2_flush) cudaFree(c->l2_flush);
     if (c->ka_bs_t4) cudaFree(c->ka_bs_t4);
+    if (c->h_planes) cudaFreeHost(c->h_planes);
+    delete c->pack_pool;
     if (c->d_sc) cudaFree(c->d_sc);
     if (c->h_sc) cudaFreeHost(c->h_sc);
     for (int i = 0; i < 24; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -211,7 +221,8 @@ struct KaChunk { uint64_t tile_end; cudaEvent_t wait; };
 // Run K-A on a device-resident batch (or on one that is still being uploaded chunk by chunk),
 // appending to the arena.
 static int run_ka(mdbg_ctx* c, const uint8_t* d_bases, const uint64_t* d_read_off, uint64_t R, uint64_t B,
-                  const std::vector<KaChunk>* plan = nullptr) {
+                  const std::vector<KaChunk>* plan = nullptr,
+                  const std::function<int(size_t)>* prepare = nullptr) {   // prepare(i): make chunk i's bytes arrive
     if (((uintptr_t)d_bases & 15) != 0) { c->err = "bases must be 16-byte aligned"; return MDBG_ERR_BAD_ARG; }
     // expected minimizers: ~2.2*density of the HPC positions; start with a generous estimate and
     // re-run the batch once with the exact size if it did not fit.
@@ -284,6 +295,7 @@ static int run_ka(mdbg_ctx* c, const uint8_t* d_bases, const uint64_t* d_read_of
             uint64_t tb = 0;
             size_t li = 0;
             for (const KaChunk& ch : *plan) {
+                if (prepare) { int prc = (*prepare)(li); if (prc) return prc; }
                 if (ch.wait) MDBG_CK(c, cudaStreamWaitEvent(c->st, ch.wait, 0));
                 A.tile_begin = tb; A.tile_end = ch.tile_end; A.tile_counter = chunk_cnt.p + li++;
                 if (bs) MDBG_CK(c, ka_bs_launch(A, c->p.hpc, c->ka_bs_grid, c->st, &c->tm.launches_push));
@@ -382,7 +394,9 @@ int mdbg_push_reads(mdbg_ctx* c, const uint8_t* bases, const uint64_t* read_off,
     c->tm.launches_push = 0;
     Tmp<uint8_t> d_bases;
     Tmp<uint64_t> d_off;
-    MDBG_CK(c, d_bases.get(c->pool, B + 16));
+    Tmp<uint32_t> d_planes;
+    const bool packed = c->upload_packed && B > 0;
+    MDBG_CK(c, d_bases.get(c->pool, B + 64));
     MDBG_CK(c, d_off.get(c->pool, n_reads + 1));
     MDBG_CK(c, cudaEventRecord(c->ev[2], c->st));
     // Upload in ~32 MB chunks cut at read starts on a second stream; K-A runs on the tiles whose
@@ -401,6 +415,69 @@ int mdbg_push_reads(mdbg_ctx* c, const uint8_t* bases, const uint64_t* read_off,
     MDBG_CK(c, cudaStreamWaitEvent(c->st, c->ev[18], 0));
     uint64_t b0 = 0;
     size_t nev = 0;
+    // ---- 4:1 upload: pack on the host (worker threads), copy the bit planes, expand on the device ----
+    const uint64_t n_words = (B + 31) / 32;
+    std::vector<uint8_t> bad_tiles;
+    uint64_t CHW = std::max<uint64_t>(2 * PACK_TILE_WORDS, (CH / 32) / PACK_TILE_WORDS * PACK_TILE_WORDS);   // words per chunk
+    std::function<int(size_t)> prepare;
+    if (packed) {
+        if (!c->pack_pool) {
+            unsigned hw = std::max<unsigned>(1, std::thread::hardware_concurrency());
+            if (const char* e = getenv("LOCAL_WORLD_SIZE")) { long v = atol(e); if (v >= 1 && v <= 64) hw = std::max<unsigned>(4, hw / (unsigned)v); }
+            int nt = (int)std::min<unsigned>(32, hw);   // one process per GPU: share the host cores between the ranks
+            if (const char* e = getenv("MDBG_PACK_THREADS")) { long v = atol(e); if (v >= 1 && v <= 256) nt = (int)v; }
+            c->pack_pool = new PackPool(nt);
+        }
+        const size_t need = (size_t)n_words * 8;
+        if (c->h_planes_cap < need) {
+            if (c->h_planes) cudaFreeHost(c->h_planes);
+            c->h_planes = nullptr; c->h_planes_cap = 0;
+            const size_t cap = need + need / 4 + 4096;
+            MDBG_CK(c, cudaHostAlloc(&c->h_planes, cap, cudaHostAllocDefault));
+            c->h_planes_cap = cap;
+        }
+        MDBG_CK(c, d_planes.get(c->pool, n_words * 2));
+        bad_tiles.assign(n_tiles, 0);
+        const uint64_t n_chunks = (n_words + CHW - 1) / CHW;
+        for (uint64_t ci = 0; ci < n_chunks; ci++) {
+            if (nev == c->copy_ev.size()) {
+                cudaEvent_t ev;
+                MDBG_CK(c, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                c->copy_ev.push_back(ev);
+            }
+            const uint64_t wb = std::min(n_words, (ci + 1) * CHW);
+            // K-A of chunk ci stops one tile short of the chunk: the look-ahead of its last tile is in the next chunk
+            // (the classic kernel may walk a long homopolymer arbitrarily far ahead: it runs once, after the last chunk)
+            const uint64_t te = wb == n_words ? n_tiles : (c->ka_bs ? wb / PACK_TILE_WORDS - 1 : 0);
+            plan.push_back(KaChunk{te, c->copy_ev[nev]});
+            nev++;
+        }
+        prepare = [&, n_words, CHW](size_t ci) -> int {
+            const uint64_t wa = (uint64_t)ci * CHW, wb = std::min(n_words, wa + CHW);
+            uint32_t* hp = (uint32_t*)c->h_planes;
+            pack_parallel(*c->pack_pool, bases, B, wa, wb, hp, bad_tiles.data());
+            MDBG_CK(c, cudaMemcpyAsync(d_planes.p + 2 * wa, hp + 2 * wa, (wb - wa) * 8, cudaMemcpyHostToDevice, c->st_copy));
+            MDBG_CK(c, cudaEventRecord(c->copy_ev[ci], c->st_copy));
+            if (wb == n_words) MDBG_CK(c, cudaEventRecord(c->ev[4], c->st_copy));
+            MDBG_CK(c, cudaStreamWaitEvent(c->st, c->copy_ev[ci], 0));
+            MDBG_CK(c, expand_planes(d_planes.p, d_bases.p, wa, wb, c->num_sms, c->st, &c->tm.launches_push));
+            // tiles with a byte outside ACGT travel as ASCII, over what the expansion wrote there
+            const uint64_t ta = wa / PACK_TILE_WORDS, tb = (wb + PACK_TILE_WORDS - 1) / PACK_TILE_WORDS;
+            for (uint64_t t = ta; t < tb;) {
+                if (!bad_tiles[t]) { t++; continue; }
+                uint64_t t2 = t;
+                while (t2 < tb && bad_tiles[t2]) t2++;
+                const uint64_t off = t * (uint64_t)KA_TILE, end = std::min<uint64_t>(B, t2 * (uint64_t)KA_TILE);
+                MDBG_CK(c, cudaMemcpyAsync(d_bases.p + off, bases + off, end - off, cudaMemcpyHostToDevice, c->st));
+                c->tm.upload_ascii_tiles += (uint32_t)(t2 - t);
+                t = t2;
+            }
+            return MDBG_OK;
+        };
+        b0 = B;                        // nothing left for the ASCII chunk loop below
+    }
+    c->tm.upload_packed = packed ? 1 : 0;
+    c->tm.upload_ascii_tiles = 0;
     while (b0 < B) {
         uint64_t target = b0 + CH;
         if (B - b0 <= CH + CH / 4 && B - b0 > CH / 2) target = B - CH / 4;   // short last chunk: short tail after the copy
@@ -421,8 +498,8 @@ int mdbg_push_reads(mdbg_ctx* c, const uint8_t* bases, const uint64_t* read_off,
         b0 = b1;
     }
     if (plan.empty()) plan.push_back(KaChunk{n_tiles, nullptr});
-    MDBG_CK(c, cudaEventRecord(c->ev[4], c->st_copy));
-    int rc = run_ka(c, d_bases, d_off, n_reads, B, &plan);
+    if (!packed) MDBG_CK(c, cudaEventRecord(c->ev[4], c->st_copy));
+    int rc = run_ka(c, d_bases, d_off, n_reads, B, &plan, packed ? &prepare : nullptr);
     if (rc == MDBG_ERR_ALPHABET) {  // turn the batch offset into (read, offset) like SURVEY 5 asks
         uint64_t pos = c->h_sc->err_pos;
         uint64_t r = std::upper_bound(read_off, read_off + n_reads + 1, pos) - read_off - 1;

@@ -10,6 +10,7 @@
 
 #include "../../include/mdbg.h"
 #include "mdbg_kernels.h"
+#include "pack_host.h"
 
 namespace mdbg {
 
@@ -73,6 +74,9 @@ struct mdbg_ctx {
     int device = 0, num_sms = 0, ka_grid = 0;
     bool ka_bs = false;                             // bit-sliced K-A variant selected and applicable
     int ka_bs_grid = 0;
+    bool upload_packed = false;                     // mdbg_push_reads: 2-bit planes over PCIe, expanded on the device
+    mdbg::PackPool* pack_pool = nullptr;            // host worker threads of the packer
+    void* h_planes = nullptr; size_t h_planes_cap = 0;   // pinned staging of the bit planes
     void* ka_bs_t4 = nullptr;                       // device copy of the 4-base ntHash tables
     cudaStream_t st = nullptr;
     cudaStream_t st_copy = nullptr;                 // uploads overlapped with K-A

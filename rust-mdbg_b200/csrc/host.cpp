@@ -5,6 +5,7 @@
 #include <vector>
 
 #include "../../include/mdbg.h"
+#include "pack_host.h"
 #include "mdbg_common.cuh"
 
 extern "C" {
@@ -199,6 +200,19 @@ int mdbg_write_sequences(const mdbg_graph* g, const uint8_t* bases, const uint64
     ok = ok && w.end();
     ok = (fclose(f) == 0) && ok;
     return ok ? MDBG_OK : MDBG_ERR_IO;
+}
+
+int mdbg_pack_bases_host(const uint8_t* bases, uint64_t n_bases, uint32_t* planes, uint8_t* bad_tiles, int threads) {
+    if ((!bases && n_bases) || !planes) return MDBG_ERR_BAD_ARG;
+    const uint64_t n_words = (n_bases + 31) / 32;
+    if (bad_tiles) memset(bad_tiles, 0, (size_t)((n_bases + 4095) / 4096));
+    if (threads <= 1) {
+        mdbg::pack_words(bases, n_bases, 0, n_words, planes, bad_tiles);
+    } else {
+        mdbg::PackPool pool(threads);
+        mdbg::pack_parallel(pool, bases, n_bases, 0, n_words, planes, bad_tiles);
+    }
+    return MDBG_OK;
 }
 
 }  // extern "C"

@@ -69,8 +69,6 @@ struct __align__(16) WarpSmem {
     } u;
     Carry carry;
     uint32_t qn;
-    uint32_t flags;                    // look-ahead verdict of the tile (bit 0: unusable)
-    uint32_t hcnt;
     unsigned long long base;
 };
 static_assert(sizeof(uint32_t) * 4 * CW % 16 == 0, "CA..ACC are cleared with 128-bit stores");
@@ -82,6 +80,7 @@ BS_DEV uint32_t bs_shfl(uint32_t v, int src) { return __shfl_sync(0xffffffffu, v
 BS_DEV uint32_t bs_shfl_up(uint32_t v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
 BS_DEV void bs_syncwarp() { __syncwarp(); }
 BS_DEV bool bs_any(bool p) { return __any_sync(0xffffffffu, p) != 0; }
+BS_DEV uint32_t bs_ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
 BS_DEV uint32_t bs_atomic_or_s(uint32_t* p, uint32_t v) { return atomicOr(p, v); }
 BS_DEV uint32_t bs_atomic_add_s(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
 BS_DEV uint32_t bs_atomic_add_g32(unsigned int* p, uint32_t v) { return atomicAdd(p, v); }
@@ -107,6 +106,7 @@ uint32_t bs_shfl(uint32_t v, int src);
 uint32_t bs_shfl_up(uint32_t v, int d);
 void bs_syncwarp();
 bool bs_any(bool p);
+uint32_t bs_ballot(bool p);
 uint32_t bs_atomic_or_s(uint32_t* p, uint32_t v);
 uint32_t bs_atomic_add_s(uint32_t* p, uint32_t v);
 uint32_t bs_atomic_add_g32(unsigned int* p, uint32_t v);
@@ -292,53 +292,46 @@ BS_DEV void process_tile(const KAArgs& A, WarpSmem& sm, const int lane, const ui
         }
         if (lane == 31) sm.cpre[NW] = o;
     }
-    // look-ahead: the first HPC bases after the tile
-    if (lane == 0) {
-        uint32_t ha = 0, hb = 0, hrs = 0, hcnt = 0, unusable = 0;
-        if (t0 + TILE < B) {
-            if (top) {
-                BadAcc hacc{0, 0, 0};
-                uint32_t xa, xb;
-                gather32(sm.raw + 32 * RSTRIDE, xa, xb, hacc);
-                const int64_t left = B - (t0 + TILE);
-                uint32_t hm = HPC ? ((xa ^ ((xa << 1) | (tail31 & 1u))) | (xb ^ ((xb << 1) | (tail31 >> 1)))) : 0xFFFFFFFFu;
-                uint32_t hs = 0;
-                uint64_t r = lbn;
-                int guard = 0;
-                for (; r <= A.n_reads && guard < 64; r++, guard++) {
-                    const int64_t x = (int64_t)bs_ldg64(A.read_off + r) - (t0 + TILE);
-                    if (x >= 32) break;
-                    hs |= 1u << x;
-                }
-                if (guard >= 64) unusable = 1;
-                hm |= hs;
-                if (left < 32) hm &= low_mask((uint32_t)left);
-                if (bad_of(hacc) != 0) unusable = 1;   // conservative: the filler past the batch end is 'A'
-                const uint32_t runs = popc32(hm);
-                while (hm && hcnt < (uint32_t)HALO_RUNS) {   // the first runs, one at a time (top tiles only)
-#if defined(__CUDA_ARCH__)
-                    const uint32_t k = (uint32_t)__ffs((int)hm) - 1u;
-#else
-                    const uint32_t k = (uint32_t)__builtin_ctz(hm);
-#endif
-                    hm &= hm - 1u;
-                    ha |= ((xa >> k) & 1u) << hcnt;
-                    hb |= ((xb >> k) & 1u) << hcnt;
-                    hrs |= ((hs >> k) & 1u) << hcnt;
-                    hcnt++;
-                }
-                if (!(hcnt >= (uint32_t)(L - 1) || (left <= 32 && hcnt == runs))) unusable = 1;
-            } else {
-                const Carry cy = sm.carry;
-                ha = cy.a; hb = cy.b; hrs = cy.rs; hcnt = cy.cnt;
-                if (cy.bad || !cy.ok) unusable = 1;
+    // look-ahead: the first HPC bases after the tile (uniform control flow: every lane takes part)
+    uint32_t hcnt = 0, unusable = 0;
+    if (t0 + TILE < B) {
+        if (top) {                     // from the 32 bytes after the tile: one byte per lane
+            const int64_t left = B - (t0 + TILE);
+            const uint32_t c = sm.raw[32 * RSTRIDE + lane];
+            const bool valid = (int64_t)lane < left;
+            const uint32_t code = (c >> 1) & 3u;
+            uint32_t prevc = bs_shfl_up(code, 1);
+            if (lane == 0) prevc = tail31;
+            uint32_t hs = 0;           // read starts inside the look-ahead (typically none or one)
+            int guard = 0;
+            for (uint64_t r = lbn; r <= A.n_reads && guard < 64; r++, guard++) {
+                const int64_t x = (int64_t)bs_ldg64(A.read_off + r) - (t0 + TILE);
+                if (x >= 32) break;
+                hs |= 1u << x;
             }
-            put_bits(sm.CA, Ctile, ha);
-            put_bits(sm.CB, Ctile, hb);
-            put_bits(sm.RS, Ctile, hrs);
+            const bool rstart = ((hs >> lane) & 1u) != 0;
+            const bool isrun = valid && (!HPC || code != prevc || rstart);
+            const uint32_t hm = bs_ballot(isrun);
+            const bool badb = bs_any(valid && !is_acgt(c));
+            const uint32_t rank = popc32(hm & low_mask((uint32_t)lane)), runs = popc32(hm);
+            hcnt = runs < (uint32_t)HALO_RUNS ? runs : (uint32_t)HALO_RUNS;
+            if (isrun && rank < (uint32_t)HALO_RUNS) {
+                const uint32_t o = Ctile + rank, w = o >> 5, bit = 1u << (o & 31u);
+                if (code & 1u) bs_atomic_or_s(sm.CA + w, bit);
+                if (code & 2u) bs_atomic_or_s(sm.CB + w, bit);
+                if (rstart) bs_atomic_or_s(sm.RS + w, bit);
+            }
+            if (guard >= 64 || badb || !(hcnt >= (uint32_t)(L - 1) || (left <= 32 && hcnt == runs))) unusable = 1;
+        } else {                       // from the tile above, processed just before by this warp
+            const Carry cy = sm.carry;
+            hcnt = cy.cnt;
+            if (cy.bad || !cy.ok) unusable = 1;
+            if (lane == 0) {
+                put_bits(sm.CA, Ctile, cy.a);
+                put_bits(sm.CB, Ctile, cy.b);
+                put_bits(sm.RS, Ctile, cy.rs);
+            }
         }
-        sm.hcnt = hcnt;
-        sm.flags = unusable;
     }
     bs_syncwarp();                     // the rows are dead from here on ...
     if (next.valid) stage_issue(A, sm, lane, next.tile, next.top);   // ... refill them for the next tile
@@ -350,8 +343,8 @@ BS_DEV void process_tile(const KAArgs& A, WarpSmem& sm, const int lane, const ui
             bs_atomic_or_s(sm.RS + (comp >> 5), 1u << (comp & 31u));
         }
     }
-    const uint32_t Ctotal = Ctile + sm.hcnt;
-    bool dirty = tile_bad || (sm.flags & 1u);
+    const uint32_t Ctotal = Ctile + hcnt;
+    bool dirty = tile_bad || unusable;
     bs_syncwarp();
     const uint32_t rs0 = sm.RS[0];     // for the tile below (RS is recycled after P5)
 
@@ -465,7 +458,7 @@ BS_DEV void process_tile(const KAArgs& A, WarpSmem& sm, const int lane, const ui
     if (lane == 0) {
         if (A.dbg) {                   // per-tile state for the emulator-vs-GPU comparison
             uint32_t* d = A.dbg + tile * 8;
-            d[0] = Ctile; d[1] = Ctotal; d[2] = (sm.flags & 1u) | (tile_bad ? 2u : 0u) | (dirty ? 4u : 0u);
+            d[0] = Ctile; d[1] = Ctotal; d[2] = unusable | (tile_bad ? 2u : 0u) | (dirty ? 4u : 0u);
             d[3] = sm.qn; d[4] = dirty ? 0u : accpre[NW]; d[5] = sm.CA[0]; d[6] = sm.CB[0]; d[7] = sm.mraw[0];
         }
         // what the tile below needs to know about this one

@@ -68,6 +68,10 @@ int ka_max_blocks_per_sm(int hpc);
 // on the device)
 cudaError_t ka_launch_list(const KAArgs& A, int hpc, int grid, cudaStream_t st, uint64_t* launches);
 
+// ---- 4:1 upload (expand.cu): bit planes -> ASCII bases in HBM -----------------------------------
+cudaError_t expand_planes(const uint32_t* planes, uint8_t* bases, uint64_t w_begin, uint64_t w_end, int num_sms,
+                          cudaStream_t st, uint64_t* launches);
+
 // ---- K-A, bit-sliced variant (ka_bitslice.cu) -----------------------------------------------
 bool ka_bs_supported(uint32_t l, uint64_t bound);
 constexpr size_t KA_BS_TABLE_BYTES = 256 * 16;

@@ -1,0 +1,160 @@
+// pack_host.cc -- host side of the 4:1 upload of mdbg_push_reads ("pack on host to
+// cut PCIe 4x").  ASCII bases -> two bit planes per 32 bases (plane a = bit 1, plane b = bit 2 of the
+// byte: A 00, C 01, T 10, G 11 -- the 2-bit code of the kernels), validated on the way: a 4 KiB tile
+// holding any byte outside ACGT is flagged and travels as ASCII instead.  The device expands the
+// planes back to ASCII in HBM (expand.cu) and the kernels run unchanged, so what crosses PCIe is 2 bits
+// per base while every result stays bit-identical.  Plain g++ (SSSE3 when available), worker threads.
+#include <stdint.h>
+#include <string.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#if defined(__SSSE3__)
+#include <tmmintrin.h>
+#endif
+
+#include "pack_host.h"
+
+namespace mdbg {
+
+namespace {
+
+inline bool acgt(uint8_t c) { return c == 'A' || c == 'C' || c == 'G' || c == 'T'; }
+
+// one word of 32 bases at p (all 32 readable) -> planes; returns true if every byte is ACGT
+inline bool pack_word(const uint8_t* p, uint32_t& a, uint32_t& b) {
+#if defined(__SSSE3__)
+    const __m128i v0 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(p));
+    const __m128i v1 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(p + 16));
+    // movemask takes bit 7 of every byte: shifting the 16-bit lanes left by 6 (5) brings bit 1 (2) there
+    a = (uint32_t)_mm_movemask_epi8(_mm_slli_epi16(v0, 6)) | ((uint32_t)_mm_movemask_epi8(_mm_slli_epi16(v1, 6)) << 16);
+    b = (uint32_t)_mm_movemask_epi8(_mm_slli_epi16(v0, 5)) | ((uint32_t)_mm_movemask_epi8(_mm_slli_epi16(v1, 5)) << 16);
+    const __m128i lut = _mm_setr_epi8('A', 'C', 'T', 'G', 'A', 'C', 'T', 'G', 'A', 'C', 'T', 'G', 'A', 'C', 'T', 'G');
+    const __m128i three = _mm_set1_epi8(3);
+    const __m128i c0 = _mm_and_si128(_mm_srli_epi16(v0, 1), three), c1 = _mm_and_si128(_mm_srli_epi16(v1, 1), three);
+    const __m128i ok = _mm_and_si128(_mm_cmpeq_epi8(_mm_shuffle_epi8(lut, c0), v0), _mm_cmpeq_epi8(_mm_shuffle_epi8(lut, c1), v1));
+    return _mm_movemask_epi8(ok) == 0xFFFF;
+#else
+    uint32_t aa = 0, bb = 0;
+    bool ok = true;
+    for (int k = 0; k < 32; k++) {
+        const uint8_t c = p[k];
+        aa |= (uint32_t)((c >> 1) & 1u) << k;
+        bb |= (uint32_t)((c >> 2) & 1u) << k;
+        ok = ok && acgt(c);
+    }
+    a = aa; b = bb;
+    return ok;
+#endif
+}
+
+}  // namespace
+
+void pack_words(const uint8_t* bases, uint64_t n_bases, uint64_t w_begin, uint64_t w_end, uint32_t* planes,
+                uint8_t* bad_tiles) {
+    for (uint64_t w = w_begin; w < w_end; w++) {
+        const uint64_t off = w * 32;
+        uint32_t a, b;
+        bool ok;
+        if (off + 32 <= n_bases) {
+            ok = pack_word(bases + off, a, b);
+        } else {                       // ragged end of the batch: pad with 'A' (code 0)
+            uint8_t buf[32];
+            memset(buf, 'A', 32);
+            if (off < n_bases) memcpy(buf, bases + off, n_bases - off);
+            ok = pack_word(buf, a, b);
+        }
+        planes[2 * w] = a;
+        planes[2 * w + 1] = b;
+        if (!ok && bad_tiles) bad_tiles[w / PACK_TILE_WORDS] = 1;   // racing writers store the same value
+    }
+}
+
+// ---- a small persistent worker pool --------------------------------------------------------------
+struct PackPool::Impl {
+    std::vector<std::thread> workers;
+    std::mutex mu;
+    std::condition_variable cv_work, cv_done;
+    const std::function<void(uint64_t)>* fn = nullptr;
+    uint64_t n_items = 0;
+    std::atomic<uint64_t> next{0};
+    uint64_t generation = 0;
+    int active = 0;
+    bool stop = false;
+
+    void work() {
+        for (;;) {
+            const uint64_t i = next.fetch_add(1, std::memory_order_relaxed);
+            if (i >= n_items) break;
+            (*fn)(i);
+        }
+    }
+    void loop() {
+        uint64_t seen = 0;
+        std::unique_lock<std::mutex> lk(mu);
+        for (;;) {
+            cv_work.wait(lk, [&] { return stop || generation != seen; });
+            if (stop) return;
+            seen = generation;
+            lk.unlock();
+            work();
+            lk.lock();
+            if (--active == 0) cv_done.notify_all();
+        }
+    }
+};
+
+PackPool::PackPool(int threads) : impl_(new Impl()) {
+    if (threads < 1) threads = 1;
+    for (int i = 0; i + 1 < threads; i++) impl_->workers.emplace_back([this] { impl_->loop(); });
+}
+
+PackPool::~PackPool() {
+    {
+        std::lock_guard<std::mutex> lk(impl_->mu);
+        impl_->stop = true;
+    }
+    impl_->cv_work.notify_all();
+    for (auto& t : impl_->workers) t.join();
+    delete impl_;
+}
+
+int PackPool::threads() const { return (int)impl_->workers.size() + 1; }
+
+void PackPool::parallel_for(uint64_t n_items, const std::function<void(uint64_t)>& fn) {
+    if (n_items == 0) return;
+    if (impl_->workers.empty() || n_items == 1) {
+        for (uint64_t i = 0; i < n_items; i++) fn(i);
+        return;
+    }
+    {
+        std::lock_guard<std::mutex> lk(impl_->mu);
+        impl_->fn = &fn;
+        impl_->n_items = n_items;
+        impl_->next.store(0, std::memory_order_relaxed);
+        impl_->active = (int)impl_->workers.size();
+        impl_->generation++;
+    }
+    impl_->cv_work.notify_all();
+    impl_->work();                     // the caller works too
+    std::unique_lock<std::mutex> lk(impl_->mu);
+    impl_->cv_done.wait(lk, [&] { return impl_->active == 0; });
+    impl_->fn = nullptr;
+}
+
+void pack_parallel(PackPool& pool, const uint8_t* bases, uint64_t n_bases, uint64_t w_begin, uint64_t w_end,
+                   uint32_t* planes, uint8_t* bad_tiles) {
+    const uint64_t BLK = 64 * PACK_TILE_WORDS;     // 64 tiles (256 KiB of bases) per work item
+    const uint64_t first = w_begin / BLK, last = (w_end + BLK - 1) / BLK;
+    pool.parallel_for(last - first, [&](uint64_t i) {
+        const uint64_t lo = std::max(w_begin, (first + i) * BLK), hi = std::min(w_end, (first + i + 1) * BLK);
+        if (lo < hi) pack_words(bases, n_bases, lo, hi, planes, bad_tiles);
+    });
+}
+
+}  // namespace mdbg

@@ -48,7 +48,8 @@ class CTimings(ctypes.Structure):
                [("launches_push", u64), ("launches_finish", u64), ("ka_launches", u64),
                 ("ka_ms_sum", ctypes.c_float), ("table_attempts", u32), ("ka_dense_tiles", u32),
                 ("ms_ka_kernel", ctypes.c_float), ("ms_ka_start", ctypes.c_float),
-                ("ka_variant_used", u32), ("ka_dirty_tiles", u32)]
+                ("ka_variant_used", u32), ("ka_dirty_tiles", u32), ("upload_packed", u32),
+                ("upload_ascii_tiles", u32)]
 
 
 class CSynth(ctypes.Structure):
@@ -105,6 +106,7 @@ SYMBOLS = {
     "mdbg_tuple_fingerprint": (u64, [vp, u32, u64]),
     "mdbg_write_gfa": (ctypes.c_int, [GP, ctypes.c_char_p]),
     "mdbg_write_sequences": (ctypes.c_int, [GP, vp, vp, ctypes.c_char_p, ctypes.c_int]),
+    "mdbg_pack_bases_host": (ctypes.c_int, [vp, u64, vp, vp, ctypes.c_int]),
 }
 
 _lib = None

@@ -12,6 +12,7 @@
 #include <thread>
 #include <vector>
 
+#include "../../rust-mdbg_b200/csrc/expand_math.h"
 #include "../../rust-mdbg_b200/csrc/ka_bitslice_body.h"
 
 namespace {
@@ -47,6 +48,14 @@ bool bs_any(bool p) {
     sync();
     bool r = false;
     for (int i = 0; i < 32; i++) r = r || g_warp->vote[i];
+    sync();
+    return r;
+}
+uint32_t bs_ballot(bool p) {
+    g_warp->vote[g_lane] = p ? 1u : 0u;
+    sync();
+    uint32_t r = 0;
+    for (int i = 0; i < 32; i++) r |= g_warp->vote[i] << i;
     sync();
     return r;
 }
@@ -160,5 +169,6 @@ void bs_model_planes(const uint8_t* p32, uint32_t* a, uint32_t* b, uint32_t* bad
 }
 void bs_model_pext(uint32_t m, uint32_t* x, uint32_t* y) { bs::pext_pair(m, *x, *y); }
 uint32_t bs_model_select(uint32_t m, uint32_t k) { return bs::select_bit(m, k); }
+uint32_t bs_model_expand4(uint32_t a, uint32_t b) { return mdbg::expand4(a, b); }
 
 }  // extern "C"

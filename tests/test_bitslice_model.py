@@ -350,3 +350,32 @@ def test_model_window_across_long_homopolymer(model, oracle):
         assert len(h) > 0
     dirty, n, nt = run_model(model, oracle, seqs, l, d, group=3, return_dirty=True)
     assert len(dirty) >= 1 and n > 0
+
+
+@pytest.mark.parametrize("group", [1, 4])
+def test_model_read_start_inside_look_ahead(model, oracle, group):
+    """An l-mer that would be a minimizer straddles a tile edge AND a read boundary lying in the
+    look-ahead of the lower tile: it belongs to no read and must not be emitted (top-tile and
+    carried look-ahead)."""
+    l, d = 12, 0.0039
+    bound = oracle.lib().orc_hash_bound(d)
+    rng = np.random.default_rng(55 + group)
+    seqs, total = [], 0
+    for i in range(24):
+        w = passing_lmer(rng, l, bound, lambda s: True)
+        edge = (total // TILE + 2) * TILE                  # a tile edge comfortably ahead
+        delta = int(rng.integers(1, 11))                   # the next read starts delta bytes after the edge
+        j = int(rng.integers(1, l - delta)) + delta        # bases of w before the read boundary (> delta)
+        start_w = edge + delta - j                         # w[0] lies before the edge: owned by the lower tile
+        pre = bytearray(rand_seq(rng, start_w - total))
+        if pre and pre[-1] == w[0]:
+            pre[-1] = b"ACGT"[(b"ACGT".index(w[0]) + 1) % 4]
+        seqs.append(bytes(pre) + w[:j])
+        total += len(seqs[-1])
+        assert total == edge + delta
+        tail = bytearray(rand_seq(rng, int(rng.integers(50, 3000))))
+        if tail[0] == w[-1]:
+            tail[0] = b"ACGT"[(b"ACGT".index(w[-1]) + 1) % 4]
+        seqs.append(w[j:] + bytes(tail))
+        total += len(seqs[-1])
+    run_model(model, oracle, seqs, l, d, group=group, max_dirty=0)
