@@ -328,11 +328,13 @@ def main():
         packed_up = bool(tm_last.get("upload_packed", 0))
         # bytes that crossed PCIe host->device: the bases as 2-bit planes (8 B per 32 bases) plus any 4 KiB tile
         # sent as ASCII, or the ASCII bases; plus the read offsets
-        h2d_bases = ((total + 31) // 32) * 8 + 4096 * int(tm_last.get("upload_ascii_tiles", 0)) if packed_up else total
+        h2d_bases = int(tm_last.get("upload_h2d_bytes", total)) if packed_up else total
         e2e = {"value": bases_all * steps / (e2e_ms * 1e-3) / 1e9, "unit": "Gbases/s",
                "h2d_bytes_per_step": int(h2d_bases + 8 * (reads_per_rank + 1)), "d2h_bytes_per_step": int(d2h_bytes),
-               "upload": "2-bit planes packed by %s host threads inside the call, expanded on the device" %
-                         os.environ.get("MDBG_PACK_THREADS", "min(32, nproc / local ranks)") if packed_up else "ASCII",
+               "upload": ("%s: 2-bit planes packed by %s host threads inside the call and expanded on the device; "
+                          "%d of the 4 KiB tiles went unpacked (copy engine idle / bytes outside ACGT)" %
+                          (os.environ.get("MDBG_UPLOAD", "hybrid"), os.environ.get("MDBG_PACK_THREADS", "min(32, nproc / local ranks)"),
+                           int(tm_last.get("upload_ascii_tiles", 0)))) if packed_up else "ASCII",
                "ms_per_step": e2e_ms / steps, "timing": "host wall clock around K steps, max over ranks",
                "stage_ms_per_step": {k_: v_ / steps for k_, v_ in e2e_parts.items()}}
         ctx.host_free_pinned(hb); ctx.host_free_pinned(ho)

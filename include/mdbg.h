@@ -166,7 +166,9 @@ typedef struct {
     uint32_t ka_variant_used;                  /* 1 classic, 2 bit-sliced (last push)          */
     uint32_t ka_dirty_tiles;                   /* bit-sliced: tiles handed to the classic kernel */
     uint32_t upload_packed;                    /* last mdbg_push_reads: 1 = bases crossed PCIe as 2-bit planes */
-    uint32_t upload_ascii_tiles;               /* ... of which 4 KiB tiles sent as ASCII (bytes outside ACGT)  */
+    uint32_t upload_ascii_tiles;               /* ... 4 KiB tiles sent as ASCII instead (bytes outside ACGT, or
+                                                  chunks sent unpacked because the copy engine was idle)       */
+    uint64_t upload_h2d_bytes;                 /* bytes of bases that crossed PCIe in the last mdbg_push_reads */
 } mdbg_timings;
 int mdbg_get_timings(mdbg_ctx* ctx, mdbg_timings* out);
 void* mdbg_stream(mdbg_ctx* ctx);              /* the cudaStream_t all kernels run on        */
@@ -227,7 +229,8 @@ int mdbg_write_sequences(const mdbg_graph* g, const uint8_t* bases, const uint64
 
 /* ---- host ingest: 2-bit packing for the 4:1 upload (reference side: the reads the
  *      parser hands to Read::extract, main.rs:163-178,830-839) ----------------------------------
- * mdbg_push_reads packs host buffers like this itself (MDBG_UPLOAD=ascii turns it off); the entry
+ * mdbg_push_reads packs host buffers like this itself (MDBG_UPLOAD=ascii turns it off, =packed packs
+ * every chunk, default: chunks go unpacked whenever the copy engine would otherwise idle); the entry
  * point is public for hosts that pack while they parse.  planes[2w], planes[2w+1] = bit 1 and bit 2
  * of the 32 bases [32w, 32w+32) (A 00, C 01, T 10, G 11; bases past n_bases read as A); bad_tiles[t]
  * (may be NULL) is set to 1 when the 4096-base tile t holds a byte outside ACGT -- such tiles must

@@ -131,8 +131,9 @@ int mdbg_ctx_create(const mdbg_params* p, mdbg_ctx** out) {
         }
     }
     {   // host buffers travel 4:1 packed (pack_host.cc) unless MDBG_UPLOAD=ascii
-        const char* e = getenv("MDBG_UPLOAD");
+        const char* e = getenv("MDBG_UPLOAD");      // ascii | packed | hybrid (default)
         c->upload_packed = !(e && !strcmp(e, "ascii"));
+        c->upload_hybrid = !(e && !strcmp(e, "packed"));
     }
     memset(&c->tm, 0, sizeof(c->tm));
     *out = c;
@@ -418,7 +419,8 @@ int mdbg_push_reads(mdbg_ctx* c, const uint8_t* bases, const uint64_t* read_off,
     // ---- 4:1 upload: pack on the host (worker threads), copy the bit planes, expand on the device ----
     const uint64_t n_words = (B + 31) / 32;
     std::vector<uint8_t> bad_tiles;
-    uint64_t CHW = std::max<uint64_t>(2 * PACK_TILE_WORDS, (CH / 32) / PACK_TILE_WORDS * PACK_TILE_WORDS);   // words per chunk
+    // words per chunk of the packed / hybrid upload: a quarter of the ASCII chunk (8 MB of bases by default)
+    uint64_t CHW = std::max<uint64_t>(2 * PACK_TILE_WORDS, (CH / 4 / 32) / PACK_TILE_WORDS * PACK_TILE_WORDS);
     std::function<int(size_t)> prepare;
     if (packed) {
         if (!c->pack_pool) {
@@ -452,10 +454,30 @@ int mdbg_push_reads(mdbg_ctx* c, const uint8_t* bases, const uint64_t* read_off,
             plan.push_back(KaChunk{te, c->copy_ev[nev]});
             nev++;
         }
-        prepare = [&, n_words, CHW](size_t ci) -> int {
+        // Two resources move the batch: the host cores (packing) and the copy engine.  A chunk is packed
+        // unless the copy engine has run dry, in which case it is sent as it is (ASCII) -- the engine then
+        // has work for the time the cores need to pack the next chunks.  MDBG_UPLOAD=packed packs everything.
+        const bool hybrid = c->upload_hybrid;
+        prepare = [&, n_words, CHW, hybrid](size_t ci) -> int {
             const uint64_t wa = (uint64_t)ci * CHW, wb = std::min(n_words, wa + CHW);
             uint32_t* hp = (uint32_t*)c->h_planes;
+            bool engine_idle = ci == 0;
+            if (hybrid && ci > 0) {
+                const cudaError_t q = cudaEventQuery(c->copy_ev[ci - 1]);
+                engine_idle = q == cudaSuccess;
+                if (q == cudaErrorNotReady) (void)cudaGetLastError();   // "not ready" is an answer, not an error
+            }
+            if (hybrid && engine_idle) {
+                const uint64_t off = wa * 32, end = std::min<uint64_t>(B, wb * 32);
+                MDBG_CK(c, cudaMemcpyAsync(d_bases.p + off, bases + off, end - off, cudaMemcpyHostToDevice, c->st_copy));
+                MDBG_CK(c, cudaEventRecord(c->copy_ev[ci], c->st_copy));
+                if (wb == n_words) MDBG_CK(c, cudaEventRecord(c->ev[4], c->st_copy));
+                c->tm.upload_ascii_tiles += (uint32_t)((wb - wa + PACK_TILE_WORDS - 1) / PACK_TILE_WORDS);
+                c->tm.upload_h2d_bytes += end - off;
+                return MDBG_OK;        // run_ka makes the compute stream wait for copy_ev[ci]
+            }
             pack_parallel(*c->pack_pool, bases, B, wa, wb, hp, bad_tiles.data());
+            c->tm.upload_h2d_bytes += (wb - wa) * 8;
             MDBG_CK(c, cudaMemcpyAsync(d_planes.p + 2 * wa, hp + 2 * wa, (wb - wa) * 8, cudaMemcpyHostToDevice, c->st_copy));
             MDBG_CK(c, cudaEventRecord(c->copy_ev[ci], c->st_copy));
             if (wb == n_words) MDBG_CK(c, cudaEventRecord(c->ev[4], c->st_copy));
@@ -470,6 +492,7 @@ int mdbg_push_reads(mdbg_ctx* c, const uint8_t* bases, const uint64_t* read_off,
                 const uint64_t off = t * (uint64_t)KA_TILE, end = std::min<uint64_t>(B, t2 * (uint64_t)KA_TILE);
                 MDBG_CK(c, cudaMemcpyAsync(d_bases.p + off, bases + off, end - off, cudaMemcpyHostToDevice, c->st));
                 c->tm.upload_ascii_tiles += (uint32_t)(t2 - t);
+                c->tm.upload_h2d_bytes += end - off;
                 t = t2;
             }
             return MDBG_OK;
@@ -478,6 +501,7 @@ int mdbg_push_reads(mdbg_ctx* c, const uint8_t* bases, const uint64_t* read_off,
     }
     c->tm.upload_packed = packed ? 1 : 0;
     c->tm.upload_ascii_tiles = 0;
+    c->tm.upload_h2d_bytes = packed ? 0 : B;
     while (b0 < B) {
         uint64_t target = b0 + CH;
         if (B - b0 <= CH + CH / 4 && B - b0 > CH / 2) target = B - CH / 4;   // short last chunk: short tail after the copy

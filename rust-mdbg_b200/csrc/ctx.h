@@ -74,6 +74,7 @@ struct mdbg_ctx {
     int device = 0, num_sms = 0, ka_grid = 0;
     bool ka_bs = false;                             // bit-sliced K-A variant selected and applicable
     int ka_bs_grid = 0;
+    bool upload_hybrid = false;                     // ... and chunks go as ASCII whenever the copy engine runs dry
     bool upload_packed = false;                     // mdbg_push_reads: 2-bit planes over PCIe, expanded on the device
     mdbg::PackPool* pack_pool = nullptr;            // host worker threads of the packer
     void* h_planes = nullptr; size_t h_planes_cap = 0;   // pinned staging of the bit planes
