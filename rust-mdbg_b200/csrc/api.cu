@@ -11,6 +11,7 @@
 #include <string>
 #include <vector>
 
+#include <chrono>
 #include <functional>
 #include <thread>
 
@@ -457,17 +458,21 @@ int mdbg_push_reads(mdbg_ctx* c, const uint8_t* bases, const uint64_t* read_off,
         // Two resources move the batch: the host cores (packing) and the copy engine.  A chunk is packed
         // unless the copy engine has run dry, in which case it is sent as it is (ASCII) -- the engine then
         // has work for the time the cores need to pack the next chunks.  MDBG_UPLOAD=packed packs everything.
+        // The decision is made on a host-side model of the engine's backlog: bytes queued so far at the link
+        // rate (MDBG_PCIE_GBPS, default 50) against the measured packing time of a chunk.
         const bool hybrid = c->upload_hybrid;
-        prepare = [&, n_words, CHW, hybrid](size_t ci) -> int {
+        double link_rate = 50e9;
+        if (const char* e = getenv("MDBG_PCIE_GBPS")) { double v = atof(e); if (v >= 1 && v <= 1000) link_rate = v * 1e9; }
+        double busy_until = 0, pack_s_per_byte = 1.0 / 40e9;
+        auto now_s = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+        prepare = [&, n_words, CHW, hybrid, link_rate, busy_until, pack_s_per_byte, now_s](size_t ci) mutable -> int {
             const uint64_t wa = (uint64_t)ci * CHW, wb = std::min(n_words, wa + CHW);
             uint32_t* hp = (uint32_t*)c->h_planes;
-            bool engine_idle = ci == 0;
-            if (hybrid && ci > 0) {
-                const cudaError_t q = cudaEventQuery(c->copy_ev[ci - 1]);
-                engine_idle = q == cudaSuccess;
-                if (q == cudaErrorNotReady) (void)cudaGetLastError();   // "not ready" is an answer, not an error
-            }
-            if (hybrid && engine_idle) {
+            const uint64_t chunk_bytes = std::min<uint64_t>(B, wb * 32) - wa * 32;
+            const double t_dec = now_s();
+            const double backlog = std::max(0.0, busy_until - t_dec);
+            if (hybrid && backlog < pack_s_per_byte * (double)chunk_bytes) {   // the engine would run dry while we pack
+                busy_until = std::max(t_dec, busy_until) + (double)chunk_bytes / link_rate;
                 const uint64_t off = wa * 32, end = std::min<uint64_t>(B, wb * 32);
                 MDBG_CK(c, cudaMemcpyAsync(d_bases.p + off, bases + off, end - off, cudaMemcpyHostToDevice, c->st_copy));
                 MDBG_CK(c, cudaEventRecord(c->copy_ev[ci], c->st_copy));
@@ -477,6 +482,11 @@ int mdbg_push_reads(mdbg_ctx* c, const uint8_t* bases, const uint64_t* read_off,
                 return MDBG_OK;        // run_ka makes the compute stream wait for copy_ev[ci]
             }
             pack_parallel(*c->pack_pool, bases, B, wa, wb, hp, bad_tiles.data());
+            {
+                const double t_end = now_s(), per_byte = (t_end - t_dec) / (double)std::max<uint64_t>(1, chunk_bytes);
+                pack_s_per_byte = 0.5 * pack_s_per_byte + 0.5 * per_byte;
+                busy_until = std::max(t_end, busy_until) + (double)(wb - wa) * 8 / link_rate;
+            }
             c->tm.upload_h2d_bytes += (wb - wa) * 8;
             MDBG_CK(c, cudaMemcpyAsync(d_planes.p + 2 * wa, hp + 2 * wa, (wb - wa) * 8, cudaMemcpyHostToDevice, c->st_copy));
             MDBG_CK(c, cudaEventRecord(c->copy_ev[ci], c->st_copy));

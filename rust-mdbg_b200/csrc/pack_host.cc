@@ -115,6 +115,18 @@ void pack_words(const uint8_t* bases, uint64_t n_bases, uint64_t w_begin, uint64
 }
 
 // ---- a small persistent worker pool --------------------------------------------------------------
+// Work arrives in bursts (one parallel_for per upload chunk, every ~100 us): workers poll for the next
+// burst for a short while before they go to sleep on the condition variable, and the caller polls for
+// completion -- a futex wake-up per chunk and worker would cost as much as the packing itself.
+namespace {
+inline void cpu_relax() {
+#if defined(MDBG_PACK_X86)
+    _mm_pause();
+#endif
+}
+constexpr int SPIN_LIMIT = 1 << 15;    // ~0.2-0.5 ms of polling
+}  // namespace
+
 struct PackPool::Impl {
     std::vector<std::thread> workers;
     std::mutex mu;
@@ -122,9 +134,9 @@ struct PackPool::Impl {
     const std::function<void(uint64_t)>* fn = nullptr;
     uint64_t n_items = 0;
     std::atomic<uint64_t> next{0};
-    uint64_t generation = 0;
-    int active = 0;
-    bool stop = false;
+    std::atomic<uint64_t> generation{0};
+    std::atomic<int> active{0};
+    std::atomic<bool> stop{false};
 
     void work() {
         for (;;) {
@@ -135,15 +147,20 @@ struct PackPool::Impl {
     }
     void loop() {
         uint64_t seen = 0;
-        std::unique_lock<std::mutex> lk(mu);
         for (;;) {
-            cv_work.wait(lk, [&] { return stop || generation != seen; });
-            if (stop) return;
-            seen = generation;
-            lk.unlock();
+            int spins = 0;
+            while (generation.load(std::memory_order_acquire) == seen && !stop.load(std::memory_order_acquire)) {
+                if (++spins < SPIN_LIMIT) { cpu_relax(); continue; }
+                std::unique_lock<std::mutex> lk(mu);
+                cv_work.wait(lk, [&] { return stop.load() || generation.load() != seen; });
+            }
+            if (stop.load(std::memory_order_acquire)) return;
+            seen = generation.load(std::memory_order_acquire);
             work();
-            lk.lock();
-            if (--active == 0) cv_done.notify_all();
+            if (active.fetch_sub(1, std::memory_order_acq_rel) == 1) {
+                std::lock_guard<std::mutex> lk(mu);
+                cv_done.notify_all();
+            }
         }
     }
 };
@@ -156,7 +173,7 @@ PackPool::PackPool(int threads) : impl_(new Impl()) {
 PackPool::~PackPool() {
     {
         std::lock_guard<std::mutex> lk(impl_->mu);
-        impl_->stop = true;
+        impl_->stop.store(true, std::memory_order_release);
     }
     impl_->cv_work.notify_all();
     for (auto& t : impl_->workers) t.join();
@@ -172,23 +189,27 @@ void PackPool::parallel_for(uint64_t n_items, const std::function<void(uint64_t)
         return;
     }
     {
-        std::lock_guard<std::mutex> lk(impl_->mu);
+        std::lock_guard<std::mutex> lk(impl_->mu);   // a worker about to sleep sees the new generation
         impl_->fn = &fn;
         impl_->n_items = n_items;
         impl_->next.store(0, std::memory_order_relaxed);
-        impl_->active = (int)impl_->workers.size();
-        impl_->generation++;
+        impl_->active.store((int)impl_->workers.size(), std::memory_order_relaxed);
+        impl_->generation.fetch_add(1, std::memory_order_release);
     }
     impl_->cv_work.notify_all();
     impl_->work();                     // the caller works too
-    std::unique_lock<std::mutex> lk(impl_->mu);
-    impl_->cv_done.wait(lk, [&] { return impl_->active == 0; });
+    int spins = 0;
+    while (impl_->active.load(std::memory_order_acquire) != 0) {
+        if (++spins < SPIN_LIMIT) { cpu_relax(); continue; }
+        std::unique_lock<std::mutex> lk(impl_->mu);
+        impl_->cv_done.wait(lk, [&] { return impl_->active.load() == 0; });
+    }
     impl_->fn = nullptr;
 }
 
 void pack_parallel(PackPool& pool, const uint8_t* bases, uint64_t n_bases, uint64_t w_begin, uint64_t w_end,
                    uint32_t* planes, uint8_t* bad_tiles) {
-    const uint64_t BLK = 64 * PACK_TILE_WORDS;     // 64 tiles (256 KiB of bases) per work item
+    const uint64_t BLK = 16 * PACK_TILE_WORDS;     // 16 tiles (64 KiB of bases) per work item
     const uint64_t first = w_begin / BLK, last = (w_end + BLK - 1) / BLK;
     pool.parallel_for(last - first, [&](uint64_t i) {
         const uint64_t lo = std::max(w_begin, (first + i) * BLK), hi = std::min(w_end, (first + i + 1) * BLK);

@@ -376,3 +376,37 @@ def test_degenerate_inputs(mdbg, oracle):
         ctx.push_reads(b1, o1); ctx.push_reads(b0, o0); ctx.push_reads(b2, o2)
         bases, off = pack_reads(seqs)
         compare_graph(ctx.finish(), oracle.build_graph(bases, off, 5, 10, 0.01))
+
+
+@pytest.mark.parametrize("mode,gbps", [("ascii", None), ("packed", None), ("hybrid", "1000"), ("hybrid", "3"), ("hybrid", None)])
+def test_upload_modes_equal_oracle(mdbg, oracle, mode, gbps, monkeypatch):
+    """mdbg_push_reads moves host buffers as ASCII, as 2-bit planes packed on the host and expanded on the
+    device, or as a mix decided chunk by chunk: all three must give the oracle's minimizers and graph.
+    256 KiB chunks so that a 3 MB batch crosses many chunk boundaries (N, homopolymers and tiny reads on them)."""
+    monkeypatch.setenv("MDBG_UPLOAD", mode)
+    monkeypatch.setenv("MDBG_UPLOAD_CHUNK_MB", "1")
+    if gbps:
+        monkeypatch.setenv("MDBG_PCIE_GBPS", gbps)
+    else:
+        monkeypatch.delenv("MDBG_PCIE_GBPS", raising=False)
+    rng = np.random.default_rng(77)
+    seqs = genome_reads(rng, 200000, 260, mean=11000, sd=3000, err=0.002)
+    seqs[3] = seqs[3][:500] + b"N" * 37 + seqs[3][537:]
+    seqs[40] = b"A" * 300000 + seqs[40]                     # a homopolymer across a chunk boundary
+    seqs[41] = b"N" * 5000
+    seqs[100:100] = [b"", b"ACGT", b"T" * 9000]
+    bases, off = pack_reads(seqs)
+    assert len(bases) > 10 * 262144
+    k, l, d = 8, 12, 0.003
+    with mdbg.Context(mdbg.Params(k=k, l=l, density=d, min_abundance=2, presimp=0.01)) as ctx:
+        ctx.push_reads(bases, off)
+        tm = ctx.timings()
+        h, p, mo = ctx.get_minimizers()
+        g = ctx.finish()
+    assert tm["upload_packed"] == (0 if mode == "ascii" else 1)
+    if mode == "packed":
+        assert 0 < tm["upload_ascii_tiles"] < 20            # only the tiles holding N
+        assert tm["upload_h2d_bytes"] < len(bases) // 3
+    o = oracle.build_graph(bases, off, k, l, d, 2, 0.01)
+    assert np.array_equal(h, o.m_hash) and np.array_equal(p, o.m_pos) and np.array_equal(mo, o.m_off)
+    compare_graph(g, o, check_seqlines=False)
