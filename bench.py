@@ -252,7 +252,9 @@ def main():
     achieved = alg_bytes / (ka_avg_ms * 1e-3) / 1e9
     peak, peak_src = measured_peak()
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "ka_traffic.json")
+    # DRAM bytes of one launch from the committed ncu capture of the kernel variant that ran
+    tp = os.path.join(ROOT, "profiles", "ka_traffic_bitslice.json" if int(tm.get("ka_variant_used", 1)) == 2
+                      else "ka_traffic.json")
     if os.path.exists(tp):
         try:
             tj = json.load(open(tp))
