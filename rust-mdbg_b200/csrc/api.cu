@@ -217,6 +217,8 @@ static int ensure_arena(mdbg_ctx* c, uint64_t m_items, uint64_t r_items) {
     return MDBG_OK;
 }
 
+constexpr uint64_t UPLOAD_SLOTS = 8;   // chunk-sized pinned staging slots of the packed upload
+
 // One launch of K-A covers tiles [prev tile_end, tile_end) and may first wait for an upload event.
 struct KaChunk { uint64_t tile_end; cudaEvent_t wait; };
 
@@ -431,7 +433,10 @@ int mdbg_push_reads(mdbg_ctx* c, const uint8_t* bases, const uint64_t* read_off,
             if (const char* e = getenv("MDBG_PACK_THREADS")) { long v = atol(e); if (v >= 1 && v <= 256) nt = (int)v; }
             c->pack_pool = new PackPool(nt);
         }
-        const size_t need = (size_t)n_words * 8;
+        // pinned staging: a ring of UPLOAD_SLOTS chunk-sized slots (a slot is reused once the copy that read
+        // it has completed), not a second copy of the batch
+        const uint64_t n_chunks = (n_words + CHW - 1) / CHW;
+        const size_t need = (size_t)std::min<uint64_t>(n_chunks, UPLOAD_SLOTS) * CHW * 8;
         if (c->h_planes_cap < need) {
             if (c->h_planes) cudaFreeHost(c->h_planes);
             c->h_planes = nullptr; c->h_planes_cap = 0;
@@ -441,7 +446,6 @@ int mdbg_push_reads(mdbg_ctx* c, const uint8_t* bases, const uint64_t* read_off,
         }
         MDBG_CK(c, d_planes.get(c->pool, n_words * 2));
         bad_tiles.assign(n_tiles, 0);
-        const uint64_t n_chunks = (n_words + CHW - 1) / CHW;
         for (uint64_t ci = 0; ci < n_chunks; ci++) {
             if (nev == c->copy_ev.size()) {
                 cudaEvent_t ev;
@@ -467,7 +471,9 @@ int mdbg_push_reads(mdbg_ctx* c, const uint8_t* bases, const uint64_t* read_off,
         auto now_s = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
         prepare = [&, n_words, CHW, hybrid, link_rate, busy_until, pack_s_per_byte, now_s](size_t ci) mutable -> int {
             const uint64_t wa = (uint64_t)ci * CHW, wb = std::min(n_words, wa + CHW);
-            uint32_t* hp = (uint32_t*)c->h_planes;
+            // this chunk's slot of the staging ring, addressed as if the ring were the whole batch
+            uint32_t* hp = reinterpret_cast<uint32_t*>(reinterpret_cast<uintptr_t>(c->h_planes) +
+                                                       8 * ((ci % UPLOAD_SLOTS) * CHW) - 8 * wa);
             const uint64_t chunk_bytes = std::min<uint64_t>(B, wb * 32) - wa * 32;
             const double t_dec = now_s();
             const double backlog = std::max(0.0, busy_until - t_dec);
@@ -481,6 +487,7 @@ int mdbg_push_reads(mdbg_ctx* c, const uint8_t* bases, const uint64_t* read_off,
                 c->tm.upload_h2d_bytes += end - off;
                 return MDBG_OK;        // run_ka makes the compute stream wait for copy_ev[ci]
             }
+            if (ci >= UPLOAD_SLOTS) MDBG_CK(c, cudaEventSynchronize(c->copy_ev[ci - UPLOAD_SLOTS]));   // slot free again
             pack_parallel(*c->pack_pool, bases, B, wa, wb, hp, bad_tiles.data());
             {
                 const double t_end = now_s(), per_byte = (t_end - t_dec) / (double)std::max<uint64_t>(1, chunk_bytes);
