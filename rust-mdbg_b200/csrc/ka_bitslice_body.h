@@ -86,13 +86,6 @@ BS_DEV uint32_t bs_atomic_add_s(uint32_t* p, uint32_t v) { return atomicAdd(p, v
 BS_DEV uint32_t bs_atomic_add_g32(unsigned int* p, uint32_t v) { return atomicAdd(p, v); }
 BS_DEV unsigned long long bs_atomic_add_g64(unsigned long long* p, unsigned long long v) { return atomicAdd(p, v); }
 BS_DEV uint64_t bs_ldg64(const uint64_t* p) { return __ldg(p); }
-BS_DEV T4Entry bs_ldg_t4(const T4Entry* p) {
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
-    T4Entry e;
-    e.f = ((uint64_t)v.y << 32) | v.x;
-    e.r = ((uint64_t)v.w << 32) | v.z;
-    return e;
-}
 // 16 bytes global -> shared without a register round trip (LDGSTS); completion: bs_stage_wait()
 BS_DEV void bs_cp_async16(uint8_t* dst_smem, const uint8_t* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src)
@@ -112,7 +105,6 @@ uint32_t bs_atomic_add_s(uint32_t* p, uint32_t v);
 uint32_t bs_atomic_add_g32(unsigned int* p, uint32_t v);
 unsigned long long bs_atomic_add_g64(unsigned long long* p, unsigned long long v);
 inline uint64_t bs_ldg64(const uint64_t* p) { return *p; }
-inline T4Entry bs_ldg_t4(const T4Entry* p) { return *p; }
 inline void bs_cp_async16(uint8_t* dst, const uint8_t* src) { __builtin_memcpy(dst, src, 16); }
 inline void bs_stage_commit() {}
 inline void bs_stage_wait() {}
