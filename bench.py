@@ -31,6 +31,10 @@ WORKLOADS = {
                      desc="synthetic E. coli 5 Mbp HiFi 50x, k=21 l=12 d=0.003"),
     "dmel50x": dict(genome_len=140_000_000, coverage=50.0, k=35, l=12, density=0.002,
                     desc="synthetic D. melanogaster 140 Mbp HiFi 50x, k=35 l=12 d=0.002"),
+    # BASELINE config 4 as weak-scaling shards: 6.5x of a 3 Gbp genome per GPU (19.5 Gbases, 19.5 GB of ASCII
+    # bases in HBM) = the 52x / 156 Gbases job on 8 GPUs.  Not measured in round 1.
+    "human52x_per8": dict(genome_len=3_000_000_000, coverage=6.5, k=35, l=12, density=0.002,
+                          desc="synthetic human 3 Gbp HiFi, 6.5x per GPU (52x on 8 GPUs), k=35 l=12 d=0.002"),
     "tiny": dict(genome_len=200_000, coverage=20.0, k=21, l=12, density=0.003, desc="smoke-size"),
 }
 MIN_ABUNDANCE, PRESIMP = 2, 0.01

@@ -467,9 +467,15 @@ int mdbg_push_reads(mdbg_ctx* c, const uint8_t* bases, const uint64_t* read_off,
         const bool hybrid = c->upload_hybrid;
         double link_rate = 50e9;
         if (const char* e = getenv("MDBG_PCIE_GBPS")) { double v = atof(e); if (v >= 1 && v <= 1000) link_rate = v * 1e9; }
+        double ascii_rate = link_rate;   // pageable source: the driver stages ASCII chunks through its own pinned buffer
+        {
+            cudaPointerAttributes pa{};
+            if (cudaPointerGetAttributes(&pa, bases) != cudaSuccess) (void)cudaGetLastError();
+            else if (pa.type == cudaMemoryTypeUnregistered) ascii_rate = std::min(link_rate, 12e9);
+        }
         double busy_until = 0, pack_s_per_byte = 1.0 / 40e9;
         auto now_s = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-        prepare = [&, n_words, CHW, hybrid, link_rate, busy_until, pack_s_per_byte, now_s](size_t ci) mutable -> int {
+        prepare = [&, n_words, CHW, hybrid, link_rate, ascii_rate, busy_until, pack_s_per_byte, now_s](size_t ci) mutable -> int {
             const uint64_t wa = (uint64_t)ci * CHW, wb = std::min(n_words, wa + CHW);
             // this chunk's slot of the staging ring, addressed as if the ring were the whole batch
             uint32_t* hp = reinterpret_cast<uint32_t*>(reinterpret_cast<uintptr_t>(c->h_planes) +
@@ -478,7 +484,7 @@ int mdbg_push_reads(mdbg_ctx* c, const uint8_t* bases, const uint64_t* read_off,
             const double t_dec = now_s();
             const double backlog = std::max(0.0, busy_until - t_dec);
             if (hybrid && backlog < pack_s_per_byte * (double)chunk_bytes) {   // the engine would run dry while we pack
-                busy_until = std::max(t_dec, busy_until) + (double)chunk_bytes / link_rate;
+                busy_until = std::max(t_dec, busy_until) + (double)chunk_bytes / ascii_rate;
                 const uint64_t off = wa * 32, end = std::min<uint64_t>(B, wb * 32);
                 MDBG_CK(c, cudaMemcpyAsync(d_bases.p + off, bases + off, end - off, cudaMemcpyHostToDevice, c->st_copy));
                 MDBG_CK(c, cudaEventRecord(c->copy_ev[ci], c->st_copy));
