@@ -137,6 +137,30 @@ BS_DEV void gather32(const uint8_t* p, uint32_t& A, uint32_t& B, BadAcc& acc) {
     bad_accumulate(acc, v1.x); bad_accumulate(acc, v1.y); bad_accumulate(acc, v1.z); bad_accumulate(acc, v1.w);
 }
 
+// Queue the set bits of `cand` (HPC positions s + k).  Default: one shared-memory atomic per candidate;
+// MDBG_BS_CAND_BATCH: one per lane and call (the lane reserves all its slots at once).
+BS_DEV void push_candidates(WarpSmem& sm, uint32_t cand, const uint32_t s) {
+#if defined(MDBG_BS_CAND_BATCH)
+    if (!cand) return;
+    uint32_t qi = bs_atomic_add_s(&sm.qn, popc32(cand));
+#endif
+    while (cand) {
+#if defined(__CUDA_ARCH__)
+        const uint32_t k = (uint32_t)__ffs((int)cand) - 1u;
+#else
+        const uint32_t k = (uint32_t)__builtin_ctz(cand);
+#endif
+        cand &= cand - 1u;
+#if !defined(MDBG_BS_CAND_BATCH)
+        const uint32_t qi = bs_atomic_add_s(&sm.qn, 1u);
+#endif
+        if (qi < (uint32_t)QCAP) sm.u.q.queue[qi] = s + k;
+#if defined(MDBG_BS_CAND_BATCH)
+        qi++;
+#endif
+    }
+}
+
 // The tiles of one warp, in the order it walks them: groups of S consecutive tiles claimed from an
 // atomic counter, each group from its top tile down.
 struct TileIter {
@@ -255,7 +279,14 @@ BS_DEV void process_tile(const KAArgs& A, WarpSmem& sm, const int lane, const ui
                 m &= nv >= 32 ? 0xFFFFFFFFu : (nv > 0 ? low_mask((uint32_t)nv) : 0u);
             }
             pa = PA >> 31; pb = PB >> 31;
+#if defined(MDBG_BS_PEXT_SKIP5)
+            if (HPC) {                 // the last round of the network only when some lane of the warp needs it
+                const PextState ps = pext_pair_rounds4(m, PA, PB);
+                if (bs_any(ps.mk != 0)) pext_pair_round5(ps, PA, PB);
+            } else { PA &= m; PB &= m; }
+#else
             if (HPC) pext_pair(m, PA, PB); else { PA &= m; PB &= m; }
+#endif
             sm.mraw[idx] = m;
             sm.u.t.ca[idx] = PA;
             sm.u.t.cb[idx] = PB;
@@ -342,6 +373,23 @@ BS_DEV void process_tile(const KAArgs& A, WarpSmem& sm, const int lane, const ui
 
     // ---- P4: filter -------------------------------------------------------------------------
     if (!dirty) {
+#if defined(MDBG_BS_FILTER64)
+        constexpr uint32_t STR = 65 - T;               // 64-position windows: the low half keeps all 32
+        const uint32_t nwin = (Ctile + STR - 1) / STR;
+        for (uint32_t idx = lane; idx < nwin; idx += 32) {
+            const uint32_t s = idx * STR, w = s >> 5, sh = s & 31u;
+            const uint32_t x0 = sm.CA[w], x1 = sm.CA[w + 1], x2 = sm.CA[w + 2], x3 = sm.CA[w + 3];
+            const uint32_t y0 = sm.CB[w], y1 = sm.CB[w + 1], y2 = sm.CB[w + 2], y3 = sm.CB[w + 3];
+            uint32_t c_lo, c_hi;
+            filter_window64<L, T>(fsr(x0, x1, sh), fsr(x1, x2, sh), fsr(x2, x3, sh), fsr(y0, y1, sh), fsr(y1, y2, sh),
+                                  fsr(y2, y3, sh), c_lo, c_hi);
+            const uint32_t nv = Ctile - s;
+            c_lo &= low_mask(nv);
+            c_hi &= low_mask(nv > 32u ? (nv - 32u < STR - 32u ? nv - 32u : STR - 32u) : 0u);
+            push_candidates(sm, c_lo, s);
+            push_candidates(sm, c_hi, s + 32u);
+        }
+#else
         constexpr uint32_t STR = 33 - T;
         const uint32_t nwin = (Ctile + STR - 1) / STR;
         for (uint32_t idx = lane; idx < nwin; idx += 32) {
@@ -351,17 +399,9 @@ BS_DEV void process_tile(const KAArgs& A, WarpSmem& sm, const int lane, const ui
             uint32_t cand = filter_window<L, T>(fsr(x0, x1, sh), fsr(x1, x2, sh), fsr(y0, y1, sh), fsr(y1, y2, sh));
             const uint32_t nv = Ctile - s;
             cand &= low_mask(nv < STR ? nv : STR);
-            while (cand) {
-#if defined(__CUDA_ARCH__)
-                const uint32_t k = (uint32_t)__ffs((int)cand) - 1u;
-#else
-                const uint32_t k = (uint32_t)__builtin_ctz(cand);
-#endif
-                cand &= cand - 1u;
-                const uint32_t qi = bs_atomic_add_s(&sm.qn, 1u);
-                if (qi < (uint32_t)QCAP) sm.u.q.queue[qi] = s + k;
-            }
+            push_candidates(sm, cand, s);
         }
+#endif
         bs_syncwarp();
         if (sm.qn > (uint32_t)QCAP) dirty = true;   // low-complexity sequence: exact path
     }

@@ -132,6 +132,43 @@ MDBG_HD void pext_pair(uint32_t m, uint32_t& x, uint32_t& y) {
     }
 }
 
+// The same network in two parts: rounds 0..3 (moves by 1, 2, 4, 8), then round 4 (moves by 16), which does
+// nothing unless some base has 16 or more dropped bases below it -- `mk` says so (callers vote on it).
+struct PextState { uint32_t m, mk; };
+MDBG_HD PextState pext_pair_rounds4(uint32_t m, uint32_t& x, uint32_t& y) {
+    x &= m;
+    y &= m;
+    uint32_t mk = ~m << 1;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        uint32_t mp = mk ^ (mk << 1);
+        mp ^= mp << 2;
+        mp ^= mp << 4;
+        mp ^= mp << 8;
+        mp ^= mp << 16;
+        const uint32_t mv = mp & m;
+        m = (m ^ mv) | (mv >> (1 << i));
+        uint32_t t = x & mv;
+        x = (x ^ t) | (t >> (1 << i));
+        t = y & mv;
+        y = (y ^ t) | (t >> (1 << i));
+        mk &= ~mp;
+    }
+    return PextState{m, mk};
+}
+MDBG_HD void pext_pair_round5(const PextState& st, uint32_t& x, uint32_t& y) {
+    uint32_t mp = st.mk ^ (st.mk << 1);
+    mp ^= mp << 2;
+    mp ^= mp << 4;
+    mp ^= mp << 8;
+    mp ^= mp << 16;
+    const uint32_t mv = mp & st.m;
+    uint32_t t = x & mv;
+    x = (x ^ t) | (t >> 16);
+    t = y & mv;
+    y = (y ^ t) | (t >> 16);
+}
+
 // position of the k-th (0-based) set bit of m; k < popc(m)
 MDBG_HD uint32_t select_bit(uint32_t m, uint32_t k) {
     uint32_t pos = 0, c;
@@ -172,6 +209,41 @@ MDBG_HD uint32_t filter_window(uint32_t a0, uint32_t a1, uint32_t b0, uint32_t b
         orR |= R;
     }
     return ~(orF & orR);
+}
+
+// The same filter on 64 positions [s, s+64): planes in (a0, a1, a2), (b0, b1, b2).  The low half takes its
+// chain look-ahead from the high half (funnel shift) and stays valid on all 32 positions; the high half loses
+// T-1 positions as above: 64-(T-1) valid positions per call instead of 2 x (32-(T-1)).
+template <int L, int T>
+MDBG_HD void filter_window64(uint32_t a0, uint32_t a1, uint32_t a2, uint32_t b0, uint32_t b1, uint32_t b2,
+                             uint32_t& cand_lo, uint32_t& cand_hi) {
+    uint32_t F0 = 0, R0 = 0, F1 = 0, R1 = 0;
+#pragma unroll
+    for (int j = 0; j < L; j++) {
+        const uint32_t aj0 = fsr(a0, a1, j), bj0 = fsr(b0, b1, j), aj1 = fsr(a1, a2, j), bj1 = fsr(b1, b2, j);
+        F0 = apply_tt(tt_fwd(63 - (L - 1) + j), F0, aj0, bj0);
+        R0 = apply_tt(tt_rc((64 - T) - j), R0, aj0, bj0);
+        F1 = apply_tt(tt_fwd(63 - (L - 1) + j), F1, aj1, bj1);
+        R1 = apply_tt(tt_rc((64 - T) - j), R1, aj1, bj1);
+    }
+    const uint32_t aL0 = fsr(a0, a1, L), bL0 = fsr(b0, b1, L), aL1 = fsr(a1, a2, L), bL1 = fsr(b1, b2, L);
+    uint32_t orF0 = F0, orR0 = R0, orF1 = F1, orR1 = R1;
+#pragma unroll
+    for (int t = 1; t < T; t++) {
+        const int b = 64 - t, c = 64 - T + t;
+        F0 = fsr(F0, F1, 1);
+        F1 >>= 1;
+        F0 = apply_tt(tt_fwd(b), apply_tt(tt_fwd(b - L), F0, a0, b0), aL0, bL0);
+        F1 = apply_tt(tt_fwd(b), apply_tt(tt_fwd(b - L), F1, a1, b1), aL1, bL1);
+        orF0 |= F0; orF1 |= F1;
+        R0 = fsr(R0, R1, 1);
+        R1 >>= 1;
+        R0 = apply_tt(tt_rc(c - L), apply_tt(tt_rc(c), R0, a0, b0), aL0, bL0);
+        R1 = apply_tt(tt_rc(c - L), apply_tt(tt_rc(c), R1, a1, b1), aL1, bL1);
+        orR0 |= R0; orR1 |= R1;
+    }
+    cand_lo = ~(orF0 & orR0);
+    cand_hi = ~(orF1 & orR1);
 }
 
 // ---- exact canonical hash of one window from its l codes (a = code bits 0, b = code bits 1) ----
