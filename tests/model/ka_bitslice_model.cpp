@@ -114,8 +114,8 @@ int bs_model_run(const uint8_t* bases, const uint64_t* read_off, uint64_t R, uin
     uint8_t* gb = (uint8_t*)aligned_alloc(16, (B + 15) / 16 * 16 + 16);
     memcpy(gb, bases, B);
     memset(gb + B, 0xEE, (B + 15) / 16 * 16 + 16 - B);   // poison: an illegal byte if ever looked at
-    unsigned int tile_counter = 0, dn = 0;
-    unsigned long long stage_counter = 0;
+    unsigned int tile_counter = 0, dn = *dirty_n;              // in/out: several launches share the dirty list
+    unsigned long long stage_counter = *stage_total;          // ... and the staging arrays (like run_ka's chunks)
     KAArgs A{};
     A.bases = gb; A.read_off = read_off; A.n_reads = R; A.n_bases = B;
     A.l = l; A.bound = bound;

@@ -95,7 +95,8 @@ def test_filter_and_exact_hash(model, l):
     assert hits > 0
 
 
-def run_model(model, oracle, seqs, l, d, hpc=True, group=4, n_warps=1, max_dirty=None, return_dirty=False):
+def run_model(model, oracle, seqs, l, d, hpc=True, group=4, n_warps=1, max_dirty=None, return_dirty=False,
+              launches=None):
     """Run the emulated kernel over the batch and compare every clean tile with the oracle:
     its (hash, pos) slice in order, and the (tile, rank) it leaves for every read starting in it.
     Returns (dirty tiles, minimizers checked, tiles)."""
@@ -110,10 +111,15 @@ def run_model(model, oracle, seqs, l, d, hpc=True, group=4, n_warps=1, max_dirty
     oro = np.full(R + 1, 2**64 - 1, np.uint64)
     dl, dn, st = np.zeros(n_tiles, np.uint32), ctypes.c_uint32(0), ctypes.c_uint64(0)
     bb = bases if B else np.zeros(1, np.uint8)
-    rc = model.bs_model_run(bb.ctypes.data, off.ctypes.data, R, B, l, bound, int(hpc), group, n_warps, 0, 0,
-                            tile_cnt.ctypes.data, tile_soff.ctypes.data, sh.ctypes.data, sp.ctypes.data, cap,
-                            oro.ctypes.data, dl.ctypes.data, ctypes.byref(dn), ctypes.byref(st), None)
-    assert rc == 0
+    # one launch over all tiles, or several over consecutive tile ranges (the chunks of an overlapped upload)
+    cuts = [0] + sorted(set(min(max(1, int(c)), n_tiles) for c in (launches or []))) + [n_tiles]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        if a >= b:
+            continue
+        rc = model.bs_model_run(bb.ctypes.data, off.ctypes.data, R, B, l, bound, int(hpc), group, n_warps, a, b,
+                                tile_cnt.ctypes.data, tile_soff.ctypes.data, sh.ctypes.data, sp.ctypes.data, cap,
+                                oro.ctypes.data, dl.ctypes.data, ctypes.byref(dn), ctypes.byref(st), None)
+        assert rc == 0
     dirty = set(int(x) for x in dl[:dn.value])
     assert len(dirty) == dn.value
     per_tile = [[] for _ in range(n_tiles)]          # oracle minimizers by the tile of their start
@@ -380,3 +386,14 @@ def test_model_read_start_inside_look_ahead(model, oracle, group):
         seqs.append(w[j:] + bytes(tail))
         total += len(seqs[-1])
     run_model(model, oracle, seqs, l, d, group=group, max_dirty=0)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_model_chunked_launches(model, oracle, seed):
+    """Several launches over consecutive tile ranges sharing the staging arrays and the dirty list, as
+    run_ka issues them while an upload is in flight: same result as one launch."""
+    rng = np.random.default_rng(300 + seed)
+    seqs = adversarial_batch(rng, 30)
+    nt = (sum(len(s) for s in seqs) + TILE - 1) // TILE
+    cuts = sorted(int(x) for x in rng.integers(1, nt, 4))
+    run_model(model, oracle, seqs, 12, 0.0039, group=int(rng.integers(1, 5)), n_warps=2, launches=cuts)
