@@ -304,6 +304,7 @@ def main():
         ctx.d2h(hb_arr, d_bases)     # same bytes as the device copy (generated on the device)
         d2h_bytes = 0
 
+        e2e_counts = {}
         e2e_parts = {"h2d": 0.0, "push": 0.0, "ka_start": 0.0, "ka_kernels_done": 0.0, "ka_done": 0.0, "finish": 0.0, "d2h": 0.0}
 
         def step_e2e():
@@ -316,6 +317,8 @@ def main():
             e2e_parts["ka_kernels_done"] += tm["ms_ka_kernel"]; e2e_parts["ka_done"] += tm["ms_ka"]
             e2e_parts["ka_start"] += tm["ms_ka_start"]
             nb = cg.n_nodes * (4 + 2 + 4 + 4 + 8 * cg.k) + cg.n_edges * (4 + 1 + 4 + 1 + 4)
+            e2e_counts.update(n_minimizers=int(cg.n_minimizers), n_kminmers=int(cg.n_kminmers),
+                              n_distinct=int(cg.n_distinct), n_nodes=int(cg.n_nodes), n_edges=int(cg.n_edges))
             ctx.graph_free(cg)
             return nb
 
@@ -332,6 +335,10 @@ def main():
         barrier()
         tm_last = ctx.timings()
         packed_up = bool(tm_last.get("upload_packed", 0))
+        try:
+            counts_equal = bool(e2e_counts) and all(int(stats[k_]) == v_ for k_, v_ in e2e_counts.items())
+        except Exception:
+            counts_equal = None
         # bytes that crossed PCIe host->device: the bases as 2-bit planes (8 B per 32 bases) plus any 4 KiB tile
         # sent as ASCII, or the ASCII bases; plus the read offsets
         h2d_bases = int(tm_last.get("upload_h2d_bytes", total)) if packed_up else total
@@ -342,6 +349,8 @@ def main():
                           (os.environ.get("MDBG_UPLOAD", "hybrid"), os.environ.get("MDBG_PACK_THREADS", "min(32, nproc / local ranks)"),
                            int(tm_last.get("upload_ascii_tiles", 0)))) if packed_up else "ASCII",
                "ms_per_step": e2e_ms / steps, "timing": "host wall clock around K steps, max over ranks",
+               # the graph built from the host buffers (packed / hybrid upload) against the device-resident one
+               "counts_equal_device_resident": counts_equal,
                "stage_ms_per_step": {k_: v_ / steps for k_, v_ in e2e_parts.items()}}
         ctx.host_free_pinned(hb); ctx.host_free_pinned(ho)
 
