@@ -150,6 +150,14 @@ int  mdbg_finish(mdbg_ctx* ctx, int want_seqlines, mdbg_graph* out);
 int  mdbg_finish_device(mdbg_ctx* ctx, mdbg_graph* out);
 void mdbg_graph_free(mdbg_graph* g);
 
+/* --read-stats (src/main.rs:939-975, src/read_stats.rs): for the reads of a second set, the abundance of
+ * every k-min-mer among the nodes kept by the last mdbg_finish (0 = not a node).  HOST buffers;
+ * out_counts[out_read_off[r] .. out_read_off[r+1]) belong to read r, in window order.  The pushed
+ * reads and the graph stay as they are.  *n_out = number of counts (also on MDBG_ERR_CAPACITY).    */
+int mdbg_read_stats(mdbg_ctx* ctx, const uint8_t* bases, const uint64_t* read_off, uint64_t n_reads,
+                    uint32_t* out_counts, uint64_t* out_read_off /* n_reads+1 */, uint64_t cap,
+                    uint64_t* n_out);
+
 /* Minimizers currently resident (after push): copies to HOST buffers (any may be NULL). */
 int mdbg_get_minimizers(mdbg_ctx* ctx, uint64_t* hash, uint64_t* pos, uint64_t* read_off,
                         uint64_t cap, uint64_t* n_out);

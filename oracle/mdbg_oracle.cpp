@@ -617,6 +617,32 @@ uint64_t orc_graph_minimizers(const orc_graph* g, uint64_t* hash, uint64_t* pos,
 
 // Canonical parity form of {prefix}.gfa: header (main.rs:1011), sorted S lines
 // (main.rs:1021), sorted L lines (main.rs:1095,1113).
+// --read-stats, main.rs:939-975: for every k-min-mer of every read of a second read set, the
+// abundance of its canonical tuple among the nodes that survived the abundance filter
+// (`dbg_nodes` at that point, main.rs:922-933), 0 when absent (main.rs:961-966).
+// out_off[r] = index of the first count of read r (R+1 entries); returns the number of counts, or
+// -1 on an illegal base (the crate panics there); writes at most cap counts.
+int64_t orc_read_stats(const orc_graph* g, const uint8_t* bases, const uint64_t* read_off, uint64_t R,
+                       uint32_t* out_counts, uint64_t* out_off, uint64_t cap) {
+    std::unordered_map<Tuple, uint16_t, TupleHash> ab;
+    ab.reserve(g->nodes.size() * 2);
+    for (const Node& n : g->nodes) ab[n.t] = n.e.abundance;
+    std::vector<uint64_t> t, pos;
+    uint64_t n = 0;
+    for (uint64_t r = 0; r < R; r++) {
+        if (out_off) out_off[r] = n;
+        uint64_t nh = 0, bad = 0;
+        if (extract_density(bases + read_off[r], read_off[r + 1] - read_off[r], g->p, t, pos, &nh, &bad) != 0) return -1;
+        for_each_kminmer(t, pos, g->p, [&](const Tuple& node, bool, uint64_t, uint64_t, uint64_t, uint64_t, uint64_t) {
+            auto it = ab.find(node);
+            if (n < cap && out_counts) out_counts[n] = it == ab.end() ? 0u : (uint32_t)it->second;
+            n++;
+        });
+    }
+    if (out_off) out_off[R] = n;
+    return (int64_t)n;
+}
+
 int orc_write_gfa(const orc_graph* g, const char* path) {
     FILE* f = fopen(path, "w");
     if (!f) return -1;

@@ -118,6 +118,9 @@ uint64_t orc_graph_minimizers(const orc_graph* g, uint64_t* hash, uint64_t* pos,
 
 /* Text writers in the CANONICAL PARITY FORM: header line, then sorted S
  * lines, then sorted L lines / sorted .sequences data lines without '#' header.     */
+/* --read-stats (main.rs:939-975): abundance of every k-min-mer of a second read set among the kept nodes */
+int64_t orc_read_stats(const orc_graph* g, const uint8_t* bases, const uint64_t* read_off, uint64_t R,
+                       uint32_t* out_counts, uint64_t* out_off, uint64_t cap);
 int orc_write_gfa(const orc_graph* g, const char* path);
 int orc_write_sequences(const orc_graph* g, const uint8_t* bases, const uint64_t* read_off,
                         const char* path);

@@ -76,6 +76,8 @@ def lib():
     L.orc_graph_minimizers.restype = u64
     L.orc_graph_minimizers.argtypes = [vp] * 4
     L.orc_write_gfa.argtypes = [vp, ctypes.c_char_p]
+    L.orc_read_stats.restype = ctypes.c_int64
+    L.orc_read_stats.argtypes = [vp, vp, vp, u64, vp, vp, u64]
     L.orc_write_sequences.argtypes = [vp, vp, vp, ctypes.c_char_p]
     _lib = L
     return L
@@ -197,6 +199,19 @@ class Graph:
             L.orc_graph_minimizers(handle, self.m_hash.ctypes.data, self.m_pos.ctypes.data,
                                    self.m_off.ctypes.data)
         self._bases, self._read_off = bases, read_off
+
+    def read_stats(self, bases, read_off):
+        """--read-stats (main.rs:939-975) -> (counts u32[K], first count of every read u64[R+1])."""
+        b = _buf(bases)
+        ro = np.ascontiguousarray(read_off, dtype=np.uint64)
+        R = len(ro) - 1
+        off = np.zeros(R + 1, np.uint64)
+        n = lib().orc_read_stats(self._h, b.ctypes.data, ro.ctypes.data, R, None, off.ctypes.data, 0)
+        if n < 0:
+            raise ValueError("Non-ACGTN nucleotide encountered!")
+        cnt = np.zeros(n, np.uint32)
+        lib().orc_read_stats(self._h, b.ctypes.data, ro.ctypes.data, R, cnt.ctypes.data, off.ctypes.data, n)
+        return cnt, off
 
     def write_gfa(self, path):
         return lib().orc_write_gfa(self._h, path.encode())

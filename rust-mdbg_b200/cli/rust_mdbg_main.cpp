@@ -25,6 +25,11 @@ struct Fastx {  // FASTA (multi-line) / FASTQ (4-line) records from a plain or g
     std::vector<char> buf;
     size_t pos = 0, len = 0;
     std::string pending;  // FASTA: header line already consumed
+    std::string id;       // of the record next() returned: the header up to the first space (seq_io's id())
+    void set_id(const std::string& header) {
+        size_t e = header.find(' ');
+        id = header.substr(1, e == std::string::npos ? std::string::npos : e - 1);
+    }
     bool open(const char* path, bool is_fasta) {
         f = gzopen(path, "rb");
         if (!f) return false;
@@ -57,7 +62,9 @@ struct Fastx {  // FASTA (multi-line) / FASTQ (4-line) records from a plain or g
         if (fasta) {
             if (pending.empty()) {
                 do { if (!getline(line)) return false; } while (line.empty() || line[0] != '>');
+                pending = line;
             }
+            set_id(pending);
             pending.clear();
             while (getline(line)) {
                 if (!line.empty() && line[0] == '>') { pending = line; return true; }
@@ -67,6 +74,7 @@ struct Fastx {  // FASTA (multi-line) / FASTQ (4-line) records from a plain or g
         }
         if (!getline(line)) return false;      // @id
         if (line.empty()) return false;
+        set_id(line);
         if (!getline(seq)) return false;       // sequence
         getline(line);                         // +
         getline(line);                         // qualities
@@ -95,7 +103,7 @@ std::string rust_f32(float v) {  // Rust `{}` of an f32
 
 int main(int argc, char** argv) {
     auto t_start = std::chrono::steady_clock::now();
-    std::string reads, prefix;
+    std::string reads, prefix, read_stats;
     long k = -1, l = -1, minabund = -1, threads = -1;
     double density = -1;
     float presimp = -1;
@@ -116,8 +124,9 @@ int main(int argc, char** argv) {
         else if (a == "--debug") {}
         else if (a == "--device") device = atoi(need(i));   // extension: CUDA device ordinal
         else if (a == "--bf") use_bf = true;   // ideal-filter numbering, main.rs:639-655
+        else if (a == "--read-stats") read_stats = need(i);   // main.rs:939-1004
         else if (a == "--syncmers" || a == "--uhs" || a == "--lcp" || a == "--error-correct" ||
-                 a == "--restart-from-postcor" || a == "--reference" || a == "--read-stats" || a == "--lmer-counts" ||
+                 a == "--restart-from-postcor" || a == "--reference" || a == "--lmer-counts" ||
                  a == "--lmer-counts-min" || a == "--lmer-counts-max" || a == "-n" || a == "-t" || a == "-s" ||
                  a == "--distance" || a == "--correction-threshold")
             die("`" + a + "` selects a mode outside the reads->mdBG hot path; this build refuses it rather than "
@@ -213,6 +222,60 @@ int main(int argc, char** argv) {
         printf("Number of nodes before abundance filter: %llu\n", (unsigned long long)g.n_distinct);
         printf("Number of nodes after abundance filter: %llu\n", (unsigned long long)g.n_nodes);
     } else printf("Number of mdBG nodes: %llu\n", (unsigned long long)g.n_nodes);
+    if (!read_stats.empty()) {   // main.rs:939-1004: abundance of every k-min-mer of a second read set, then exit
+        const std::string stats_path = read_stats + ".read_stats";               // read_stats.rs:26
+        FILE* sf = fopen(stats_path.c_str(), "w");
+        if (!sf) die("Couldn't create " + stats_path);
+        printf("Stats module initialized.\n");
+        printf("Parsing sequences from \"%s\"...\n", read_stats.c_str());
+        const bool sfa = read_stats.find(".fasta.") != std::string::npos || read_stats.find(".fa.") != std::string::npos ||
+                         (read_stats.size() >= 3 && read_stats.compare(read_stats.size() - 3, 3, ".fa") == 0) ||
+                         (read_stats.size() >= 6 && read_stats.compare(read_stats.size() - 6, 6, ".fasta") == 0);
+        printf(sfa ? "Format: FASTA\n" : "Format: FASTQ\n");
+        Fastx sx;
+        if (!sx.open(read_stats.c_str(), sfa)) die("Error opening compressed file: " + read_stats);
+        std::vector<std::string> ids;
+        std::vector<uint32_t> counts;
+        std::vector<uint64_t> coff;
+        auto flush_stats = [&]() {
+            if (off.size() == 1) return;
+            const uint64_t n = off.size() - 1;
+            coff.assign(n + 1, 0);
+            uint64_t need_n = 0;
+            int rc = mdbg_read_stats(ctx, pin, off.data(), n, counts.data(), coff.data(), counts.size(), &need_n);
+            if (rc == MDBG_ERR_CAPACITY) {
+                counts.resize(need_n + need_n / 8 + 1024);
+                rc = mdbg_read_stats(ctx, pin, off.data(), n, counts.data(), coff.data(), counts.size(), &need_n);
+            }
+            if (rc != MDBG_OK) die(mdbg_last_error(ctx));
+            std::string line;
+            for (uint64_t r = 0; r < n; r++) {                                    // read_stats.rs:53-64
+                line = ids[r] + ": ";
+                for (uint64_t j = coff[r]; j < coff[r + 1]; j++) { line += std::to_string(counts[j]); line += ' '; }
+                line += '\n';
+                fwrite(line.data(), 1, line.size(), sf);
+            }
+            off.assign(1, 0);
+            fill = 0;
+            ids.clear();
+        };
+        while (sx.next(s)) {
+            if (s.size() > BATCH + (64u << 20)) die("a record longer than the staging buffer (use a larger batch)");
+            if (fill + s.size() > BATCH + (64u << 20) || fill >= BATCH) flush_stats();
+            memcpy(pin + fill, s.data(), s.size());
+            fill += s.size();
+            off.push_back(fill);
+            ids.push_back(sx.id);
+        }
+        flush_stats();
+        sx.close();
+        fclose(sf);
+        printf("Read stats written, exiting.\n");
+        mdbg_graph_free(&g);
+        mdbg_host_free_pinned(pin);
+        mdbg_ctx_destroy(ctx);
+        return 0;
+    }
     if (mdbg_write_gfa(&g, (prefix + ".gfa").c_str()) != MDBG_OK) die("Couldn't create " + prefix + ".gfa");
     if (!no_basespace &&
         mdbg_write_sequences(&g, all_bases.data(), all_off.data(), (prefix + ".0.sequences").c_str(), 1) != MDBG_OK)

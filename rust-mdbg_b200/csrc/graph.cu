@@ -734,4 +734,61 @@ int mdbg_window(mdbg_ctx* c, const uint64_t* hash, const uint64_t* pos, const ui
     return MDBG_OK;
 }
 
+// --read-stats (main.rs:939-975): for every k-min-mer of every read of the batch, the abundance of its
+// canonical tuple among the nodes of the last mdbg_finish (`dbg_nodes` after the abundance filter), 0 when
+// it is none of them.  The batch goes through the same K-A as pushed reads (appended to the minimizer arena
+// and rolled back afterwards); the nodes are indexed by a sort of their tuple fingerprints.
+int mdbg_read_stats(mdbg_ctx* c, const uint8_t* bases, const uint64_t* read_off, uint64_t n_reads,
+                    uint32_t* out_counts, uint64_t* out_read_off, uint64_t cap, uint64_t* n_out) {
+    if (!c || !read_off) return MDBG_ERR_BAD_ARG;
+    MDBG_CK(c, cudaSetDevice(c->device));
+    DeviceGraph* G = c->dg;
+    if (!G) { c->err = "mdbg_read_stats needs the graph of a previous mdbg_finish"; return MDBG_ERR_BAD_ARG; }
+    if (G->k != c->p.k) { c->err = "k changed since the last mdbg_finish"; return MDBG_ERR_BAD_ARG; }
+    cudaStream_t st = c->st;
+    const uint32_t k = c->p.k;
+    const uint64_t M0 = c->M, R0 = c->R, B0 = c->n_bases;
+    int rc = mdbg_push_reads(c, bases, read_off, n_reads);      // minimizers of the batch: arena [M0, M), reads [R0, R)
+    if (rc) { c->M = M0; c->R = R0; c->n_bases = B0; return rc; }
+    struct Rollback { mdbg_ctx* c; uint64_t M, R, B; ~Rollback() { c->M = M; c->R = R; c->n_bases = B; } } rollback{c, M0, R0, B0};
+    Runner R{c};
+    Tmp<uint64_t> cnt, kmer_off;
+    MDBG_CK(c, cnt.get(c->pool, n_reads + 1));
+    MDBG_CK(c, kmer_off.get(c->pool, n_reads + 1));
+    const uint64_t* q_off = c->m_off + R0;                      // absolute arena offsets of the batch's reads
+    kb_count_kernel<<<nblk(n_reads + 1), 256, 0, st>>>(q_off, n_reads, k, cnt);
+    MDBG_CK(c, cudaGetLastError());
+    RC(R.cub([&](void* t, size_t& b) { return cub::DeviceScan::ExclusiveSum(t, b, cnt.p, kmer_off.p, n_reads + 1, st); }));
+    std::vector<uint64_t> ko(n_reads + 1);
+    MDBG_CK(c, cudaMemcpyAsync(ko.data(), kmer_off, (n_reads + 1) * 8, cudaMemcpyDeviceToHost, st));
+    MDBG_CK(c, cudaStreamSynchronize(st));
+    const uint64_t K = ko[n_reads];
+    if (n_out) *n_out = K;
+    if (out_read_off) memcpy(out_read_off, ko.data(), (n_reads + 1) * 8);
+    if (K > cap) { c->err = "output capacity too small"; return MDBG_ERR_CAPACITY; }
+    if (K == 0) return MDBG_OK;
+    if (K >= 0xFFFFFFF0ull) { c->err = "more than 2^32 k-min-mers in one read-stats batch"; return MDBG_ERR_RANGE; }
+    Tmp<uint32_t> d_out;
+    MDBG_CK(c, d_out.get(c->pool, K));
+    const uint32_t S = (uint32_t)G->n_nodes;
+    const uint64_t seed = 0x7273746174730000ull;
+    Tmp<uint64_t> fp, sfp;
+    Tmp<uint32_t> pos, spos;
+    MDBG_CK(c, fp.get(c->pool, S)); MDBG_CK(c, sfp.get(c->pool, S));
+    MDBG_CK(c, pos.get(c->pool, S)); MDBG_CK(c, spos.get(c->pool, S));
+    if (S) {
+        rs_node_fp_kernel<<<nblk(S), 256, 0, st>>>(G->tuple, S, k, seed, fp, pos);
+        MDBG_CK(c, cudaGetLastError());
+        RC(R.cub([&](void* t, size_t& b) {
+            return cub::DeviceRadixSort::SortPairs(t, b, fp.p, sfp.p, pos.p, spos.p, (int)S, 0, 64, st);
+        }));
+    }
+    MinArena A{c->m_hash, c->m_pos, q_off, n_reads};
+    rs_lookup_kernel<<<nblk(K), 256, 0, st>>>(A, kmer_off, K, k, seed, sfp, spos, S, G->tuple, G->abundance, d_out);
+    MDBG_CK(c, cudaGetLastError());
+    if (out_counts) MDBG_CK(c, cudaMemcpyAsync(out_counts, d_out, K * 4, cudaMemcpyDeviceToHost, st));
+    MDBG_CK(c, cudaStreamSynchronize(st));
+    return MDBG_OK;
+}
+
 }  // extern "C"

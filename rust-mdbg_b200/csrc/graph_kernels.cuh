@@ -201,6 +201,45 @@ __global__ void kb_export_kernel(MinArena A, const uint64_t* __restrict__ kmer_o
     }
 }
 
+// ---- --read-stats (main.rs:939-975): abundance of the k-min-mers of a second read set among the kept nodes
+// fingerprint of every node's tuple (nodes are sorted by index, the lookup wants them by fingerprint)
+__global__ void rs_node_fp_kernel(const uint64_t* __restrict__ tuple, uint32_t S, uint32_t k, uint64_t seed,
+                                  uint64_t* __restrict__ fp, uint32_t* __restrict__ pos) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= S) return;
+    uint64_t f = fp_init(seed, k);
+    for (uint32_t q = 0; q < k; q++) f = fp_mix(f, __ldg(tuple + (uint64_t)j * k + q));
+    fp[j] = f;
+    pos[j] = j;
+}
+// One thread per window of the query reads: canonical orientation, fingerprint, binary search among the
+// sorted node fingerprints, then the tuples decide (a fingerprint never does).  0 when the tuple is no node.
+__global__ void rs_lookup_kernel(MinArena A, const uint64_t* __restrict__ kmer_off, uint64_t K, uint32_t k,
+                                 uint64_t seed, const uint64_t* __restrict__ sfp, const uint32_t* __restrict__ spos,
+                                 uint32_t S, const uint64_t* __restrict__ node_tuple,
+                                 const uint16_t* __restrict__ node_ab, uint32_t* __restrict__ out) {
+    uint64_t g = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (g >= K) return;
+    const uint64_t r = owner_read(kmer_off, A.R, g);
+    const uint64_t* h = A.hash + A.off[r] + (g - kmer_off[r]);
+    const bool rv = window_reversed(h, k);
+    uint64_t f = fp_init(seed, k);
+    for (uint32_t q = 0; q < k; q++) f = fp_mix(f, __ldg(rv ? h + (k - 1 - q) : h + q));
+    uint32_t lo = 0, hi = S;           // lower bound of f in sfp
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (__ldg(sfp + mid) < f) lo = mid + 1; else hi = mid;
+    }
+    uint32_t res = 0;
+    for (uint32_t t = lo; t < S && __ldg(sfp + t) == f; t++) {
+        const uint64_t* nt = node_tuple + (uint64_t)__ldg(spos + t) * k;
+        bool eq = true;
+        for (uint32_t q = 0; q < k && eq; q++) eq = __ldg(nt + q) == __ldg(rv ? h + (k - 1 - q) : h + q);
+        if (eq) { res = __ldg(node_ab + __ldg(spos + t)); break; }
+    }
+    out[g] = res;
+}
+
 // ---- K-C ---------------------------------------------------------------------------------------
 // Open-address table of 64-bit fingerprints.  Four lanes cooperate on one key: they read one
 // aligned 32-byte sector (4 slots) per probe, vote with ballot, and the lane holding the first

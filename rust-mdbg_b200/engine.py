@@ -185,6 +185,22 @@ class Context:
         self._ck(self.L.mdbg_finish_device(self.h, ctypes.byref(cg)))
         return Graph(cg, copy_arrays=False).stats
 
+    def read_stats(self, bases, read_off):
+        """--read-stats (main.rs:939-975) against the graph of the last finish():
+        -> (counts u32[K], first count of every read u64[R+1])."""
+        b = as_u8(bases)
+        ro = np.ascontiguousarray(read_off, dtype=np.uint64)
+        R = len(ro) - 1
+        off = np.zeros(R + 1, np.uint64)
+        n = ffi.u64(0)
+        rc = self.L.mdbg_read_stats(self.h, ptr(b), ptr(ro), R, None, ptr(off), 0, ctypes.byref(n))
+        if rc not in (0, -5):
+            self._ck(rc)
+        cnt = np.zeros(n.value, np.uint32)
+        if n.value:
+            self._ck(self.L.mdbg_read_stats(self.h, ptr(b), ptr(ro), R, ptr(cnt), ptr(off), n.value, ctypes.byref(n)))
+        return cnt, off
+
     def get_minimizers(self):
         n = ffi.u64(0)
         self._ck(self.L.mdbg_get_minimizers(self.h, None, None, None, 0, ctypes.byref(n)))

@@ -107,6 +107,7 @@ SYMBOLS = {
     "mdbg_write_gfa": (ctypes.c_int, [GP, ctypes.c_char_p]),
     "mdbg_write_sequences": (ctypes.c_int, [GP, vp, vp, ctypes.c_char_p, ctypes.c_int]),
     "mdbg_pack_bases_host": (ctypes.c_int, [vp, u64, vp, vp, ctypes.c_int]),
+    "mdbg_read_stats": (ctypes.c_int, [vp, vp, vp, u64, vp, vp, u64, ctypes.POINTER(u64)]),
 }
 
 _lib = None

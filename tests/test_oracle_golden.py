@@ -178,3 +178,26 @@ def test_mt_baseline_same_node_set(oracle, example_reads):
     sa = sorted((tuple(int(x) for x in a.tuple[i]), int(a.abundance[i])) for i in range(len(a.index)))
     sb = sorted((tuple(int(x) for x in b.tuple[i]), int(b.abundance[i])) for i in range(len(b.index)))
     assert sa == sb
+
+
+def test_read_stats_against_naive_python(oracle):
+    """--read-stats (main.rs:939-975): abundance of each k-min-mer of a second read set among the kept
+    nodes, 0 when absent -- the oracle against the naive Python restatement of tests/helpers.py."""
+    from helpers import genome_reads, pack_reads, py_extract, py_kminmers
+    rng = np.random.default_rng(11)
+    k, l, d = 4, 8, 0.05
+    seqs = genome_reads(rng, 6000, 60, mean=900, sd=200, err=0.01)
+    bases, off = pack_reads(seqs)
+    g = oracle.build_graph(bases, off, k, l, d, 2, 0.01)
+    kept = {tuple(int(x) for x in g.tuple[i]): int(g.abundance[i]) for i in range(len(g.index))}
+    assert len(kept) > 20
+    query = seqs[::3] + genome_reads(rng, 6000, 10, mean=900, sd=200) + [b"", b"ACGT", b"A" * 50]
+    qb, qo = pack_reads(query)
+    cnt, coff = g.read_stats(qb, qo)
+    exp, eoff = [], [0]
+    for s in query:
+        hs, ps = py_extract(s, l, d)
+        exp += [kept.get(tuple(node), 0) for node, _, _, _ in py_kminmers(hs, ps, k, l)]
+        eoff.append(len(exp))
+    assert list(cnt) == exp and list(coff) == eoff
+    assert any(c > 0 for c in exp) and any(c == 0 for c in exp)
