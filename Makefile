@@ -23,9 +23,10 @@ $(CSRC)/%.o: $(CSRC)/%.cu $(HDR)
 $(CSRC)/%.o: $(CSRC)/%.cpp $(HDR)
 	$(NVCC) $(NVFLAGS) -x cu -c $< -o $@ 2> $@.ptxas.log || (cat $@.ptxas.log; exit 1)
 
-# host-only sources (SIMD intrinsics): plain g++
+# host-only sources (SIMD intrinsics): plain g++; -mssse3 only where the host is x86
+HOST_SIMD := $(if $(filter x86_64 i686 amd64,$(shell uname -m)),-mssse3,)
 $(CSRC)/%.o: $(CSRC)/%.cc $(HDR)
-	g++ -O3 -std=c++17 -mssse3 -fPIC -Wall -pthread -c $< -o $@
+	g++ -O3 -std=c++17 $(HOST_SIMD) -fPIC -Wall -pthread -c $< -o $@
 
 $(OUT): $(OBJ)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) -ldl -lz -lpthread

@@ -143,7 +143,9 @@ typedef struct {
 } mdbg_graph;
 
 /* Runs the table + graph stages and copies the result to host memory owned by *out
- * (release with mdbg_graph_free).  want_seqlines = 0 skips the q_* arrays (--no-basespace). */
+ * (release with mdbg_graph_free).  want_seqlines = 0 skips the q_* arrays (--no-basespace).
+ * With N GPUs (mdbg_comm_init) every rank must call it; rank 0 receives the whole graph, the other
+ * ranks the job-wide counters with NULL array members.                                       */
 int  mdbg_finish(mdbg_ctx* ctx, int want_seqlines, mdbg_graph* out);
 /* Same but leaves the graph in device memory and only returns the counters (pointer
  * members of *out are NULL): the device-resident timing path of bench.py.                  */
@@ -177,6 +179,8 @@ typedef struct {
     uint32_t upload_ascii_tiles;               /* ... 4 KiB tiles sent as ASCII instead (bytes outside ACGT, or
                                                   chunks sent unpacked because the copy engine was idle)       */
     uint64_t upload_h2d_bytes;                 /* bytes of bases that crossed PCIe in the last mdbg_push_reads */
+    float ms_exchange;                         /* N > 1: the record all-to-all of the last finish (inside ms_kb..ms_kc) */
+    uint64_t exchange_bytes;                   /* N > 1: bytes this GPU sent over NVLink in the last finish           */
 } mdbg_timings;
 int mdbg_get_timings(mdbg_ctx* ctx, mdbg_timings* out);
 void* mdbg_stream(mdbg_ctx* ctx);              /* the cudaStream_t all kernels run on        */
@@ -215,9 +219,11 @@ int mdbg_sync(mdbg_ctx* ctx);
 /* write >= L2-size bytes so the next timed iteration starts from a cold L2 */
 int mdbg_flush_l2(mdbg_ctx* ctx);
 
-/* ---- multi-GPU (one process per GPU; reads sharded by record; the minimizer arenas are
- *      all-gathered over NCCL and every tuple is counted on the owner of its fingerprint
- *      range) ------------------------------------------------------------------ */
+/* ---- multi-GPU (one process per GPU, at most 16; reads sharded by record in contiguous ranges; every
+ *      GPU windows its own reads, the k-min-mer records are bucketed by fingerprint prefix and cross
+ *      NVLink in one NCCL all-to-all so that every tuple is counted on ONE owner; the 8-byte hash arenas
+ *      are all-gathered so an owner can verify tuples; replaces the DashMap of src/main.rs:595,632-709;
+ *      SURVEY.md 8e) ---------------------------------------------------------------------------- */
 #define MDBG_NCCL_ID_BYTES 128
 int mdbg_nccl_unique_id(uint8_t id[MDBG_NCCL_ID_BYTES]);             /* rank 0, then broadcast */
 int mdbg_comm_init(mdbg_ctx* ctx, const uint8_t id[MDBG_NCCL_ID_BYTES], int rank, int world);

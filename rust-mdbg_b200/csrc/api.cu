@@ -98,6 +98,8 @@ int mdbg_ctx_create(const mdbg_params* p, mdbg_ctx** out) {
     if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, c->device);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_sc, sizeof(Scalars));
     if (e == cudaSuccess) e = cudaMallocHost(&c->h_sc, sizeof(Scalars));
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_mail, MAIL_WORDS * sizeof(uint64_t));
+    if (e == cudaSuccess) e = cudaMallocHost(&c->h_mail, MAIL_WORDS * sizeof(uint64_t));
     for (int i = 0; i < 24 && e == cudaSuccess; i++) e = cudaEventCreate(&c->ev[i]);
     if (e != cudaSuccess) {
         g_create_err = std::string("CUDA init failed: ") + cudaGetErrorString(e);
@@ -142,6 +144,7 @@ int mdbg_ctx_create(const mdbg_params* p, mdbg_ctx** out) {
 }
 
 void mdbg_graph_device_free(mdbg_ctx* ctx);  // graph.cu
+void mdbg_comm_release(mdbg_ctx* ctx);       // comm.cu
 
 void mdbg_ctx_destroy(mdbg_ctx* c) {
     if (!c) return;
@@ -157,6 +160,9 @@ void mdbg_ctx_destroy(mdbg_ctx* c) {
     delete c->pack_pool;
     if (c->d_sc) cudaFree(c->d_sc);
     if (c->h_sc) cudaFreeHost(c->h_sc);
+    if (c->d_mail) cudaFree(c->d_mail);
+    if (c->h_mail) cudaFreeHost(c->h_mail);
+    mdbg_comm_release(c);
     for (int i = 0; i < 24; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     c->pool.trim();
     for (auto ev : c->copy_ev) cudaEventDestroy(ev);

@@ -1,6 +1,6 @@
 // comm.cu -- NCCL plumbing for the multi-GPU path (one process per GPU).  The unique id is
 // created on rank 0 by mdbg_nccl_unique_id and shipped by the host (torch.distributed
-// broadcast in bench.py / tests); the exchange itself is in graph_mgpu.cu.
+// broadcast in bench.py / tests); the exchange itself is in graph.cu (build_device_graph).
 #include <cstring>
 #include <string>
 
@@ -8,6 +8,17 @@
 #include "nccl_dl.h"
 
 using namespace mdbg;
+
+// called by mdbg_ctx_destroy and before a re-init
+extern "C" void mdbg_comm_release(mdbg_ctx* c) {
+    if (c && c->comm) {
+        NcclApi& N = nccl();
+        if (N.ok) N.CommDestroy((ncclComm_t)c->comm);
+        c->comm = nullptr;
+        c->rank = 0;
+        c->world = 1;
+    }
+}
 
 extern "C" {
 
@@ -24,6 +35,7 @@ int mdbg_nccl_unique_id(uint8_t id[MDBG_NCCL_ID_BYTES]) {
 
 int mdbg_comm_init(mdbg_ctx* c, const uint8_t id[MDBG_NCCL_ID_BYTES], int rank, int world) {
     if (!c || !id || world < 1 || rank < 0 || rank >= world) return MDBG_ERR_BAD_ARG;
+    if (world > MAX_WORLD) { c->err = "more GPUs than MAX_WORLD (16) in one job"; return MDBG_ERR_BAD_ARG; }
     NcclApi& N = nccl();
     if (!N.ok) { c->err = "libnccl.so.2 could not be loaded"; return MDBG_ERR_NCCL; }
     MDBG_CK(c, cudaSetDevice(c->device));
@@ -35,6 +47,7 @@ int mdbg_comm_init(mdbg_ctx* c, const uint8_t id[MDBG_NCCL_ID_BYTES], int rank, 
         c->err = std::string("ncclCommInitRank: ") + N.GetErrorString(r);
         return MDBG_ERR_NCCL;
     }
+    mdbg_comm_release(c);   // a second init replaces the first communicator
     c->comm = (void*)comm;
     c->rank = rank;
     c->world = world;

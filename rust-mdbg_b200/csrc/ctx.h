@@ -56,6 +56,9 @@ struct Tmp {
     operator T*() const { return p; }
 };
 
+constexpr int MAX_WORLD = 16;                 // GPUs of one job (count matrices are MAX_WORLD^2 words)
+constexpr int MAIL_WORDS = 2 * MAX_WORLD * MAX_WORLD + 64;
+
 struct Scalars {  // device mailbox mirrored into pinned host memory
     unsigned long long total_out;
     unsigned long long err_pos;
@@ -93,6 +96,8 @@ struct mdbg_ctx {
     uint64_t m_cap_items = 0, r_cap_items = 0;
     mdbg::Scalars* d_sc = nullptr;
     mdbg::Scalars* h_sc = nullptr;   // pinned
+    uint64_t* d_mail = nullptr;      // MAIL_WORDS u64: sizes / counts exchanged between the GPUs ...
+    uint64_t* h_mail = nullptr;      // ... and their pinned host mirror
     void* l2_flush = nullptr; size_t l2_flush_bytes = 0;
     cudaEvent_t ev[24]{};
     mdbg_timings tm{};

@@ -4,25 +4,30 @@
 // Serial-order semantics: index = rank of a tuple's first sighting, abundance =
 // sightings (u16), seqlen/shift/sequence from the minabund-th sighting.
 //
-// One code path for 1 and N GPUs (one process per GPU, NCCL over NVLink):
-//   1. N > 1: the minimizer arenas (~12 B x 2d per base) are all-gathered, so every GPU sees every
-//      window of the job in serial order; nothing larger is exchanged
-//   2. every k-min-mer sighting this GPU owns (N > 1: tuple fingerprint in this rank's range, so
-//      every copy of a tuple meets on one owner) becomes a RECORD {window location, ordinal,
-//      RecInfo}; the canonical tuple is read from the arena, never materialised
+// One code path for 1 and N GPUs (one process per GPU, NCCL over NVLink).  Per-GPU work is
+// that GPU's share of the job (its reads, the tuples it owns, its slice of the nodes):
+//   1. K-B: every GPU turns the k-min-mer sightings of ITS reads into records {fingerprint, ordinal,
+//      window location, RecInfo} (44 bytes; the canonical tuple is a window of the hash arena, never
+//      materialised)
+//   2. N > 1: the records are bucketed by the fingerprint's prefix (range partition, stable) and cross
+//      NVLink in ONE all-to-all (grouped ncclSend/ncclRecv after an N x N count exchange), so every copy
+//      of a tuple meets on one owner; the hash arenas (8 B per minimizer) are all-gathered at a fixed
+//      pitch so that an owner can read the tuples of the records it received
 //   3. owner: open-address table (fingerprint placed, tuple verified), stable radix sort by slot,
 //      segmented reduce -> abundance / first sighting / representative sighting
-//   4. node index and node placement = ONE exclusive scan over ordinal space of the
-//      first-sighting flags (summed over the GPUs with one all-reduce)
-//   5. every GPU writes its nodes at their final places, the node arrays are all-reduced; every
-//      GPU builds the (k-1)-mer entry index and emits the edges of its slice of the nodes; presimp
-//      removals are all-gathered before the final filter
+//   4. node index and node placement = ONE exclusive scan over a 2-bit-per-ordinal bitmap of the
+//      first sightings (N > 1: the bitmaps are summed with one all-reduce: Ktot / 4 bytes)
+//   5. every owner writes a 20-byte NodeRec at the final place of each of its nodes (N > 1: summed with
+//      one all-reduce; tuples are not shipped, they are windows of the gathered arena); every GPU expands
+//      the node arrays, builds the (k-1)-mer entry index and emits the edges of ITS slice of the nodes;
+//      presimp removals are all-gathered before the final filter
 #include <cuda_runtime.h>
 
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <cub/cub.cuh>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -105,6 +110,30 @@ int allgather_u64(mdbg_ctx* c, const uint64_t* mine, int n, std::vector<uint64_t
     return MDBG_OK;
 }
 
+// A group of sends / receives that is always closed, whatever fails inside it (an open group would leave
+// the peers hanging): the first error is kept and reported after ncclGroupEnd.
+struct NcclGroup {
+    mdbg_ctx* c;
+    ncclResult_t bad = ncclSuccess;
+    bool open = false;
+    explicit NcclGroup(mdbg_ctx* ctx) : c(ctx) {
+        bad = nccl().GroupStart();
+        open = bad == ncclSuccess;
+    }
+    void send(const void* p, size_t bytes, int peer) {
+        if (bytes && bad == ncclSuccess) bad = nccl().Send(p, bytes, ncclChar, peer, (ncclComm_t)c->comm, c->st);
+    }
+    void recv(void* p, size_t bytes, int peer) {
+        if (bytes && bad == ncclSuccess) bad = nccl().Recv(p, bytes, ncclChar, peer, (ncclComm_t)c->comm, c->st);
+    }
+    int close() {
+        if (open) { ncclResult_t r = nccl().GroupEnd(); open = false; if (bad == ncclSuccess) bad = r; }
+        if (bad != ncclSuccess) { c->err = std::string("NCCL send/recv group: ") + nccl().GetErrorString(bad); return MDBG_ERR_NCCL; }
+        return MDBG_OK;
+    }
+    ~NcclGroup() { if (open) nccl().GroupEnd(); }
+};
+
 // all-gather of variable-length arrays: every rank ends with the concatenation in rank order
 int allgatherv(mdbg_ctx* c, const void* mine, uint64_t my_cnt, const std::vector<uint64_t>& cnt, void* out,
                size_t elem) {
@@ -113,45 +142,66 @@ int allgatherv(mdbg_ctx* c, const void* mine, uint64_t my_cnt, const std::vector
         if (my_cnt && out != mine) MDBG_CK(c, cudaMemcpyAsync(out, mine, my_cnt * elem, cudaMemcpyDeviceToDevice, c->st));
         return MDBG_OK;
     }
-    NcclApi& N = nccl();
+    NcclGroup g(c);
     size_t ro = 0;
-    NCK(c, N.GroupStart());
     for (int p = 0; p < W; p++) {
-        if (my_cnt) NCK(c, N.Send(mine, my_cnt * elem, ncclChar, p, (ncclComm_t)c->comm, c->st));
-        if (cnt[p]) NCK(c, N.Recv((char*)out + ro, cnt[p] * elem, ncclChar, p, (ncclComm_t)c->comm, c->st));
+        g.send(mine, my_cnt * elem, p);
+        g.recv((char*)out + ro, cnt[p] * elem, p);
         ro += cnt[p] * elem;
     }
-    NCK(c, N.GroupEnd());
-    return MDBG_OK;
+    return g.close();
 }
 
-// gather variable-length arrays on rank 0 (concatenated in rank order)
-int gatherv_root(mdbg_ctx* c, const void* mine, uint64_t my_cnt, const std::vector<uint64_t>& cnt, void* out,
-                 size_t elem) {
-    const int W = c->world;
-    if (W == 1) {
-        if (my_cnt && out != mine) MDBG_CK(c, cudaMemcpyAsync(out, mine, my_cnt * elem, cudaMemcpyDeviceToDevice, c->st));
-        return MDBG_OK;
-    }
-    NcclApi& N = nccl();
-    NCK(c, N.GroupStart());
-    if (my_cnt) NCK(c, N.Send(mine, my_cnt * elem, ncclChar, 0, (ncclComm_t)c->comm, c->st));
+// gather variable-length arrays on rank 0 (concatenated in rank order); `g` is the caller's open group
+void gatherv_root(mdbg_ctx* c, NcclGroup& g, const void* mine, uint64_t my_cnt, const std::vector<uint64_t>& cnt,
+                  void* out, size_t elem) {
+    g.send(mine, my_cnt * elem, 0);
     if (c->rank == 0) {
         size_t ro = 0;
-        for (int p = 0; p < W; p++) {
-            if (cnt[p]) NCK(c, N.Recv((char*)out + ro, cnt[p] * elem, ncclChar, p, (ncclComm_t)c->comm, c->st));
+        for (int p = 0; p < c->world; p++) {
+            g.recv((char*)out + ro, cnt[p] * elem, p);
             ro += cnt[p] * elem;
         }
     }
-    NCK(c, N.GroupEnd());
+}
+
+// all-to-all of `narr` SoA arrays: send[a] holds scnt[0] items for rank 0, then scnt[1] for rank 1, ...;
+// recv[a] receives rcnt[0] items from rank 0, then rcnt[1] from rank 1, ...  One NCCL group; the group is
+// always closed, whatever fails inside it.
+int alltoallv(mdbg_ctx* c, int narr, const void* const* send, void* const* recv, const size_t* elem,
+              const uint64_t* scnt, const uint64_t* rcnt) {
+    const int W = c->world;
+    NcclApi& N = nccl();
+    ncclResult_t bad = ncclSuccess;
+    cudaError_t cbad = cudaSuccess;
+    ncclResult_t r = N.GroupStart();
+    if (r != ncclSuccess) { c->err = std::string("ncclGroupStart: ") + N.GetErrorString(r); return MDBG_ERR_NCCL; }
+    for (int a = 0; a < narr; a++) {
+        size_t so = 0, ro = 0;
+        for (int p = 0; p < W; p++) {
+            const size_t sb = scnt[p] * elem[a], rb = rcnt[p] * elem[a];
+            if (p == c->rank) {
+                if (sb && cbad == cudaSuccess)
+                    cbad = cudaMemcpyAsync((char*)recv[a] + ro, (const char*)send[a] + so, sb, cudaMemcpyDeviceToDevice, c->st);
+            } else {
+                if (sb && bad == ncclSuccess) bad = N.Send((const char*)send[a] + so, sb, ncclChar, p, (ncclComm_t)c->comm, c->st);
+                if (rb && bad == ncclSuccess) bad = N.Recv((char*)recv[a] + ro, rb, ncclChar, p, (ncclComm_t)c->comm, c->st);
+            }
+            so += sb; ro += rb;
+        }
+    }
+    r = N.GroupEnd();
+    if (bad == ncclSuccess) bad = r;
+    if (bad != ncclSuccess) { c->err = std::string("all-to-all: ") + N.GetErrorString(bad); return MDBG_ERR_NCCL; }
+    if (cbad != cudaSuccess) { c->err = std::string("all-to-all (local part): ") + cudaGetErrorString(cbad); return MDBG_ERR_CUDA; }
     return MDBG_OK;
 }
 
-// Everything from the resident minimizers to the device graph.
+// Everything from the resident minimizers to the device graph (installed in the context only on success).
 int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
     mdbg_graph_device_free(c);
-    DeviceGraph* G = new DeviceGraph();
-    c->dg = G;
+    std::unique_ptr<DeviceGraph> Gp(new DeviceGraph());
+    DeviceGraph* G = Gp.get();
     const uint32_t k = c->p.k, l = c->p.l, minab = c->p.min_abundance;
     const float presimp = c->p.presimp;
     const uint32_t bf = (c->p.bf && minab > 1) ? 1 : 0;   // main.rs:639
@@ -160,97 +210,131 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
     c->tm.launches_finish = 0;
     c->tm.table_attempts = 0;
     c->tm.ms_kb = c->tm.ms_kc = c->tm.ms_kd = c->tm.ms_ke = 0;
+    c->tm.ms_exchange = 0; c->tm.exchange_bytes = 0;
     cudaStream_t st = c->st;
     Runner R{c};
     if (W > 1 && !c->comm) { c->err = "world > 1 but mdbg_comm_init was not called"; return MDBG_ERR_BAD_ARG; }
     if (c->M >= 0xFFFFFFF0ull) { c->err = "more than 2^32 minimizers on one GPU"; return MDBG_ERR_RANGE; }
     MDBG_CK(c, cudaEventRecord(c->ev[5], st));
-    // ---- the minimizer arena of the whole job ---------------------------------------------------
-    // N > 1: the per-GPU arenas (~2d x 12 bytes per base) are all-gathered, so every GPU sees every
-    // window of the job in serial order; nothing larger is ever exchanged.
-    MinArena A{c->m_hash, c->m_pos, c->m_off, c->R};
-    Tmp<uint64_t> g_hash, g_off, d_rmap;
-    Tmp<uint32_t> g_pos;
-    const uint64_t* d_rpre = nullptr; const uint64_t* d_rbase = nullptr;
-    if (W > 1) {
-        std::vector<uint64_t> all;
-        uint64_t mine[3] = {c->M, c->R, c->read_base_set ? c->read_base : ~0ull};
-        RC(allgather_u64(c, mine, 3, all));
-        std::vector<uint64_t> mcnt(W), rcnt(W), rmap(3 * (size_t)W + 2, 0);   // rpre[W+1] | mpre[W+1] | rbase[W]
-        uint64_t* rpre = rmap.data(); uint64_t* mpre = rpre + W + 1; uint64_t* rbase = mpre + W + 1;
-        for (int r = 0; r < W; r++) {
-            mcnt[r] = all[3 * r]; rcnt[r] = all[3 * r + 1];
-            mpre[r + 1] = mpre[r] + mcnt[r]; rpre[r + 1] = rpre[r] + rcnt[r];
-            rbase[r] = all[3 * r + 2] != ~0ull ? all[3 * r + 2] : rpre[r];
-        }
-        const uint64_t Mtot = mpre[W], Rtot = rpre[W];
-        if (Mtot >= 0xFFFFFFF0ull) { c->err = "more than 2^32 minimizers in the job"; return MDBG_ERR_RANGE; }
-        MDBG_CK(c, g_hash.get(c->pool, Mtot)); MDBG_CK(c, g_pos.get(c->pool, Mtot)); MDBG_CK(c, g_off.get(c->pool, Rtot + 1));
-        MDBG_CK(c, d_rmap.get(c->pool, rmap.size()));
-        MDBG_CK(c, cudaMemcpyAsync(d_rmap, rmap.data(), rmap.size() * 8, cudaMemcpyHostToDevice, st));
-        NCK(c, nccl().GroupStart());
-        RC(allgatherv(c, c->m_hash, c->M, mcnt, g_hash, 8));
-        RC(allgatherv(c, c->m_pos, c->M, mcnt, g_pos, 4));
-        RC(allgatherv(c, c->m_off, c->R, rcnt, g_off, 8));
-        NCK(c, nccl().GroupEnd());
-        d_rpre = d_rmap.p; d_rbase = d_rmap.p + 2 * (W + 1);
-        kb_rebase_off_kernel<<<nblk(Rtot + 1), 256, 0, st>>>(g_off, Rtot, d_rpre, d_rmap.p + (W + 1), (uint32_t)W);
-        LAUNCHED(c);
-        A = MinArena{g_hash, g_pos, g_off, Rtot};
-    }
+    const MinArena A{c->m_hash, c->m_pos, c->m_off, c->R};   // this GPU's reads
     const uint64_t nR = A.R;
 
-    // ---- K-B: records -------------------------------------------------------------------------
+    // ---- K-B: the sightings of this GPU's reads ---------------------------------------------------
     Tmp<uint64_t> cnt, kmer_off;
     MDBG_CK(c, cnt.get(c->pool, nR + 1));
     MDBG_CK(c, kmer_off.get(c->pool, nR + 1));
-    uint64_t Ktot = 0;  // sightings of the whole job (serial ordinals are 0 .. Ktot-1)
-    if (nR > 0) {
-        kb_count_kernel<<<nblk(nR + 1), 256, 0, st>>>(A.off, nR, k, cnt);
-        LAUNCHED(c);
-        RC(R.cub([&](void* t, size_t& b) { return cub::DeviceScan::ExclusiveSum(t, b, cnt.p, kmer_off.p, nR + 1, st); }));
-        MDBG_CK(c, cudaMemcpyAsync(&c->h_sc->v[0], kmer_off.p + nR, 8, cudaMemcpyDeviceToHost, st));
-        MDBG_CK(c, cudaStreamSynchronize(st));
-        Ktot = c->h_sc->v[0];
+    kb_count_kernel<<<nblk(nR + 1), 256, 0, st>>>(A.off, nR, k, cnt);   // nR == 0: a single zero
+    LAUNCHED(c);
+    RC(R.cub([&](void* t, size_t& b) { return cub::DeviceScan::ExclusiveSum(t, b, cnt.p, kmer_off.p, nR + 1, st); }));
+    // sizes of every rank: {M, R, first read, K}; one host round trip (also on one GPU: K sizes the table)
+    kx_sizes_kernel<<<1, 1, 0, st>>>(c->d_mail, c->M, c->R, c->read_base_set ? c->read_base : ~0ull, kmer_off.p + nR);
+    LAUNCHED(c);
+    if (W > 1) NCK(c, nccl().AllGather(c->d_mail, c->d_mail + 4, 4, ncclUint64, (ncclComm_t)c->comm, st));
+    else MDBG_CK(c, cudaMemcpyAsync(c->d_mail + 4, c->d_mail, 32, cudaMemcpyDeviceToDevice, st));
+    MDBG_CK(c, cudaMemcpyAsync(c->h_mail, c->d_mail + 4, (size_t)W * 32, cudaMemcpyDeviceToHost, st));
+    MDBG_CK(c, cudaStreamSynchronize(st));
+    uint64_t Ktot = 0, kbase = 0, Mpitch = 0, rbase = 0, rcount = 0;
+    for (int r = 0; r < W; r++) {
+        const uint64_t* v = c->h_mail + 4 * r;
+        if (r == rank) { kbase = Ktot; rbase = v[2] != ~0ull ? v[2] : rcount; }
+        Ktot += v[3]; rcount += v[1];
+        Mpitch = std::max(Mpitch, v[0]);
     }
-    if (Ktot >= 0x7FFFFFF0ull) { c->err = "more than 2^31 k-min-mers in the job"; return MDBG_ERR_RANGE; }
+    const uint64_t K_local = c->h_mail[4 * rank + 3];
+    if (W == 1) rbase = c->read_base;   // one GPU: reads are numbered in push order from read_base (0 unless set)
+    Mpitch = (Mpitch + 3) & ~3ull;      // 32-byte aligned rows of the gathered arena
+    if (K_local >= 0x7FFFFFF0ull) { c->err = "more than 2^31 k-min-mers on one GPU"; return MDBG_ERR_RANGE; }
+    if (W > 1 && Mpitch * (uint64_t)W >= 0xFFFFFFF0ull) { c->err = "more than 2^32 minimizers in the job"; return MDBG_ERR_RANGE; }
     G->n_kminmers = Ktot;
     const int ord_bits = std::max(1, log2_ceil(Ktot + 1));   // serial ordinals are < Ktot
-    // records this GPU owns: all of them on one GPU; with N > 1 the windows whose tuple fingerprint
-    // falls into this rank's range (every copy of a tuple meets on one owner), in ordinal order
-    uint64_t K = Ktot;
-    Tmp<uint32_t> own_g;
-    if (W > 1 && Ktot > 0) {
-        Tmp<uint8_t> own;
-        MDBG_CK(c, own.get(c->pool, Ktot)); MDBG_CK(c, own_g.get(c->pool, Ktot));
-        kb_own_kernel<<<nblk(Ktot), 256, 0, st>>>(A, kmer_off, Ktot, k, 0x6d64626700000000ull, (uint32_t)W, (uint32_t)rank, own);
-        LAUNCHED(c);
-        RC(R.cub([&](void* t, size_t& b) {
-            return cub::DeviceSelect::Flagged(t, b, cub::CountingInputIterator<uint32_t>(0), own.p, own_g.p,
-                                              (uint32_t*)&c->d_sc->v[0], (uint32_t)Ktot, st);
-        }));
-        RC(read_scalars(c));
-        K = c->h_sc->v[0] & 0xFFFFFFFFu;
+
+    // N > 1: the hash arenas of all GPUs at a fixed pitch (8 B per minimizer; positions stay at home: what a
+    // sighting needs from them travels inside its record)
+    Tmp<uint64_t> g_hash;
+    const uint64_t* arena = c->m_hash;
+    if (W > 1) {
+        MDBG_CK(c, g_hash.get(c->pool, Mpitch * (uint64_t)W));
+        if (c->M) MDBG_CK(c, cudaMemcpyAsync(g_hash.p + Mpitch * rank, c->m_hash, c->M * 8, cudaMemcpyDeviceToDevice, st));
+        if (Mpitch) NCK(c, nccl().AllGather(g_hash.p + Mpitch * rank, g_hash.p, Mpitch, ncclUint64, (ncclComm_t)c->comm, st));
+        arena = g_hash.p;
+        c->tm.exchange_bytes += Mpitch * 8 * (uint64_t)(W - 1);
     }
-    Tmp<uint64_t> r_ord_t, fp;
-    Tmp<RecInfo> r_info_t;
-    Tmp<uint32_t> wloc, iota;
-    MDBG_CK(c, r_ord_t.get(c->pool, K)); MDBG_CK(c, r_info_t.get(c->pool, K)); MDBG_CK(c, fp.get(c->pool, K));
-    MDBG_CK(c, wloc.get(c->pool, K)); MDBG_CK(c, iota.get(c->pool, K));
-    // The canonical tuples are never materialised: a record is a window of the (L2-resident)
-    // arena, read through TupleSrc.  The same pass computes the table fingerprint of the first seed.
+
+    // records of this GPU's sightings.  The canonical tuples are never materialised: a record is a window
+    // of the arena, read through TupleSrc.  The same pass computes the table fingerprint of the first seed
+    // and (N > 1) the owner of the tuple.
+    Tmp<uint64_t> l_ord, l_fp;
+    Tmp<RecInfo> l_info;
+    Tmp<uint32_t> l_wloc, iota;
+    Tmp<uint8_t> l_owner;
+    MDBG_CK(c, l_ord.get(c->pool, K_local)); MDBG_CK(c, l_info.get(c->pool, K_local)); MDBG_CK(c, l_fp.get(c->pool, K_local));
+    MDBG_CK(c, l_wloc.get(c->pool, K_local));
+    if (W > 1) MDBG_CK(c, l_owner.get(c->pool, K_local));
+    else MDBG_CK(c, iota.get(c->pool, K_local));
     const uint64_t table_seed0 = 0x7461626c65000000ull;
     uint64_t fp_mask0 = ~0ull;
     if (c->p.debug_fp_bits > 0 && c->p.debug_fp_bits < 64) fp_mask0 = (1ull << c->p.debug_fp_bits) - 1;
-    if (K) {
-        kb_records_kernel<<<nblk(K), 256, 0, st>>>(A, kmer_off, K, k, W > 1 ? own_g.p : nullptr, table_seed0, fp_mask0, d_rpre,
-                                                   d_rbase, (uint32_t)W, c->read_base, wloc, r_ord_t, r_info_t, fp, iota);
+    if (K_local) {
+        kb_records_kernel<<<nblk(K_local), 256, 0, st>>>(A, kmer_off, K_local, k, table_seed0, fp_mask0, rbase, kbase,
+                                                         W > 1 ? Mpitch * rank : 0, (uint32_t)W, l_wloc, l_ord, l_info, l_fp,
+                                                         W > 1 ? nullptr : iota.p, W > 1 ? l_owner.p : nullptr);
         LAUNCHED(c);
     }
-    const uint64_t* r_ord = r_ord_t; const RecInfo* r_info = r_info_t;
-    const TupleSrc T{A.hash, wloc.p, r_ord_t.p, k};
-    cnt.reset(); kmer_off.reset(); own_g.reset();
+    cnt.reset(); kmer_off.reset();
     MDBG_CK(c, cudaEventRecord(c->ev[6], st));
+
+    // ---- N > 1: bucket by owner, all-to-all --------------------------------------------------------
+    uint64_t K = K_local;   // records this GPU owns
+    Tmp<uint64_t> x_ord, x_fp;
+    Tmp<RecInfo> x_info;
+    Tmp<uint32_t> x_wloc;
+    const uint64_t* r_ord = l_ord; const uint64_t* r_fp_in = l_fp; const RecInfo* r_info = l_info; const uint32_t* r_wloc = l_wloc;
+    if (W > 1) {
+        Tmp<uint8_t> owner_s;
+        Tmp<uint32_t> perm_in, perm;
+        Tmp<uint64_t> s_ord, s_fp; Tmp<RecInfo> s_info; Tmp<uint32_t> s_wloc;
+        MDBG_CK(c, owner_s.get(c->pool, K_local)); MDBG_CK(c, perm_in.get(c->pool, K_local)); MDBG_CK(c, perm.get(c->pool, K_local));
+        MDBG_CK(c, s_ord.get(c->pool, K_local)); MDBG_CK(c, s_fp.get(c->pool, K_local));
+        MDBG_CK(c, s_info.get(c->pool, K_local)); MDBG_CK(c, s_wloc.get(c->pool, K_local));
+        if (K_local) {
+            iota_kernel<<<nblk(K_local), 256, 0, st>>>(perm_in, (uint32_t)K_local);
+            LAUNCHED(c);
+            RC(R.cub([&](void* t, size_t& b) {   // stable: every bucket keeps the ordinal order
+                return cub::DeviceRadixSort::SortPairs(t, b, l_owner.p, owner_s.p, perm_in.p, perm.p, (uint32_t)K_local, 0,
+                                                       std::max(1, log2_ceil((uint64_t)W)), st);
+            }));
+        }
+        kx_bounds_kernel<<<1, 32, 0, st>>>(owner_s, K_local, (uint32_t)W, c->d_mail);
+        LAUNCHED(c);
+        uint64_t* d_cnt = c->d_mail + 64;   // [W][W]: row s = what rank s sends to each rank
+        NCK(c, nccl().AllGather(c->d_mail, d_cnt, W, ncclUint64, (ncclComm_t)c->comm, st));
+        MDBG_CK(c, cudaMemcpyAsync(c->h_mail, d_cnt, (size_t)W * W * 8, cudaMemcpyDeviceToHost, st));
+        if (K_local) {
+            kx_pack_kernel<<<nblk(K_local), 256, 0, st>>>(perm, K_local, l_fp, l_ord, l_wloc, l_info, s_fp, s_ord, s_wloc, s_info);
+            LAUNCHED(c);
+        }
+        MDBG_CK(c, cudaStreamSynchronize(st));
+        uint64_t scnt[MAX_WORLD], rcnt[MAX_WORLD];
+        K = 0;
+        for (int p = 0; p < W; p++) { scnt[p] = c->h_mail[(size_t)rank * W + p]; rcnt[p] = c->h_mail[(size_t)p * W + rank]; K += rcnt[p]; }
+        if (K >= 0x7FFFFFF0ull) { c->err = "more than 2^31 k-min-mers owned by one GPU"; return MDBG_ERR_RANGE; }
+        MDBG_CK(c, x_ord.get(c->pool, K)); MDBG_CK(c, x_fp.get(c->pool, K)); MDBG_CK(c, x_info.get(c->pool, K));
+        MDBG_CK(c, x_wloc.get(c->pool, K)); MDBG_CK(c, iota.get(c->pool, K));
+        MDBG_CK(c, cudaEventRecord(c->ev[10], st));
+        const void* sv[4] = {s_fp.p, s_ord.p, s_wloc.p, s_info.p};
+        void* rv[4] = {x_fp.p, x_ord.p, x_wloc.p, x_info.p};
+        const size_t el[4] = {8, 8, 4, sizeof(RecInfo)};
+        RC(alltoallv(c, 4, sv, rv, el, scnt, rcnt));
+        MDBG_CK(c, cudaEventRecord(c->ev[11], st));
+        c->tm.exchange_bytes += (K_local - scnt[rank]) * (8 + 8 + 4 + sizeof(RecInfo));
+        if (K) { iota_kernel<<<nblk(K), 256, 0, st>>>(iota, (uint32_t)K); LAUNCHED(c); }
+        r_ord = x_ord; r_fp_in = x_fp; r_info = x_info; r_wloc = x_wloc;
+        l_owner.reset();
+        // (the local arrays stay alive until the sends have run: freed with the other table scratch)
+    }
+    uint64_t* fp = W > 1 ? x_fp.p : l_fp.p;   // rewritten in place when a collision forces a new seed
+    (void)r_fp_in;
+    const TupleSrc T{arena, r_wloc, r_ord, k};
 
     // ---- K-C table + K-D sort by slot (retry with a new seed on a fingerprint collision) ---------
     uint32_t D = 0, Q_local = 0;
@@ -298,7 +382,7 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
         D = (uint32_t)(c->h_sc->v[2] & 0xFFFFFFFFu);
     }
     MDBG_CK(c, cudaEventRecord(c->ev[7], st));   // ms_kc = table + sort by slot, ms_kd = reduce + nodes
-    slot.reset(); first.reset(); iota.reset(); sslot.reset(); fp.reset();
+    slot.reset(); first.reset(); iota.reset(); sslot.reset();
     MDBG_CK(c, first_ord.get(c->pool, D)); MDBG_CK(c, solid.get(c->pool, D)); MDBG_CK(c, nseq.get(c->pool, (uint64_t)D + 1));
     MDBG_CK(c, seq_off.get(c->pool, (uint64_t)D + 1)); MDBG_CK(c, seg_index.get(c->pool, D));
     Tmp<uint8_t> counted;
@@ -306,27 +390,32 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
     uint64_t Dtot = 0, Stot = 0, Qtot = 0;
     {
         // ---- node index and node placement from ONE prefix sum over ordinal space -----------------
-        // Every distinct tuple marks the ordinal of its first sighting (bit 0: it consumed a node
-        // index, bit 1: it is a solid node).  N > 1: the flag arrays are summed over the GPUs (an
-        // ordinal belongs to one tuple, hence one owner).  The exclusive scan then holds, at that
-        // ordinal, the tuple's node index and the place of the node in the ascending-index list:
-        // no sort of first sightings, no binary searches, no sort of nodes.
-        Tmp<uint8_t> ord_flags;
-        Tmp<uint64_t> rank64;
-        MDBG_CK(c, ord_flags.get(c->pool, Ktot + 1)); MDBG_CK(c, rank64.get(c->pool, Ktot + 1));
-        MDBG_CK(c, cudaMemsetAsync(ord_flags.p, 0, Ktot + 1, st));
+        // Every distinct tuple marks the ordinal of its first sighting in a bitmap of two bits per ordinal
+        // (it consumed a node index / it is a solid node).  N > 1: the bitmaps are summed over the GPUs (an
+        // ordinal belongs to one tuple, hence one owner).  The exclusive scan of the words' popcounts then
+        // holds, at that ordinal, the tuple's node index and the place of the node in the ascending-index
+        // list: no sort of first sightings, no binary searches, no sort of nodes.
+        const uint64_t nwords = (Ktot + 1 + 15) / 16;
+        if (nwords >= 0x7FFFFFF0ull) { c->err = "more than 2^35 k-min-mers in the job"; return MDBG_ERR_RANGE; }
+        Tmp<uint32_t> ord_bits_map;
+        Tmp<uint64_t> wscan;
+        MDBG_CK(c, ord_bits_map.get(c->pool, nwords + 1)); MDBG_CK(c, wscan.get(c->pool, nwords + 1));
+        MDBG_CK(c, cudaMemsetAsync(ord_bits_map.p, 0, (nwords + 1) * 4, st));
         MDBG_CK(c, cudaMemsetAsync(&c->d_sc->v[3], 0, 16, st));
         if (D > 0) {
             kd_segments_kernel<<<nblk(D), 256, 0, st>>>(seg_start, D, K, sj, r_ord, minab, bf, first_ord, counted, solid, nseq,
-                                                        ord_flags);
+                                                        ord_bits_map);
             LAUNCHED(c);
         }
-        if (W > 1) NCK(c, nccl().AllReduce(ord_flags.p, ord_flags.p, Ktot + 1, ncclUint8, ncclSum, (ncclComm_t)c->comm, st));
+        if (W > 1) {
+            NCK(c, nccl().AllReduce(ord_bits_map.p, ord_bits_map.p, nwords, ncclUint32, ncclSum, (ncclComm_t)c->comm, st));
+            c->tm.exchange_bytes += nwords * 4;
+        }
         RC(R.cub([&](void* t, size_t& b) {
-            cub::TransformInputIterator<uint64_t, FlagPairToU64, const uint8_t*> in(ord_flags.p, FlagPairToU64());
-            return cub::DeviceScan::ExclusiveSum(t, b, in, rank64.p, (uint32_t)(Ktot + 1), st);
+            cub::TransformInputIterator<uint64_t, FlagWordToU64, const uint32_t*> in(ord_bits_map.p, FlagWordToU64());
+            return cub::DeviceScan::ExclusiveSum(t, b, in, wscan.p, (uint32_t)(nwords + 1), st);
         }));
-        MDBG_CK(c, cudaMemcpyAsync(&c->d_sc->v[3], rank64.p + Ktot, 8, cudaMemcpyDeviceToDevice, st));
+        MDBG_CK(c, cudaMemcpyAsync(&c->d_sc->v[3], wscan.p + nwords, 8, cudaMemcpyDeviceToDevice, st));
         if (want_seqlines && D > 0) {
             MDBG_CK(c, cudaMemsetAsync(nseq.p + D, 0, 4, st));
             RC(R.cub([&](void* t, size_t& b) { return cub::DeviceScan::ExclusiveSum(t, b, nseq.p, seq_off.p, D + 1, st); }));
@@ -346,32 +435,27 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
         }
         if (Stot >= 0x7FFFFFF0ull) { c->err = "more than 2^31 nodes"; return MDBG_ERR_RANGE; }
         G->n_distinct = Dtot; G->n_nodes = Stot; G->n_seqlines = want_seqlines ? Qtot : 0;
-        // node arrays: every GPU writes the nodes it owns at their final places; N > 1: the arrays
-        // (zero elsewhere) are summed so that every GPU holds all nodes for the edge stage
-        const uint64_t Sp = Stot + (Stot & 1);   // u16 arrays are reduced as u32 words
-        MDBG_CK(c, G->index.get(c->pool, Stot)); MDBG_CK(c, G->abundance.get(c->pool, Sp));
+        // nodes: every owner writes a NodeRec at the final place of each node it owns; N > 1: the records
+        // (zero elsewhere) are summed, then every GPU expands the node arrays (tuples from the arena)
+        Tmp<NodeRec> nrec;
+        MDBG_CK(c, nrec.get(c->pool, Stot));
+        MDBG_CK(c, G->index.get(c->pool, Stot)); MDBG_CK(c, G->abundance.get(c->pool, Stot));
         MDBG_CK(c, G->seqlen.get(c->pool, Stot)); MDBG_CK(c, G->shift.get(c->pool, 2 * Stot));
         MDBG_CK(c, G->tuple.get(c->pool, Stot * k));
-        if (W > 1 && Stot > 0) {
-            MDBG_CK(c, cudaMemsetAsync(G->index.p, 0, Stot * 4, st)); MDBG_CK(c, cudaMemsetAsync(G->abundance.p, 0, Sp * 2, st));
-            MDBG_CK(c, cudaMemsetAsync(G->seqlen.p, 0, Stot * 4, st)); MDBG_CK(c, cudaMemsetAsync(G->shift.p, 0, Stot * 4, st));
-            MDBG_CK(c, cudaMemsetAsync(G->tuple.p, 0, Stot * k * 8, st));
-        }
+        if (W > 1 && Stot > 0) MDBG_CK(c, cudaMemsetAsync(nrec.p, 0, Stot * sizeof(NodeRec), st));
         if (D > 0) {
-            NodeOut NO{G->index, G->abundance, G->seqlen, G->shift, G->tuple};
-            kd_nodes_direct_kernel<<<nblk(D), 256, 0, st>>>(D, minab, K, seg_start, sj, first_ord, counted, solid, rank64, T,
-                                                            r_ord, r_info, seg_index, NO);
+            kd_nodes_kernel<<<nblk(D), 256, 0, st>>>(D, minab, K, seg_start, sj, first_ord, counted, solid, ord_bits_map, wscan,
+                                                     r_wloc, r_ord, r_info, seg_index, nrec);
             LAUNCHED(c);
         }
         if (W > 1 && Stot > 0) {
-            ncclComm_t cm = (ncclComm_t)c->comm;
-            NCK(c, nccl().GroupStart());
-            NCK(c, nccl().AllReduce(G->index.p, G->index.p, Stot, ncclUint32, ncclSum, cm, st));
-            NCK(c, nccl().AllReduce(G->abundance.p, G->abundance.p, Sp / 2, ncclUint32, ncclSum, cm, st));
-            NCK(c, nccl().AllReduce(G->seqlen.p, G->seqlen.p, Stot, ncclUint32, ncclSum, cm, st));
-            NCK(c, nccl().AllReduce(G->shift.p, G->shift.p, Stot, ncclUint32, ncclSum, cm, st));
-            NCK(c, nccl().AllReduce(G->tuple.p, G->tuple.p, Stot * k, ncclUint64, ncclSum, cm, st));
-            NCK(c, nccl().GroupEnd());
+            NCK(c, nccl().AllReduce(nrec.p, nrec.p, Stot * (sizeof(NodeRec) / 4), ncclUint32, ncclSum, (ncclComm_t)c->comm, st));
+            c->tm.exchange_bytes += Stot * sizeof(NodeRec);
+        }
+        if (Stot > 0) {
+            NodeOut NO{G->index, G->abundance, G->seqlen, G->shift, G->tuple};
+            kd_expand_kernel<<<nblk(Stot * k), 256, 0, st>>>(nrec, Stot, k, arena, NO);
+            LAUNCHED(c);
         }
         first_ord.reset(); solid.reset();
     }
@@ -399,7 +483,8 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
     MDBG_CK(c, cudaEventRecord(c->ev[8], st));
     // free table-stage scratch before the edge stage
     nseq.reset(); seq_off.reset(); seg_index.reset(); seg_start.reset(); sj.reset();
-    wloc.reset(); r_ord_t.reset(); r_info_t.reset(); g_hash.reset(); g_pos.reset(); g_off.reset();
+    l_wloc.reset(); l_ord.reset(); l_info.reset(); l_fp.reset(); x_wloc.reset(); x_ord.reset(); x_info.reset(); x_fp.reset();
+    g_hash.reset();
 
     // ---- K-E: edges of this GPU's slice of the nodes ----------------------------------------------
     uint32_t E = 0;
@@ -504,6 +589,7 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
         for (int r = 0; r < W; r++) { G->n_edges += all[2 * r]; G->presimp_removed += all[2 * r + 1]; }
     }
     MDBG_CK(c, cudaEventRecord(c->ev[9], st));
+    c->dg = Gp.release();
     return MDBG_OK;
 }
 
@@ -524,6 +610,7 @@ int finish_timings(mdbg_ctx* c) {
     cudaEventElapsedTime(&c->tm.ms_kd, c->ev[7], c->ev[8]);
     cudaEventElapsedTime(&c->tm.ms_ke, c->ev[8], c->ev[9]);
     cudaEventElapsedTime(&c->tm.ms_total_finish, c->ev[5], c->ev[9]);
+    if (c->world > 1) cudaEventElapsedTime(&c->tm.ms_exchange, c->ev[10], c->ev[11]);
     return MDBG_OK;
 }
 
@@ -578,8 +665,8 @@ int mdbg_finish_device(mdbg_ctx* c, mdbg_graph* out) {
     return MDBG_OK;
 }
 
-// Host copy.  With N GPUs every rank gets all nodes; rank 0 additionally gets ALL edges and
-// .sequences lines (gathered over NCCL), the other ranks their own slices.
+// Host copy.  With N GPUs rank 0 gets the whole graph (edges and .sequences lines are gathered over
+// NCCL); the other ranks get the job-wide counters only (array members NULL).
 int mdbg_finish(mdbg_ctx* c, int want_seqlines, mdbg_graph* out) {
     if (!c || !out) return MDBG_ERR_BAD_ARG;
     MDBG_CK(c, cudaSetDevice(c->device));
@@ -588,9 +675,6 @@ int mdbg_finish(mdbg_ctx* c, int want_seqlines, mdbg_graph* out) {
     RC(finish_timings(c));
     fill_counters(c, out);
     DeviceGraph* G = c->dg;
-    HostGraph* H = new HostGraph();
-    H->c = c;
-    out->_owner = H;
     const int W = c->world;
     const uint64_t S = G->n_nodes, k = G->k;
     MDBG_CK(c, cudaEventRecord(c->ev[13], c->st));
@@ -609,12 +693,14 @@ int mdbg_finish(mdbg_ctx* c, int want_seqlines, mdbg_graph* out) {
         uint64_t En = c->rank == 0 ? Et : 0, Qn = c->rank == 0 ? Qt : 0;
         MDBG_CK(c, g_n1.get(c->pool, En)); MDBG_CK(c, g_n2.get(c->pool, En)); MDBG_CK(c, g_ov.get(c->pool, En));
         MDBG_CK(c, g_o1.get(c->pool, En)); MDBG_CK(c, g_o2.get(c->pool, En)); MDBG_CK(c, g_seq.get(c->pool, Qn));
-        NCK(c, nccl().GroupStart());
-        RC(gatherv_root(c, G->e_n1, E, ec, g_n1, 4)); RC(gatherv_root(c, G->e_n2, E, ec, g_n2, 4));
-        RC(gatherv_root(c, G->e_ov, E, ec, g_ov, 4)); RC(gatherv_root(c, G->e_o1, E, ec, g_o1, 1));
-        RC(gatherv_root(c, G->e_o2, E, ec, g_o2, 1));
-        if (want_seqlines) RC(gatherv_root(c, G->seq, Q, qc, g_seq, sizeof(SeqRec)));
-        NCK(c, nccl().GroupEnd());
+        {
+            NcclGroup g(c);
+            gatherv_root(c, g, G->e_n1, E, ec, g_n1, 4); gatherv_root(c, g, G->e_n2, E, ec, g_n2, 4);
+            gatherv_root(c, g, G->e_ov, E, ec, g_ov, 4); gatherv_root(c, g, G->e_o1, E, ec, g_o1, 1);
+            gatherv_root(c, g, G->e_o2, E, ec, g_o2, 1);
+            if (want_seqlines) gatherv_root(c, g, G->seq, Q, qc, g_seq, sizeof(SeqRec));
+            RC(g.close());
+        }
         if (c->rank == 0) {   // slices are contiguous node ranges: the concatenation is already sorted
             E = Et; p_n1 = g_n1; p_n2 = g_n2; p_ov = g_ov; p_o1 = g_o1; p_o2 = g_o2;
             if (want_seqlines && Qt > 0) {   // emission order = ordinal order over all owners
@@ -631,6 +717,14 @@ int mdbg_finish(mdbg_ctx* c, int want_seqlines, mdbg_graph* out) {
             Q = Qt;
         }
     }
+    // N > 1: the host copy lives on rank 0 (all nodes, all edges, all .sequences lines); the other ranks
+    // return the job-wide counters with NULL arrays -- nobody downloads a graph nobody reads
+    if (W > 1 && c->rank != 0) {
+        MDBG_CK(c, cudaEventRecord(c->ev[14], c->st));
+        MDBG_CK(c, cudaStreamSynchronize(c->st));
+        cudaEventElapsedTime(&c->tm.ms_d2h, c->ev[13], c->ev[14]);
+        return MDBG_OK;
+    }
     Tmp<uint32_t> q_index; Tmp<uint64_t> q_read, q_start, q_end, q_shift; Tmp<uint8_t> q_rev;
     if (want_seqlines) {
         MDBG_CK(c, q_index.get(c->pool, Q)); MDBG_CK(c, q_read.get(c->pool, Q)); MDBG_CK(c, q_start.get(c->pool, Q));
@@ -644,6 +738,9 @@ int mdbg_finish(mdbg_ctx* c, int want_seqlines, mdbg_graph* out) {
             MDBG_CK(c, cudaGetLastError());
         }
     }
+    HostGraph* H = new HostGraph();
+    H->c = c;
+    out->_owner = H;   // from here on mdbg_graph_free releases whatever was allocated
     size_t need = S * (4 + 2 + 4 + 4 + 8 * k) + E * 14 + Q * (4 + 8 * 3 + 1 + 16) + 64 * 20;
     RC(host_block(c, H, need));
     out->node_index = H->take<uint32_t>(S); out->abundance = H->take<uint16_t>(S); out->seqlen = H->take<uint32_t>(S);
@@ -655,13 +752,11 @@ int mdbg_finish(mdbg_ctx* c, int want_seqlines, mdbg_graph* out) {
     RC(d2h(c, out->tuple, G->tuple.p, S * k));
     RC(d2h(c, out->e_n1, p_n1, E)); RC(d2h(c, out->e_o1, p_o1, E)); RC(d2h(c, out->e_n2, p_n2, E));
     RC(d2h(c, out->e_o2, p_o2, E)); RC(d2h(c, out->e_overlap, p_ov, E));
-    out->n_edges = (W > 1 && c->rank != 0) ? E : out->n_edges;
     if (want_seqlines) {
         out->q_index = H->take<uint32_t>(Q); out->q_read = H->take<uint64_t>(Q); out->q_start = H->take<uint64_t>(Q);
         out->q_end = H->take<uint64_t>(Q); out->q_reversed = H->take<uint8_t>(Q); out->q_shift = H->take<uint64_t>(2 * Q);
         RC(d2h(c, out->q_index, q_index.p, Q)); RC(d2h(c, out->q_read, q_read.p, Q)); RC(d2h(c, out->q_start, q_start.p, Q));
         RC(d2h(c, out->q_end, q_end.p, Q)); RC(d2h(c, out->q_reversed, q_rev.p, Q)); RC(d2h(c, out->q_shift, q_shift.p, 2 * Q));
-        out->n_seqlines = (W > 1 && c->rank != 0) ? Q : out->n_seqlines;
     }
     MDBG_CK(c, cudaEventRecord(c->ev[14], c->st));
     MDBG_CK(c, cudaStreamSynchronize(c->st));

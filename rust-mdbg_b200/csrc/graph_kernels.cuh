@@ -59,10 +59,11 @@ __device__ __forceinline__ bool window_reversed(const uint64_t* __restrict__ h, 
     return true;  // palindrome => reversed (kmer_vec.rs:37-38)
 }
 
-// Record of one k-min-mer sighting, as exchanged between GPUs (SoA: tuple / ord / info).
-//   tuple : k u64, canonical orientation
+// Record of one k-min-mer sighting, as exchanged between GPUs (SoA: fp / ord / wloc / info, 44 bytes).
+//   fp    : table fingerprint of the canonical tuple (places it; identity is decided on the tuples)
 //   ord   : global ordinal of the sighting (serial (read, i) order over the whole job), bit 63 =
 //           the window was reversed
+//   wloc  : first element of the window in the job-wide hash arena (the tuple itself)
 //   info  : what add_kminmer needs from the sighting (main.rs:769-778)
 struct RecInfo {
     uint32_t p0;      // raw position of the first minimizer           (read_offsets.0)
@@ -75,10 +76,9 @@ constexpr uint64_t ORD_REV = 1ull << 63;
 constexpr uint64_t ORD_MASK = ORD_REV - 1;
 
 // Where the canonical tuple of record j lives: nowhere of its own.  A record is a window of the
-// minimizer arena (wloc[j], read backwards when ord[j] says reversed); the arena is ~2d x 12 bytes
-// per base and stays in L2, so the K x k x 8 bytes of tuples are never materialised.  With N GPUs
-// the arena is the all-gathered arena of the whole job, so this also holds for the owner of a
-// tuple whose sightings came from other GPUs.
+// minimizer hash arena (wloc[j], read backwards when ord[j] says reversed), so the K x k x 8 bytes of
+// tuples are never materialised.  With N GPUs `hash` is the all-gathered arena of the whole job (8 B per
+// minimizer), so this also holds for the owner of a tuple whose sightings came from other GPUs.
 struct TupleSrc {
     const uint64_t* hash;   // arena hashes
     const uint32_t* wloc;   // [K] first arena element of the window
@@ -91,48 +91,21 @@ struct TupleSrc {
     }
 };
 
-// N > 1, after the arenas were all-gathered: the per-rank read offsets become offsets into the
-// concatenated arena.  rpre = prefix of reads per rank [W+1], mpre = prefix of minimizers [W+1].
-__global__ void kb_rebase_off_kernel(uint64_t* __restrict__ off, uint64_t R, const uint64_t* __restrict__ rpre,
-                                     const uint64_t* __restrict__ mpre, uint32_t world) {
-    uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (r > R) return;
-    if (r == R) { off[R] = mpre[world]; return; }
-    uint32_t w = 0;
-    while (w + 1 < world && rpre[w + 1] <= r) w++;
-    off[r] += mpre[w];
-}
-
-// N > 1: own[g] = 1 if this GPU owns the tuple of window g (range partition on the tuple
-// fingerprint, mdbg_owner_of_fingerprint).  Every GPU scans all windows of the job -- two passes
-// over an L2-resident arena -- instead of shipping K x k x 8 bytes of tuples through an all-to-all.
-__global__ void kb_own_kernel(MinArena A, const uint64_t* __restrict__ kmer_off, uint64_t K, uint32_t k,
-                              uint64_t seed, uint32_t world, uint32_t rank, uint8_t* __restrict__ own) {
-    uint64_t g = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (g >= K) return;
-    uint64_t r = owner_read(kmer_off, A.R, g);
-    uint64_t lo = __ldg(A.off + r) + (g - __ldg(kmer_off + r));
-    const uint64_t* h = A.hash + lo;
-    bool rv = window_reversed(h, k);
-    uint64_t f = fp_init(seed, k);
-    for (uint32_t j = 0; j < k; j++) f = fp_mix(f, rv ? __ldg(h + k - 1 - j) : __ldg(h + j));
-    own[g] = (uint32_t)__umul64hi(f, (uint64_t)world) == rank ? 1 : 0;
-}
-
-// One thread per record j of this GPU (window g = own[j], or j itself on one GPU): orientation,
-// ordinal (= g: windows are numbered in serial (read, i) order over the whole job), RecInfo, window
-// location and the table fingerprint of the first seed (masked, never KC_EMPTY).
-//   read id: reads of rank w are numbered rbase[w] + (r - rpre[w])  (one GPU: base0 + r)
+// One thread per k-min-mer sighting of THIS GPU's reads (window g of the local arena, serial (read, i)
+// order): orientation, job-wide ordinal (kbase + g: ranks hold contiguous read ranges, so ordinals
+// of rank r start at the number of sightings of the ranks before it), RecInfo, the window's location
+// in the job-wide arena (mbase + local index: with N GPUs the hash arenas are all-gathered at a fixed
+// pitch, mbase = rank * pitch) and the table fingerprint of the first seed (masked, never KC_EMPTY).
+// N > 1: owner[j] = GPU that counts this tuple = range partition of the UNMASKED fingerprint
+// (mdbg_owner_of_fingerprint), so every copy of a tuple meets on one owner.
 __global__ void kb_records_kernel(MinArena A, const uint64_t* __restrict__ kmer_off, uint64_t K, uint32_t k,
-                                  const uint32_t* __restrict__ own, uint64_t seed, uint64_t fp_mask,
-                                  const uint64_t* __restrict__ rpre, const uint64_t* __restrict__ rbase,
-                                  uint32_t world, uint64_t base0,
+                                  uint64_t seed, uint64_t fp_mask, uint64_t read_base, uint64_t kbase,
+                                  uint64_t mbase, uint32_t world,
                                   uint32_t* __restrict__ wloc, uint64_t* __restrict__ ord,
                                   RecInfo* __restrict__ info, uint64_t* __restrict__ fp,
-                                  uint32_t* __restrict__ iota) {
-    uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (j >= K) return;
-    uint64_t g = own ? (uint64_t)__ldg(own + j) : j;
+                                  uint32_t* __restrict__ iota, uint8_t* __restrict__ owner) {
+    uint64_t g = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (g >= K) return;
     uint64_t r = owner_read(kmer_off, A.R, g);
     uint64_t i = g - __ldg(kmer_off + r);
     uint64_t lo = __ldg(A.off + r) + i;
@@ -141,25 +114,50 @@ __global__ void kb_records_kernel(MinArena A, const uint64_t* __restrict__ kmer_
     bool rv = window_reversed(h, k);
     uint64_t f = fp_init(seed, k);
     for (uint32_t q = 0; q < k; q++) f = fp_mix(f, rv ? __ldg(h + k - 1 - q) : __ldg(h + q));
+    if (owner) owner[g] = (uint8_t)__umul64hi(f, (uint64_t)world);
     f &= fp_mask;
     if (f == KC_EMPTY) f = KC_EMPTY - 1;
-    fp[j] = f;
-    iota[j] = (uint32_t)j;
-    wloc[j] = (uint32_t)lo;
-    ord[j] = g | (rv ? ORD_REV : 0);
-    uint64_t read = base0 + r;
-    if (world > 1) {
-        uint32_t w = 0;
-        while (w + 1 < world && __ldg(rpre + w + 1) <= r) w++;
-        read = __ldg(rbase + w) + (r - __ldg(rpre + w));
-    }
+    fp[g] = f;
+    if (iota) iota[g] = (uint32_t)g;
+    wloc[g] = (uint32_t)(mbase + lo);
+    ord[g] = (kbase + g) | (rv ? ORD_REV : 0);
     RecInfo ri;
     ri.p0 = p[0];
     ri.d01 = p[1] - p[0];
     ri.dlast = p[k - 1] - p[k - 2];
     ri.span = p[k - 1] - p[0];
-    ri.read = read;
-    info[j] = ri;
+    ri.read = read_base + r;
+    info[g] = ri;
+}
+
+// ---- the exchange (N > 1): records bucketed by owner, one all-to-all over NVLink ----------------
+// {M, R, first read, K} of this rank, assembled on the device (K is the last entry of a device scan)
+__global__ void kx_sizes_kernel(uint64_t* __restrict__ out, uint64_t M, uint64_t R, uint64_t read_base,
+                                const uint64_t* __restrict__ k_total) {
+    out[0] = M; out[1] = R; out[2] = read_base; out[3] = *k_total;
+}
+// cnt[w] = records whose owner is w, from the owner-sorted key array (W + 1 binary searches)
+__global__ void kx_bounds_kernel(const uint8_t* __restrict__ sorted, uint64_t K, uint32_t W, uint64_t* __restrict__ cnt) {
+    uint32_t w = threadIdx.x;
+    if (w >= W) return;
+    uint64_t b[2];
+    for (int t = 0; t < 2; t++) {
+        uint32_t key = w + t;
+        uint64_t lo = 0, hi = K;
+        while (lo < hi) { uint64_t mid = (lo + hi) >> 1; if (__ldg(sorted + mid) < key) lo = mid + 1; else hi = mid; }
+        b[t] = lo;
+    }
+    cnt[w] = b[1] - b[0];
+}
+// send buffers: the records in owner order (stable, so every bucket ascends in ordinal)
+__global__ void kx_pack_kernel(const uint32_t* __restrict__ perm, uint64_t K, const uint64_t* __restrict__ fp,
+                               const uint64_t* __restrict__ ord, const uint32_t* __restrict__ wloc,
+                               const RecInfo* __restrict__ info, uint64_t* __restrict__ s_fp,
+                               uint64_t* __restrict__ s_ord, uint32_t* __restrict__ s_wloc, RecInfo* __restrict__ s_info) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= K) return;
+    uint32_t j = __ldg(perm + i);
+    s_fp[i] = fp[j]; s_ord[i] = ord[j]; s_wloc[i] = wloc[j]; s_info[i] = info[j];
 }
 
 // table fingerprint of the canonical tuples
@@ -307,11 +305,15 @@ __global__ void kd_heads_kernel(const uint32_t* __restrict__ sslot, uint64_t K, 
 //   nseq      : sightings with previous_abundance == minabund-1 (u16 counter): main.rs:680,696
 //   bf (main.rs:639-655, ideal filter): a tuple enters the table at its SECOND sighting, so the
 //   index order is the order of second sightings and tuples seen once are not counted
+// "How many tuples were first seen earlier" is a prefix sum over ordinal space.  ord_bits holds two
+// bits per ordinal (16 ordinals per word): bit 0 = this ordinal consumed a node index, bit 1 = ... of
+// a solid node.  N > 1: the bitmaps of the GPUs are summed (an ordinal belongs to one tuple, hence to
+// one owner: the fields never collide, the sum is the union).
 __global__ void kd_segments_kernel(const uint32_t* __restrict__ seg_start, uint32_t D, uint64_t K,
                                    const uint32_t* __restrict__ sj, const uint64_t* __restrict__ ord,
                                    uint32_t minab, uint32_t bf, uint64_t* __restrict__ first_ord,
                                    uint8_t* __restrict__ counted, uint8_t* __restrict__ solid,
-                                   uint32_t* __restrict__ nseq, uint8_t* __restrict__ ord_flags) {
+                                   uint32_t* __restrict__ nseq, uint32_t* __restrict__ ord_bits) {
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= D) return;
     uint32_t st = seg_start[s];
@@ -325,55 +327,87 @@ __global__ void kd_segments_kernel(const uint32_t* __restrict__ seg_start, uint3
     const bool sol = (minab == 1 || ab >= minab);
     solid[s] = sol ? 1 : 0;
     nseq[s] = cnt >= minab ? 1 + (cnt - minab) / 65536u : 0;
-    // "how many tuples were first seen earlier" is a prefix sum over ordinal space: bit 0 = this
-    // ordinal consumed a node index, bit 1 = ... of a solid node (N > 1: the flag arrays of the
-    // GPUs are summed, every ordinal belongs to one tuple and so to one owner)
-    if (in_table) ord_flags[fo] = (uint8_t)(1 | (sol ? 2 : 0));
+    if (in_table) atomicOr(ord_bits + (fo >> 4), (sol ? 3u : 1u) << (2 * (uint32_t)(fo & 15)));
 }
 
-// u8 flag pair -> packed u64 counters (low 32: index consumers, high 32: solid nodes) for ONE scan
-struct FlagPairToU64 {
-    __host__ __device__ __forceinline__ uint64_t operator()(uint8_t f) const {
-        return (uint64_t)(f & 1u) | ((uint64_t)((f >> 1) & 1u) << 32);
+// bitmap word -> packed u64 counters (low 32: index consumers, high 32: solid nodes) for ONE scan
+struct FlagWordToU64 {
+    __host__ __device__ __forceinline__ uint64_t operator()(uint32_t w) const {
+#if defined(__CUDA_ARCH__)
+        return (uint64_t)__popc(w & 0x55555555u) | ((uint64_t)__popc(w & 0xAAAAAAAAu) << 32);
+#else
+        return (uint64_t)__builtin_popcount(w & 0x55555555u) | ((uint64_t)__builtin_popcount(w & 0xAAAAAAAAu) << 32);
+#endif
     }
 };
+// packed (node index | node position << 32) of the tuple first seen at ordinal fo: the exclusive scan of the
+// bitmap words plus the fields below fo in its own word
+__device__ __forceinline__ uint64_t ordinal_rank(const uint32_t* __restrict__ ord_bits,
+                                                 const uint64_t* __restrict__ wscan, uint64_t fo) {
+    const uint32_t w = __ldg(ord_bits + (fo >> 4)) & ((1u << (2 * (uint32_t)(fo & 15))) - 1u);
+    return __ldg(wscan + (fo >> 4)) + ((uint64_t)__popc(w & 0x55555555u) | ((uint64_t)__popc(w & 0xAAAAAAAAu) << 32));
+}
 
-// The exclusive scan of the (job-wide) ordinal flags gives, at a tuple's first sighting, its node
+// What the other GPUs need to know about a node (20 bytes; the tuple is a window of the all-gathered hash
+// arena, so it is not shipped): written by the owner at the node's final position n, zero elsewhere, and
+// summed over the GPUs (N > 1).
+struct NodeRec { uint32_t index, seqlen, wloc, ab_sh0, sh1_rev; };
+static_assert(sizeof(NodeRec) == 20, "NodeRec is reduced as 5 u32 words");
+
+// The exclusive scan of the (job-wide) ordinal bitmap gives, at a tuple's first sighting, its node
 // index (low half) and -- because index order IS first-sighting order -- the position of a solid
 // node in the ascending-index node list (high half): nodes are written in place, no sort, no
 // binary searches.  One thread per distinct tuple of this GPU; also leaves every tuple's index in
 // seg_index (for .sequences).
-struct NodeOut { uint32_t* index; uint16_t* abundance; uint32_t* seqlen; uint16_t* shift; uint64_t* tuple; };
-__global__ void kd_nodes_direct_kernel(uint32_t D, uint32_t minab, uint64_t K,
-                                       const uint32_t* __restrict__ seg_start, const uint32_t* __restrict__ sj,
-                                       const uint64_t* __restrict__ first_ord, const uint8_t* __restrict__ counted,
-                                       const uint8_t* __restrict__ solid, const uint64_t* __restrict__ rank64,
-                                       TupleSrc T, const uint64_t* __restrict__ ord,
-                                       const RecInfo* __restrict__ info, uint32_t* __restrict__ seg_index,
-                                       NodeOut O) {
+__global__ void kd_nodes_kernel(uint32_t D, uint32_t minab, uint64_t K,
+                                const uint32_t* __restrict__ seg_start, const uint32_t* __restrict__ sj,
+                                const uint64_t* __restrict__ first_ord, const uint8_t* __restrict__ counted,
+                                const uint8_t* __restrict__ solid, const uint32_t* __restrict__ ord_bits,
+                                const uint64_t* __restrict__ wscan, const uint32_t* __restrict__ wloc,
+                                const uint64_t* __restrict__ ord, const RecInfo* __restrict__ info,
+                                uint32_t* __restrict__ seg_index, NodeRec* __restrict__ nodes) {
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= D) return;
     if (!counted[s]) { seg_index[s] = 0xFFFFFFFFu; return; }
-    const uint64_t rk = rank64[first_ord[s]];
+    const uint64_t rk = ordinal_rank(ord_bits, wscan, first_ord[s]);
     const uint32_t index = (uint32_t)rk, n = (uint32_t)(rk >> 32);
     seg_index[s] = index;
     if (!solid[s]) return;
-    const uint32_t k = T.k;
     uint32_t st = seg_start[s];
     uint32_t en = (s + 1 < D) ? seg_start[s + 1] : (uint32_t)K;
     uint32_t cnt = en - st;
     uint32_t rep_rank = (minab - 1) + 65536u * ((cnt - minab) / 65536u);  // last overwrite, main.rs:680-684
-    uint32_t j = sj[st + rep_rank];
+    uint32_t j = sj[st + rep_rank], j0 = sj[st];
     bool rv = (ord[j] & ORD_REV) != 0;
     RecInfo ri = info[j];
-    O.index[n] = index;
-    O.seqlen[n] = ri.span + 2;                                      // read_offsets.2, main.rs:778
-    O.abundance[n] = (uint16_t)(cnt & 0xFFFFu);
-    O.shift[2 * n] = (uint16_t)(rv ? ri.dlast : ri.d01);            // lowprec_shift, main.rs:675
-    O.shift[2 * n + 1] = (uint16_t)(rv ? ri.d01 : ri.dlast);
-    const uint64_t* t; int step;
-    T.row(sj[st], t, step);
-    for (uint32_t q = 0; q < k; q++) O.tuple[(uint64_t)n * k + q] = t[(int64_t)q * step];
+    NodeRec nr;
+    nr.index = index;
+    nr.seqlen = ri.span + 2;                                              // read_offsets.2, main.rs:778
+    nr.wloc = wloc[j0];                                                   // the tuple: first sighting's window
+    nr.ab_sh0 = (cnt & 0xFFFFu) | ((uint32_t)(uint16_t)(rv ? ri.dlast : ri.d01) << 16);   // lowprec_shift, main.rs:675
+    nr.sh1_rev = (uint32_t)(uint16_t)(rv ? ri.d01 : ri.dlast) | ((ord[j0] & ORD_REV) ? 0x10000u : 0u);
+    nodes[n] = nr;
+}
+
+// Node arrays of the whole job on this GPU: one thread per tuple element (coalesced), the tuple read from
+// the hash arena in canonical orientation.
+struct NodeOut { uint32_t* index; uint16_t* abundance; uint32_t* seqlen; uint16_t* shift; uint64_t* tuple; };
+__global__ void kd_expand_kernel(const NodeRec* __restrict__ nodes, uint64_t S, uint32_t k,
+                                 const uint64_t* __restrict__ hash, NodeOut O) {
+    uint64_t e = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (e >= S * k) return;
+    const uint64_t n = e / k;
+    const uint32_t q = (uint32_t)(e - n * k);
+    const NodeRec nr = nodes[n];
+    const bool rv = (nr.sh1_rev & 0x10000u) != 0;
+    O.tuple[e] = __ldg(hash + nr.wloc + (rv ? k - 1 - q : q));
+    if (q == 0) {
+        O.index[n] = nr.index;
+        O.seqlen[n] = nr.seqlen;
+        O.abundance[n] = (uint16_t)(nr.ab_sh0 & 0xFFFFu);
+        O.shift[2 * n] = (uint16_t)(nr.ab_sh0 >> 16);
+        O.shift[2 * n + 1] = (uint16_t)(nr.sh1_rev & 0xFFFFu);
+    }
 }
 
 struct SeqRec { uint64_t ord; uint32_t index, pad; uint64_t read, start, end, shift0, shift1; };

@@ -49,7 +49,8 @@ class CTimings(ctypes.Structure):
                 ("ka_ms_sum", ctypes.c_float), ("table_attempts", u32), ("ka_dense_tiles", u32),
                 ("ms_ka_kernel", ctypes.c_float), ("ms_ka_start", ctypes.c_float),
                 ("ka_variant_used", u32), ("ka_dirty_tiles", u32), ("upload_packed", u32),
-                ("upload_ascii_tiles", u32), ("upload_h2d_bytes", u64)]
+                ("upload_ascii_tiles", u32), ("upload_h2d_bytes", u64), ("ms_exchange", ctypes.c_float),
+                ("exchange_bytes", u64)]
 
 
 class CSynth(ctypes.Structure):
