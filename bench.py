@@ -9,8 +9,11 @@ extraction (K-A) + windowing/canonicalisation (K-B) + node table (K-C/K-D) + edg
 `value` is timed with the reads already resident in HBM (CUDA events on the launching stream);
 `e2e` is the same metric through the host-facing C ABI with pinned HOST buffers: H2D of the
 reads and D2H of the graph are inside the timed region.  The default workload is BASELINE
-config 2 (synthetic E. coli 5 Mbp, HiFi 50x, k=21 l=12 d=0.003); per-GPU work is fixed as N
-grows (weak scaling): rank r builds reads [r*R, (r+1)*R) of the same job.
+config 3 (synthetic D. melanogaster 140 Mbp, HiFi 50x, k=35 l=12 d=0.002: the largest
+single-GPU configuration, 7 Gbases per step); the N=1 line also carries a short device-resident
+measurement of config 2 (`ecoli50x`).  Per-GPU work is fixed as N grows (weak scaling): rank r
+builds reads [r*R, (r+1)*R) of the same job, and the N>1 line carries `parity_vs_single_gpu`:
+the N-GPU graph of a bounded job against the graph ONE GPU context builds from the same reads.
 `--impl reference` times the CPU restatement of the reference algorithm (oracle/, the Rust
 reference cannot be built in this image) in the reference's thread structure on the host cores.
 """
@@ -32,7 +35,7 @@ WORKLOADS = {
     "dmel50x": dict(genome_len=140_000_000, coverage=50.0, k=35, l=12, density=0.002,
                     desc="synthetic D. melanogaster 140 Mbp HiFi 50x, k=35 l=12 d=0.002"),
     # BASELINE config 4 as weak-scaling shards: 6.5x of a 3 Gbp genome per GPU (19.5 Gbases, 19.5 GB of ASCII
-    # bases in HBM) = the 52x / 156 Gbases job on 8 GPUs.  Not measured in round 1.
+    # bases in HBM) = the 52x / 156 Gbases job on 8 GPUs (run with --gpus 8 --workload human52x_per8).
     "human52x_per8": dict(genome_len=3_000_000_000, coverage=6.5, k=35, l=12, density=0.002,
                           desc="synthetic human 3 Gbp HiFi, 6.5x per GPU (52x on 8 GPUs), k=35 l=12 d=0.002"),
     "tiny": dict(genome_len=200_000, coverage=20.0, k=21, l=12, density=0.003, desc="smoke-size"),
@@ -135,7 +138,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="ecoli50x", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="dmel50x", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-extra", action="store_true", help="skip the short ecoli50x line at N=1")
+    ap.add_argument("--no-parity", action="store_true", help="N>1: skip the N-GPU == 1-GPU graph comparison")
+    ap.add_argument("--parity-gbases", type=float, default=24.0, help="N>1: size cap of the parity job (whole job)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ka-variant", default="default", choices=["default", "classic", "bitslice"],
                     help="K-A kernel (mdbg_params.ka_variant); default = the library's choice")
@@ -161,7 +167,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        n = max(64, reads_per_rank // 4)          # bounded sample of the same workload per step
+        n = max(64, min(reads_per_rank, 60000))   # bounded sample of the same workload per step (~0.9 Gbases)
         v, cores, total, sec, st = cpu_reference_run(wl, n, steps, warmup)
         sample = "first %d reads (%d bases) of the workload per step" % (n, total)
         out = {"impl": "reference", "metric": "Gbases/sec reads->mdBG", "value": v, "unit": "Gbases/s",
@@ -255,21 +261,28 @@ def main():
     ka_avg_ms = ka_ms / steps
     achieved = alg_bytes / (ka_avg_ms * 1e-3) / 1e9
     peak, peak_src = measured_peak()
-    traffic = None
-    # DRAM bytes of one launch from the committed ncu capture of the kernel variant that ran
-    tp = os.path.join(ROOT, "profiles", "ka_traffic_bitslice.json" if int(tm.get("ka_variant_used", 1)) == 2
-                      else "ka_traffic.json")
+    # DRAM bytes of one launch from the committed `ncu --set full` capture (tools/ncu_traffic.py) of the
+    # kernel variant that ran -- only while the capture belongs to THIS kernel (hash of its sources) and workload
+    traffic, traffic_note = None, "no capture"
+    variant_name = "bitslice" if int(tm.get("ka_variant_used", 1)) == 2 else "classic"
+    tp = os.path.join(ROOT, "profiles", "ka_traffic_bitslice.json" if variant_name == "bitslice" else "ka_traffic.json")
     if os.path.exists(tp):
         try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            from ka_hash import ka_source_hash
             tj = json.load(open(tp))
-            if tj.get("workload") == args.workload and int(tm.get("ka_variant_used", 1)) == int(tj.get("ka_variant", 1)):
-                traffic = tj.get("dram_bytes_per_launch")
-        except Exception:
-            pass
+            if tj.get("workload") != args.workload:
+                traffic_note = "capture is of workload %s" % tj.get("workload")
+            elif tj.get("source_hash") != ka_source_hash(variant_name):
+                traffic_note = "stale: the kernel sources changed since the capture"
+            else:
+                traffic, traffic_note = tj.get("dram_bytes_per_launch"), "ncu dram__bytes_read.sum + dram__bytes_write.sum, " + str(tj.get("report"))
+        except Exception as e:
+            traffic_note = "unreadable capture: %s" % e
     ka_variant = {1: "classic", 2: "bitslice"}.get(int(tm.get("ka_variant_used", 1)), "classic")
     roofline = {"kernel": "ka_bitslice_kernel" if ka_variant == "bitslice" else "ka_minimizers_kernel",
                 "ka_variant": ka_variant, "ka_dirty_tiles": int(tm.get("ka_dirty_tiles", 0)), "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": ka_avg_ms,
                 "share_of_step": ka_avg_ms / (dev_ms / steps)}
 
@@ -354,10 +367,81 @@ def main():
                "stage_ms_per_step": {k_: v_ / steps for k_, v_ in e2e_parts.items()}}
         ctx.host_free_pinned(hb); ctx.host_free_pinned(ho)
 
+    # ------------------------------------------------------------------ N>1: the N-GPU graph == the 1-GPU graph
+    parity = None
+    if world > 1 and not args.no_parity:
+        import numpy as np
+        # a bounded job: the first P reads of every rank's shard (all of them if the whole job fits the cap)
+        P = int(min(reads_per_rank, max(64, args.parity_gbases * 1e9 / 15000.0 / world)))
+        nb_p = int(ro[P])
+        ctx.reset()
+        ctx.set_read_base(rank * P)
+        ctx.push_reads_device(d_bases, d_off, P, nb_p)
+        g_multi = ctx.finish(want_seqlines=False)          # rank 0: the whole graph; other ranks: counters
+        ctx.reset()
+        ctx.set_read_base(rank * reads_per_rank)
+        ok, detail = None, ""
+        if rank == 0:
+            one = m.Context(m.Params(k=wl["k"], l=wl["l"], density=wl["density"], min_abundance=MIN_ABUNDANCE,
+                                     presimp=PRESIMP, device=local_rank, ka_variant=args.ka_variant))
+            for r_ in range(world):                        # the same reads, in rank order, through ONE context
+                ro_r, tot_r = synth.plan(r_ * reads_per_rank, P)
+                one_off = one.device_malloc((P + 1) * 8)
+                one_b = one.device_malloc(tot_r + 64)
+                synth.fill_device(one, r_ * reads_per_rank, P, ro_r, one_b, one_off)
+                one.push_reads_device(one_b, one_off, P, tot_r)
+                one.device_free(one_b); one.device_free(one_off)
+            g_one = one.finish(want_seqlines=False)
+            one.close()
+            bad = [a for a in ("index", "abundance", "seqlen", "shift", "tuple", "e_n1", "e_n2", "e_o1", "e_o2", "e_ov")
+                   if not np.array_equal(getattr(g_multi, a), getattr(g_one, a))]
+            bad += [c_ for c_ in ("n_kminmers", "n_distinct", "n_nodes", "n_edges", "presimp_removed")
+                    if g_multi.stats[c_] != g_one.stats[c_]]
+            ok = not bad and g_one.stats["n_nodes"] > 0
+            detail = "mismatch: " + ",".join(bad) if bad else "nodes (index, abundance, seqlen, shift, tuple) and edges bit-identical"
+            parity = {"parity_vs_single_gpu": bool(ok), "detail": detail,
+                      "job": "first %d reads of every rank's shard (%d reads, %.2f Gbases in all)" %
+                             (P, P * world, P * world * 15000.0 / 1e9),
+                      "n_nodes": int(g_one.stats["n_nodes"]), "n_edges": int(g_one.stats["n_edges"]),
+                      "n_kminmers": int(g_one.stats["n_kminmers"])}
+        barrier()
+
+    # ------------------------------------------------------------------ N=1: config 2 as an extra line
+    extra = None
+    if world == 1 and rank == 0 and not args.no_extra and args.workload != "ecoli50x":
+        w2 = WORKLOADS["ecoli50x"]
+        s2 = m.Synth(genome_len=w2["genome_len"])
+        n2 = s2.num_reads(w2["coverage"])
+        ro2, tot2 = s2.plan(0, n2)
+        c2 = m.Context(m.Params(k=w2["k"], l=w2["l"], density=w2["density"], min_abundance=MIN_ABUNDANCE, presimp=PRESIMP,
+                                device=local_rank, ka_variant=args.ka_variant))
+        b2 = c2.device_malloc(tot2 + 64); o2 = c2.device_malloc((n2 + 1) * 8)
+        s2.fill_device(c2, 0, n2, ro2, b2, o2)
+
+        def step2():
+            c2.reset()
+            c2.push_reads_device(b2, o2, n2, tot2)
+            return c2.finish_device()
+        for _ in range(5):
+            step2()
+        c2.sync(); c2.timer_start()
+        ka2, st2 = 0.0, None
+        for _ in range(20):
+            st2 = step2()
+            ka2 += c2.timings()["ms_ka_kernel"]
+        ms2 = c2.timer_stop() / 20
+        alg2 = tot2 + 12 * st2["n_minimizers"] + 16 * (n2 + 1)
+        extra = {"ecoli50x": {"workload": w2["desc"], "value": tot2 / (ms2 * 1e-3) / 1e9, "unit": "Gbases/s", "ms_per_step": ms2,
+                              "steps": 20, "warmup": 5, "ka_kernel_ms": ka2 / 20,
+                              "ka_roofline_frac": alg2 / (ka2 / 20 * 1e-3) / 1e9 / peak,
+                              "counts": {k_: int(v_) for k_, v_ in st2.items()}}}
+        c2.device_free(b2); c2.device_free(o2)
+        c2.close()
+
     # ------------------------------------------------------------------ CPU baseline (rank 0, N=1)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        n = max(64, reads_per_rank // 2)
+        n = max(64, min(reads_per_rank // 2, 140000))        # <= ~2 Gbases: 10-30 s of CPU work
         v, cores, tot, sec, _ = cpu_reference_run(wl, n, 1, 0)
         cpu = {"value": v, "unit": "Gbases/s", "cores": cores, "kind": "port",
                "sample": "first %d reads (%d bases) of the workload, %.1f s" % (n, tot, sec)}
@@ -373,6 +457,10 @@ def main():
                "counts": {k_: int(v_) for k_, v_ in stats.items()}}
         if multik is not None:
             out["multik"] = multik
+        if parity is not None:
+            out.update(parity)
+        if extra is not None:
+            out["extra"] = extra
         _emit(json.dumps(out))
     ctx.device_free(d_bases); ctx.device_free(d_off)
     ctx.close()

@@ -1,8 +1,11 @@
-"""World-size-2 `gloo` test (CPU) of the N>1 host logic: read sharding (mdbg_shard_reads), the
-fingerprint-range owner function (mdbg_owner_of_fingerprint / mdbg_tuple_fingerprint), serial
-ordinals across ranks and the node-index rule (sum of lower_bounds over the ranks' sorted
-first-sighting lists) -- the same plan graph.cu executes with NCCL.  The per-read minimizers
-come from the oracle (this is a test); the merged table must equal the single-process oracle."""
+"""World-size-2 `gloo` test (CPU) of the N>1 plan graph.cu executes with NCCL: read sharding
+(mdbg_shard_reads), serial ordinals across ranks (ordinal base = sightings of the ranks before), the
+fingerprint-prefix owner function (mdbg_owner_of_fingerprint / mdbg_tuple_fingerprint), the all-to-all
+of records bucketed by owner (stable: every bucket ascends in ordinal), and the node-index rule: every
+owner marks the first sighting of each of its tuples in a bitmap of two bits per ordinal, the bitmaps
+are SUMMED over the ranks (an ordinal has one owner, so the sum is the union) and the prefix popcount
+below a tuple's first sighting is its node index.  The per-read minimizers come from the oracle (this
+is a test); the merged table must equal the single-process oracle."""
 import ctypes
 import os
 import sys
@@ -56,12 +59,21 @@ def _worker(rank, world, port, k, l, d, minab, out):
         for ordinal, node in part:
             e = table.setdefault(node, [ordinal, 0])
             e[1] += 1
-    firsts = sorted(e[0] for e in table.values())
-    allfirsts = [None] * world
-    dist.all_gather_object(allfirsts, firsts)
+    ktot = sum(counts)
+    nwords = (ktot + 1 + 15) // 16
+    bits = np.zeros(nwords, np.int64)
+    for node, (first, cnt) in table.items():
+        solid = minab == 1 or (cnt & 0xFFFF) >= minab
+        bits[first >> 4] |= (3 if solid else 1) << (2 * (first & 15))
+    t = torch.from_numpy(bits)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)          # graph.cu: ncclAllReduce(ncclUint32, ncclSum)
+    bits = t.numpy().astype(np.uint32)
+    pop = np.array([bin(int(w) & 0x55555555).count("1") for w in bits], np.int64)
+    wscan = np.concatenate([[0], np.cumsum(pop)])
     mine = {}
     for node, (first, cnt) in table.items():
-        index = sum(int(np.searchsorted(np.array(f, dtype=np.int64), first, side="left")) for f in allfirsts)
+        below = int(bits[first >> 4]) & ((1 << (2 * (first & 15))) - 1)
+        index = int(wscan[first >> 4]) + bin(below & 0x55555555).count("1")
         if minab == 1 or (cnt & 0xFFFF) >= minab:
             mine[node] = (index, cnt & 0xFFFF)
     allnodes = [None] * world

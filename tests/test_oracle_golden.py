@@ -201,3 +201,21 @@ def test_read_stats_against_naive_python(oracle):
         eoff.append(len(exp))
     assert list(cnt) == exp and list(coff) == eoff
     assert any(c > 0 for c in exp) and any(c == 0 for c in exp)
+
+
+def test_oracle_reproduces_synthetic_digests(oracle):
+    """tests/golden/synth_graph_hashes.json (BASELINE config 2 in full): the oracle of this checkout still
+    produces the committed digests -- a change of the restatement cannot slip through unnoticed.  (The
+    1.05 Gbase slice of config 3 is re-derived by the GPU test, which runs the oracle anyway.)"""
+    import json
+    import os
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    import make_synth_hashes as G
+    gold = json.load(open(os.path.join(here, "golden", "synth_graph_hashes.json")))
+    c, host, ro, total = G.build_case("ecoli50x_full", threads=8)
+    o = oracle.build_graph(host, ro, c["k"], c["l"], c["density"], 2, 0.01)
+    assert int(total) == gold["ecoli50x_full"]["n_bases"]
+    assert G.graph_digest(o) == gold["ecoli50x_full"]["graph_sha256"]
+    assert G.minimizer_digest(o.m_hash, o.m_pos, o.m_off) == gold["ecoli50x_full"]["minimizers_sha256"]
