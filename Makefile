@@ -12,7 +12,7 @@ HDR := $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh include/*.h)
 
 CLI := rust-mdbg_b200/rust-mdbg
 
-all: $(OUT) $(CLI) oracle model model
+all: $(OUT) $(CLI) oracle model
 
 $(CLI): rust-mdbg_b200/cli/rust_mdbg_main.cpp include/mdbg.h $(OUT)
 	g++ -O2 -std=c++17 -Wall -o $@ $< -Lrust-mdbg_b200 -lmdbg_b200 -lz -Wl,-rpath,'$$ORIGIN'
@@ -40,23 +40,8 @@ model: $(MODEL)
 $(MODEL): tests/model/ka_bitslice_model.cpp $(HDR)
 	g++ -O2 -std=c++17 -fPIC -Wall -Wno-unknown-pragmas -pthread -I/usr/local/cuda/include -shared -o $@ $<
 
-# Opt-in variants of the bit-sliced K-A kernel (A/B measurements: MDBG_LIB=rust-mdbg_b200/libmdbg_b200_opt.so):
-# the last compaction round only on a warp vote, one queue atomic per lane, 64-position filter windows.
-# Same results (the CPU model of the variant runs the same tests); not part of `all` except the model.
-BS_OPT := -DMDBG_BS_PEXT_SKIP5 -DMDBG_BS_CAND_BATCH -DMDBG_BS_FILTER64
-MODEL_OPT := tests/model/libka_bitslice_model_opt.so
-$(MODEL_OPT): tests/model/ka_bitslice_model.cpp $(HDR)
-	g++ -O2 -std=c++17 -fPIC -Wall -Wno-unknown-pragmas -pthread $(BS_OPT) -I/usr/local/cuda/include -shared -o $@ $<
-model: $(MODEL_OPT)
-OUT_OPT := rust-mdbg_b200/libmdbg_b200_opt.so
-$(CSRC)/ka_bitslice_opt.o: $(CSRC)/ka_bitslice.cu $(HDR)
-	$(NVCC) $(NVFLAGS) $(BS_OPT) -c $< -o $@ 2> $@.ptxas.log || (cat $@.ptxas.log; exit 1)
-$(OUT_OPT): $(OBJ) $(CSRC)/ka_bitslice_opt.o
-	$(NVCC) $(ARCH) -shared -o $@ $(filter-out $(CSRC)/ka_bitslice.o,$(OBJ)) $(CSRC)/ka_bitslice_opt.o -ldl -lz -lpthread
-variants: $(OUT_OPT)
-
 clean:
-	rm -f $(CSRC)/*.o $(CSRC)/*.log $(OUT) $(OUT_OPT) $(CLI) tests/model/*.so
+	rm -f $(CSRC)/*.o $(CSRC)/*.log $(OUT) $(CLI) tests/model/*.so
 	$(MAKE) -C oracle clean
 
-.PHONY: all oracle model variants clean
+.PHONY: all oracle model clean

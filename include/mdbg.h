@@ -240,6 +240,14 @@ int mdbg_write_gfa(const mdbg_graph* g, const char* path);                   /* 
  * the HOST copies of the reads in global read order.                                       */
 int mdbg_write_sequences(const mdbg_graph* g, const uint8_t* bases, const uint64_t* read_off,
                          const char* path, int lz4_frame);
+/* Streaming form of the same writer (main.rs:696-707 writes a line while the worker still holds the read):
+ * the q-entries are in serial (read, window) order, so a host that walks its reads once more in input order
+ * hands over each read the writer asks for and never holds the whole read set.  *g must outlive the writer. */
+typedef struct mdbg_seq_writer mdbg_seq_writer;
+int      mdbg_seq_writer_open(const mdbg_graph* g, const char* path, int lz4_frame, mdbg_seq_writer** out);
+uint64_t mdbg_seq_writer_next_read(const mdbg_seq_writer* w);      /* UINT64_MAX: every line is written */
+int      mdbg_seq_writer_read(mdbg_seq_writer* w, uint64_t read_index, const uint8_t* read_bases, uint64_t read_len);
+int      mdbg_seq_writer_close(mdbg_seq_writer* w);                /* MDBG_ERR_IO if a needed read never came */
 
 /* ---- host ingest: 2-bit packing for the 4:1 upload (reference side: the reads the
  *      parser hands to Read::extract, main.rs:163-178,830-839) ----------------------------------

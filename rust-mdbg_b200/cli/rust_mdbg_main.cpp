@@ -1,7 +1,9 @@
 // rust-mdbg (B200) -- command line front end with the reference's flags (src/main.rs:228-423) for
 // the hot path: reads (FASTA/FASTQ, plain or .gz) -> {prefix}.gfa + {prefix}.0.sequences.
-// Host ingest only: parse, batch, mdbg_push_reads; all compute is in
-// libmdbg_b200.so.  Modes outside the hot path are refused, never silently run elsewhere.
+// Host ingest only: parallel parse (ingest.hpp) into two pinned batch buffers, one
+// being filled while the other is inside mdbg_push_reads; all compute is in libmdbg_b200.so.  The reads are
+// NOT kept in memory: the .sequences lines are cut in a second pass over the input (mdbg_seq_writer_*).
+// Modes outside the hot path are refused, never silently run elsewhere.
 // stdout follows the reference line by line.
 #include <sys/resource.h>
 #include <zlib.h>
@@ -15,73 +17,13 @@
 #include <string>
 #include <vector>
 
+#include <future>
+#include <thread>
+
 #include "../../include/mdbg.h"
+#include "ingest.hpp"
 
 namespace {
-
-struct Fastx {  // FASTA (multi-line) / FASTQ (4-line) records from a plain or gzip file (zlib reads both)
-    gzFile f = nullptr;
-    bool fasta = true;
-    std::vector<char> buf;
-    size_t pos = 0, len = 0;
-    std::string pending;  // FASTA: header line already consumed
-    std::string id;       // of the record next() returned: the header up to the first space (seq_io's id())
-    void set_id(const std::string& header) {
-        size_t e = header.find(' ');
-        id = header.substr(1, e == std::string::npos ? std::string::npos : e - 1);
-    }
-    bool open(const char* path, bool is_fasta) {
-        f = gzopen(path, "rb");
-        if (!f) return false;
-        gzbuffer(f, 1 << 20);
-        buf.resize(1 << 22);
-        fasta = is_fasta;
-        return true;
-    }
-    bool getline(std::string& out) {
-        out.clear();
-        for (;;) {
-            if (pos == len) {
-                int n = gzread(f, buf.data(), (unsigned)buf.size());
-                if (n <= 0) return !out.empty();
-                pos = 0; len = (size_t)n;
-            }
-            char* s = buf.data() + pos;
-            char* e = (char*)memchr(s, '\n', len - pos);
-            if (e) { out.append(s, e - s); pos = (e - buf.data()) + 1; break; }
-            out.append(s, len - pos);
-            pos = len;
-        }
-        if (!out.empty() && out.back() == '\r') out.pop_back();
-        return true;
-    }
-    // appends the sequence to `seq`; false at end of file
-    bool next(std::string& seq) {
-        std::string line;
-        seq.clear();
-        if (fasta) {
-            if (pending.empty()) {
-                do { if (!getline(line)) return false; } while (line.empty() || line[0] != '>');
-                pending = line;
-            }
-            set_id(pending);
-            pending.clear();
-            while (getline(line)) {
-                if (!line.empty() && line[0] == '>') { pending = line; return true; }
-                seq += line;
-            }
-            return true;
-        }
-        if (!getline(line)) return false;      // @id
-        if (line.empty()) return false;
-        set_id(line);
-        if (!getline(seq)) return false;       // sequence
-        getline(line);                         // +
-        getline(line);                         // qualities
-        return true;
-    }
-    void close() { if (f) gzclose(f); f = nullptr; }
-};
 
 [[noreturn]] void die(const std::string& m) { fprintf(stderr, "error: %s\n", m.c_str()); exit(1); }
 
@@ -97,6 +39,32 @@ std::string rust_f32(float v) {  // Rust `{}` of an f32
     char b[64];
     for (int p = 1; p <= 9; p++) { snprintf(b, sizeof b, "%.*g", p, (double)v); if (strtof(b, nullptr) == v) break; }
     return std::string(b);
+}
+
+double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+// Runs `consume(batch, first_read_index)` over every batch of `path`, in file order, while the next batch is
+// being parsed into the other pinned buffer.  Returns the number of reads.
+template <class F>
+unsigned long long for_each_batch(const std::string& path, bool fasta, bool want_ids, int threads, uint8_t* pin[2],
+                                  size_t cap, size_t target, F&& consume) {
+    ingest::Reader rd(threads);
+    if (!rd.open(path.c_str(), fasta, want_ids)) die("Error opening compressed file: " + path);
+    ingest::Batch bt[2];
+    for (int i = 0; i < 2; i++) { bt[i].bases = pin[i]; bt[i].cap = cap; }
+    std::string err;
+    unsigned long long n = 0;
+    auto fill = [&](int i) { return rd.next_batch(bt[i], target, err); };
+    std::future<bool> nxt = std::async(std::launch::async, fill, 0);
+    for (int i = 0;; i ^= 1) {
+        const bool have = nxt.get();
+        if (!err.empty()) die(err);
+        if (!have) break;
+        nxt = std::async(std::launch::async, fill, i ^ 1);     // parse the next batch while this one is consumed
+        consume(bt[i], n);
+        n += bt[i].n_reads();
+    }
+    return n;
 }
 
 }  // namespace
@@ -145,12 +113,17 @@ int main(int argc, char** argv) {
     if (k < 0 && l < 0 && density < 0) {   // main.rs:468-472, 214-226
         printf("Autodetecting values for k, l, and density.\n");
         printf("Parsing input sequences to estimate mean read length...\n");
-        Fastx fx;
-        if (!fx.open(reads.c_str(), fasta)) die("Error opening compressed file: " + reads);
-        std::string s;
         unsigned long long tot = 0, n = 0;
-        while (n < 100 && fx.next(s)) { tot += s.size(); n++; }
-        fx.close();
+        {
+            ingest::Reader rd(1);
+            if (!rd.open(reads.c_str(), fasta, false)) die("Error opening compressed file: " + reads);
+            ingest::Batch b;
+            std::vector<uint8_t> tmp(96u << 20);
+            b.bases = tmp.data(); b.cap = tmp.size();
+            std::string err;
+            if (rd.next_batch(b, 8u << 20, err))
+                for (; n < 100 && n < b.n_reads(); n++) tot += b.off[n + 1] - b.off[n];
+        }
         unsigned long long mean = n ? tot / n : 0;
         printf("Detected mean read length of %llu bp.\n", mean);
         dd = 0.003; kk = (long)(dd * (double)mean); ll = 12;
@@ -182,38 +155,22 @@ int main(int argc, char** argv) {
     if (mdbg_ctx_create(&P, &ctx) != MDBG_OK) die(mdbg_last_error(nullptr));
 
     printf("Parsing input sequences...\n");
-    Fastx fx;
-    if (!fx.open(reads.c_str(), fasta)) die("Error opening compressed file: " + reads);
-    const size_t BATCH = 256u << 20;
-    std::vector<uint8_t> all_bases;        // kept only for the .sequences slices
-    std::vector<uint64_t> all_off{0};
-    uint8_t* pin = nullptr;
-    if (mdbg_host_alloc_pinned(BATCH + (64u << 20), (void**)&pin) != MDBG_OK) die("cudaMallocHost failed");
-    std::vector<uint64_t> off{0};
-    size_t fill = 0;
-    unsigned long long nb_reads = 0;
-    std::string s;
-    auto flush = [&]() {
-        if (off.size() == 1) return;
-        if (mdbg_push_reads(ctx, pin, off.data(), off.size() - 1) != MDBG_OK) die(mdbg_last_error(ctx));
-        if (!no_basespace) {
-            size_t base = all_bases.size();
-            all_bases.insert(all_bases.end(), pin, pin + fill);
-            for (size_t i = 1; i < off.size(); i++) all_off.push_back(base + off[i]);
-        }
-        off.assign(1, 0);
-        fill = 0;
-    };
-    while (fx.next(s)) {
-        if (s.size() > BATCH + (64u << 20)) die("a record longer than the staging buffer (use a larger batch)");
-        if (fill + s.size() > BATCH + (64u << 20) || fill >= BATCH) flush();
-        memcpy(pin + fill, s.data(), s.size());
-        fill += s.size();
-        off.push_back(fill);
-        nb_reads++;
-    }
-    flush();
-    fx.close();
+    const int n_threads = (int)std::max<long>(1, threads > 0 ? threads : (long)std::thread::hardware_concurrency());
+    const size_t BATCH = 256u << 20, CAP = BATCH + (160u << 20);   // text window per batch; room for a gz block + carry
+    uint8_t* pin[2] = {nullptr, nullptr};
+    for (int i = 0; i < 2; i++)
+        if (mdbg_host_alloc_pinned(CAP, (void**)&pin[i]) != MDBG_OK) die("cudaMallocHost failed");
+    const double t_ingest = now_s();
+    double t_push = 0;
+    unsigned long long nb_bases = 0;
+    unsigned long long nb_reads = for_each_batch(reads, fasta, false, n_threads, pin, CAP, BATCH,
+        [&](ingest::Batch& b, unsigned long long) {
+            const double t0 = now_s();
+            if (mdbg_push_reads(ctx, b.bases, b.off.data(), b.n_reads()) != MDBG_OK) die(mdbg_last_error(ctx));
+            t_push += now_s() - t0;
+            nb_bases += b.fill;
+        });
+    const double t_ingest_end = now_s();
     fprintf(stderr, "Converted reads to k-min-mers.\n");
     printf("Number of reads: %llu\n", nb_reads);
     mdbg_graph g;
@@ -232,58 +189,61 @@ int main(int argc, char** argv) {
                          (read_stats.size() >= 3 && read_stats.compare(read_stats.size() - 3, 3, ".fa") == 0) ||
                          (read_stats.size() >= 6 && read_stats.compare(read_stats.size() - 6, 6, ".fasta") == 0);
         printf(sfa ? "Format: FASTA\n" : "Format: FASTQ\n");
-        Fastx sx;
-        if (!sx.open(read_stats.c_str(), sfa)) die("Error opening compressed file: " + read_stats);
-        std::vector<std::string> ids;
         std::vector<uint32_t> counts;
         std::vector<uint64_t> coff;
-        auto flush_stats = [&]() {
-            if (off.size() == 1) return;
-            const uint64_t n = off.size() - 1;
+        for_each_batch(read_stats, sfa, true, n_threads, pin, CAP, BATCH, [&](ingest::Batch& b, unsigned long long) {
+            const uint64_t n = b.n_reads();
             coff.assign(n + 1, 0);
             uint64_t need_n = 0;
-            int rc = mdbg_read_stats(ctx, pin, off.data(), n, counts.data(), coff.data(), counts.size(), &need_n);
+            int rc = mdbg_read_stats(ctx, b.bases, b.off.data(), n, counts.data(), coff.data(), counts.size(), &need_n);
             if (rc == MDBG_ERR_CAPACITY) {
                 counts.resize(need_n + need_n / 8 + 1024);
-                rc = mdbg_read_stats(ctx, pin, off.data(), n, counts.data(), coff.data(), counts.size(), &need_n);
+                rc = mdbg_read_stats(ctx, b.bases, b.off.data(), n, counts.data(), coff.data(), counts.size(), &need_n);
             }
             if (rc != MDBG_OK) die(mdbg_last_error(ctx));
             std::string line;
             for (uint64_t r = 0; r < n; r++) {                                    // read_stats.rs:53-64
-                line = ids[r] + ": ";
+                line = b.ids[r] + ": ";
                 for (uint64_t j = coff[r]; j < coff[r + 1]; j++) { line += std::to_string(counts[j]); line += ' '; }
                 line += '\n';
                 fwrite(line.data(), 1, line.size(), sf);
             }
-            off.assign(1, 0);
-            fill = 0;
-            ids.clear();
-        };
-        while (sx.next(s)) {
-            if (s.size() > BATCH + (64u << 20)) die("a record longer than the staging buffer (use a larger batch)");
-            if (fill + s.size() > BATCH + (64u << 20) || fill >= BATCH) flush_stats();
-            memcpy(pin + fill, s.data(), s.size());
-            fill += s.size();
-            off.push_back(fill);
-            ids.push_back(sx.id);
-        }
-        flush_stats();
-        sx.close();
+        });
         fclose(sf);
         printf("Read stats written, exiting.\n");
         mdbg_graph_free(&g);
-        mdbg_host_free_pinned(pin);
+        mdbg_host_free_pinned(pin[0]); mdbg_host_free_pinned(pin[1]);
         mdbg_ctx_destroy(ctx);
         return 0;
     }
+    const double t_graph = now_s();
     if (mdbg_write_gfa(&g, (prefix + ".gfa").c_str()) != MDBG_OK) die("Couldn't create " + prefix + ".gfa");
-    if (!no_basespace &&
-        mdbg_write_sequences(&g, all_bases.data(), all_off.data(), (prefix + ".0.sequences").c_str(), 1) != MDBG_OK)
-        die("Couldn't create file: " + prefix + ".0.sequences");
+    const double t_gfa = now_s();
+    if (!no_basespace) {   // second pass over the input: cut the .sequences lines (main.rs:696-707) without holding the reads
+        mdbg_seq_writer* sw = nullptr;
+        const std::string sp = prefix + ".0.sequences";
+        if (mdbg_seq_writer_open(&g, sp.c_str(), 1, &sw) != MDBG_OK) die("Couldn't create file: " + sp);
+        if (mdbg_seq_writer_next_read(sw) != UINT64_MAX)
+            for_each_batch(reads, fasta, false, n_threads, pin, CAP, BATCH, [&](ingest::Batch& b, unsigned long long first) {
+                for (uint64_t r; (r = mdbg_seq_writer_next_read(sw)) != UINT64_MAX && r < first + b.n_reads();) {
+                    if (r < first) die("internal: .sequences lines out of read order");
+                    const uint64_t i = r - first;
+                    if (mdbg_seq_writer_read(sw, r, b.bases + b.off[i], b.off[i + 1] - b.off[i]) != MDBG_OK)
+                        die("Couldn't write file: " + sp);
+                }
+            });
+        if (mdbg_seq_writer_close(sw) != MDBG_OK) die("Couldn't write file: " + sp);
+    }
+    const double t_seq = now_s();
+    if (getenv("MDBG_CLI_TIMING"))
+        fprintf(stderr, "[timing] ingest+K-A %.3f s (%.3f inside mdbg_push_reads, %.2f Gbases/s over %llu bases, %d parser threads), "
+                "finish %.3f s, .gfa %.3f s, .sequences %.3f s\n", t_ingest_end - t_ingest, t_push,
+                (double)nb_bases / (t_ingest_end - t_ingest) / 1e9, nb_bases, n_threads, t_graph - t_ingest_end, t_gfa - t_graph,
+                t_seq - t_gfa);
     printf("Number of mdBG edges: %llu\n", (unsigned long long)g.n_edges);
     if (ps > 0.0f) printf("Pre-simp = %s: %llu edges removed.\n", rust_f32(ps).c_str(), (unsigned long long)g.presimp_removed);
     mdbg_graph_free(&g);
-    mdbg_host_free_pinned(pin);
+    mdbg_host_free_pinned(pin[0]); mdbg_host_free_pinned(pin[1]);
     mdbg_ctx_destroy(ctx);
     double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
     printf("Total execution time: %.9gs\n", sec);

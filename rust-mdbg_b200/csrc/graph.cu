@@ -520,7 +520,7 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
         uint32_t EP = 0, NR = 0;
         bool overflow = false;
         if (q_n > 0) {
-            ke_join_kernel<0><<<nblk(q_n, 128), 128, 0, st>>>(NV, ekey, erev, skey, sval, inv, presimp, q_lo, q_n, cnt_q, nullptr,
+            ke_join_kernel<0><<<nblk((uint64_t)q_n * KE_LANES, 128), 128, 0, st>>>(NV, ekey, erev, skey, sval, inv, presimp, q_lo, q_n, cnt_q, nullptr,
                                                               cap_e, cap_r, &c->d_sc->v[6]);
             LAUNCHED(c);
             RC(R.cub([&](void* t, size_t& b) { return cub::DeviceScan::ExclusiveSum(t, b, cnt_q.p, off_q.p, q_n + 1, st); }));
@@ -536,7 +536,7 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
         MDBG_CK(c, pend.get(c->pool, EP)); MDBG_CK(c, removed.get(c->pool, NR));
         if (EP > 0 || NR > 0) {
             if (overflow) {
-                ke_join_kernel<1><<<nblk(q_n, 128), 128, 0, st>>>(NV, ekey, erev, skey, sval, inv, presimp, q_lo, q_n, nullptr,
+                ke_join_kernel<1><<<nblk((uint64_t)q_n * KE_LANES, 128), 128, 0, st>>>(NV, ekey, erev, skey, sval, inv, presimp, q_lo, q_n, nullptr,
                                                                   off_q, pend, removed, nullptr);
                 LAUNCHED(c);
                 ke_group_sort_kernel<<<nblk(q_n / 2), 256, 0, st>>>(pend, off_q, q_n / 2);

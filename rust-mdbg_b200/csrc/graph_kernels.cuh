@@ -505,12 +505,52 @@ __global__ void ke_inverse_kernel(const uint32_t* __restrict__ sval, uint32_t n,
     if (m < n) inv[sval[m]] = m;
 }
 
-// One thread per (n1, key) with key in [suffix_norm, prefix_norm] (main.rs:1050-1052).
+// EIGHT lanes per (n1, key) with key in [suffix_norm, prefix_norm] (main.rs:1050-1052): the lanes split the
+// k-1 elements of every tuple comparison (a chain of dependent 8-byte loads when one thread walks it), vote
+// with shuffles inside their group, and all of them keep the (identical) bookkeeping; lane 0 writes.
 //   MODE 0 (capture): decide the edges once, park up to KE_CAP_E kept edges / KE_CAP_R presimp
 //          removals of the query in fixed slots, write the packed counts (edges | removals << 32);
 //          a query that needs more raises *overflow and the host falls back to MODE 1
 //   MODE 1 (write): emit at the scanned packed offsets (exact, any bucket size)
 constexpr uint32_t KE_CAP_E = 8, KE_CAP_R = 4;
+constexpr uint32_t KE_LANES = 8;
+
+// bit 0: the entry's normalised (k-1)-mer equals the query's; bits 1..4: the four orientation identities of
+// main.rs:1062-1075 -- (+,+) n1.suffix == n2.prefix, (+,-) n1.suffix == rev_n2.prefix, (-,+) rev_n1.suffix ==
+// n2.prefix, (-,-) rev_n1.suffix == rev_n2.prefix.  Every lane of the group returns the same word.
+__device__ __forceinline__ uint32_t ke_compare(const uint64_t* __restrict__ t1, const uint64_t* __restrict__ t2,
+                                               const uint64_t* __restrict__ qsub, bool qrev,
+                                               const uint64_t* __restrict__ esub, bool er, uint32_t k,
+                                               uint32_t sub, uint32_t gmask) {
+    const uint32_t k1 = k - 1;
+    uint32_t ok = 31u;
+    for (uint32_t base = 0; base < k1; base += KE_LANES) {   // same trip count for every lane of the group
+        const uint32_t j = base + sub;
+        if (j < k1) {
+            const uint64_t qa = __ldg(qrev ? qsub + (k1 - 1 - j) : qsub + j);
+            const uint64_t ea = __ldg(er ? esub + (k1 - 1 - j) : esub + j);
+            const uint64_t a1 = __ldg(t1 + 1 + j), a2 = __ldg(t1 + k - 2 - j);
+            const uint64_t c1 = __ldg(t2 + j), c2 = __ldg(t2 + k - 1 - j);
+            if (qa != ea) ok &= ~1u;
+            if (a1 != c1) ok &= ~2u;
+            if (a1 != c2) ok &= ~4u;
+            if (a2 != c1) ok &= ~8u;
+            if (a2 != c2) ok &= ~16u;
+        }
+        if (base == 0) {   // after the first 8 elements almost every foreign key is known: leave together
+            uint32_t r = ok;
+            r &= __shfl_xor_sync(gmask, r, 1);
+            r &= __shfl_xor_sync(gmask, r, 2);
+            r &= __shfl_xor_sync(gmask, r, 4);
+            if ((r & 1u) == 0u) return 0u;
+        }
+    }
+    ok &= __shfl_xor_sync(gmask, ok, 1);
+    ok &= __shfl_xor_sync(gmask, ok, 2);
+    ok &= __shfl_xor_sync(gmask, ok, 4);
+    return (ok & 1u) ? ok : 0u;
+}
+
 template <int MODE>
 __global__ void ke_join_kernel(NodeView N, const uint64_t* __restrict__ ekey, const uint8_t* __restrict__ erev,
                                const uint64_t* __restrict__ skey, const uint32_t* __restrict__ sval,
@@ -519,9 +559,11 @@ __global__ void ke_join_kernel(NodeView N, const uint64_t* __restrict__ ekey, co
                                EdgeRec* __restrict__ edges, uint64_t* __restrict__ removed,
                                unsigned long long* __restrict__ overflow) {
     // queries [q_lo, q_lo + q_n) of the 2S (n1, key) pairs: the slice of nodes this GPU emits edges for
-    uint32_t qq = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t S = N.S, k = N.k, k1 = k - 1;
-    if (qq >= q_n) return;
+    const uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    const uint32_t qq = (uint32_t)(tid / KE_LANES), sub = (uint32_t)(tid % KE_LANES);
+    const uint32_t gmask = 0xFFu << ((threadIdx.x & 31u) & ~7u);
+    const uint32_t S = N.S, k = N.k;
+    if (qq >= q_n) return;      // whole groups leave together (blockDim is a multiple of 8)
     uint32_t q = q_lo + qq;
     uint32_t n1 = q >> 1, which = q & 1;
     uint32_t qe = 2 * n1 + (which == 0 ? 1 : 0);  // which 0: suffix entry, 1: prefix entry
@@ -534,8 +576,10 @@ __global__ void ke_join_kernel(NodeView N, const uint64_t* __restrict__ ekey, co
     const uint64_t* qsub = t1 + (qe & 1);
     bool qrev = erev[qe];
     uint32_t ab1 = N.abundance[n1];
-    // pass 0: number of potential edges and max abundance; pass 1: decide each edge
+    // pass 0: number of potential edges and max abundance; pass 1: decide each edge.  The comparison words
+    // of the first 12 entries of the bucket are kept from pass 0 (5 bits each).
     uint32_t npot = 0, abmax = 0, ne = 0, nr = 0;
+    uint64_t cache = 0;
     const uint64_t o64 = MODE == 1 ? off[qq] : 0;
     const uint32_t oe = MODE == 1 ? (uint32_t)o64 : qq * KE_CAP_E;
     const uint32_t orr = MODE == 1 ? (uint32_t)(o64 >> 32) : qq * KE_CAP_R;
@@ -545,27 +589,23 @@ __global__ void ke_join_kernel(NodeView N, const uint64_t* __restrict__ ekey, co
             uint32_t ent = sval[e];
             uint32_t n2 = ent >> 1;
             const uint64_t* t2 = N.tuple + (uint64_t)n2 * k;
-            const uint64_t* esub = t2 + (ent & 1);
-            bool er = erev[ent];
-            // same (k-1)-mer key? (fingerprints only bucket; identity is on the tuples)
-            bool same = eq_range(qrev ? qsub + k1 - 1 : qsub, qrev ? -1 : 1, er ? esub + k1 - 1 : esub, er ? -1 : 1, k1);
-            if (!same) continue;
-            // the four orientation identities of main.rs:1062-1075
-            bool t[4];
-            t[0] = eq_range(t1 + 1, 1, t2, 1, k1);              // n1.suffix == n2.prefix       (+,+)
-            t[1] = eq_range(t1 + 1, 1, t2 + k - 1, -1, k1);     // n1.suffix == rev_n2.prefix   (+,-)
-            t[2] = eq_range(t1 + k - 2, -1, t2, 1, k1);         // rev_n1.suffix == n2.prefix   (-,+)
-            t[3] = eq_range(t1 + k - 2, -1, t2 + k - 1, -1, k1);  // rev_n1.suffix == rev_n2.prefix (-,-)
+            uint32_t t;
+            if (pass == 1 && e - b0 < 12) t = (uint32_t)(cache >> (5 * (e - b0))) & 31u;
+            else {
+                t = ke_compare(t1, t2, qsub, qrev, t2 + (ent & 1), erev[ent] != 0, k, sub, gmask);
+                if (pass == 0 && e - b0 < 12) cache |= (uint64_t)t << (5 * (e - b0));
+            }
+            if (!(t & 1u)) continue;   // another (k-1)-mer in the same fingerprint bucket
             uint32_t ab2 = N.abundance[n2];
             for (int o = 0; o < 4; o++) {
-                if (!t[o]) continue;
+                if (!((t >> (1 + o)) & 1u)) continue;
                 if (pass == 0) { npot++; abmax = ab2 > abmax ? ab2 : abmax; continue; }
                 if (presimp > 0.0f && npot >= 2 && (float)ab2 < presimp * (float)abref) {  // main.rs:1086
-                    if (MODE == 1 || nr < KE_CAP_R) removed[orr + nr] = ((uint64_t)N.index[n1] << 32) | N.index[n2];
+                    if (sub == 0 && (MODE == 1 || nr < KE_CAP_R)) removed[orr + nr] = ((uint64_t)N.index[n1] << 32) | N.index[n2];
                     nr++;
                     continue;
                 }
-                if (MODE == 1 || ne < KE_CAP_E) {
+                if (sub == 0 && (MODE == 1 || ne < KE_CAP_E)) {
                     uint32_t sh = (o < 2) ? N.shift[2 * n1] : N.shift[2 * n1 + 1];
                     uint32_t a = N.seqlen[n1] - sh, b = N.seqlen[n2] - 1;  // main.rs:1091-1092
                     EdgeRec r;
@@ -578,7 +618,7 @@ __global__ void ke_join_kernel(NodeView N, const uint64_t* __restrict__ ekey, co
         }
         if (npot == 0) break;
     }
-    if (MODE == 0) {
+    if (MODE == 0 && sub == 0) {
         cnt[qq] = (uint64_t)ne | ((uint64_t)nr << 32);
         if (ne > KE_CAP_E || nr > KE_CAP_R) atomicAdd(overflow, 1ull);
     }

@@ -156,6 +156,8 @@ int mdbg_write_gfa(const mdbg_graph* g, const char* path) {
     if (!g || !path) return MDBG_ERR_BAD_ARG;
     FILE* f = fopen(path, "w");
     if (!f) return MDBG_ERR_IO;
+    std::vector<char> big(8u << 20);
+    setvbuf(f, big.data(), _IOFBF, big.size());
     fputs("H\tVN:Z:1.0\n", f);
     for (uint64_t i = 0; i < g->n_nodes; i++)
         fprintf(f, "S\t%u\t*\tLN:i:%u\tKC:i:%u\n", g->node_index[i], g->seqlen[i], (unsigned)g->abundance[i]);
@@ -168,38 +170,87 @@ int mdbg_write_gfa(const mdbg_graph* g, const char* path) {
 // {prefix}.{tid}.sequences: 4 '#' header lines (main.rs:625-628) then one line per q-entry
 // "{index}\t{:?Vec<u64>}\t{seq}\t*\t*\t({s0}, {s1})" (main.rs:702), seq = raw[start..end),
 // reverse-complemented when the node was reversed (main.rs:700-701).
-int mdbg_write_sequences(const mdbg_graph* g, const uint8_t* bases, const uint64_t* read_off, const char* path,
-                         int lz4_frame) {
-    if (!g || !path || (g->n_seqlines && (!g->q_index || !bases || !read_off))) return MDBG_ERR_BAD_ARG;
+// Streaming form: the q-entries are in serial (read, window) order, so a host that walks its reads once
+// more in input order hands every read the writer asks for to mdbg_seq_writer_read -- nobody has to keep
+// the whole read set in memory (the reference writes each line while it still holds the read, main.rs:696).
+struct mdbg_seq_writer {
+    const mdbg_graph* g = nullptr;
+    FILE* f = nullptr;
+    Lz4StoredWriter w{nullptr, false, {}};
+    uint64_t q = 0;
+    bool ok = true;
+    std::string line, rc;
+};
+
+int mdbg_seq_writer_open(const mdbg_graph* g, const char* path, int lz4_frame, mdbg_seq_writer** out) {
+    if (!g || !path || !out || (g->n_seqlines && !g->q_index)) return MDBG_ERR_BAD_ARG;
+    *out = nullptr;
     FILE* f = fopen(path, "wb");
     if (!f) return MDBG_ERR_IO;
-    Lz4StoredWriter w{f, lz4_frame != 0, {}};
-    bool ok = w.begin();
-    std::string line = "# k = " + std::to_string(g->k) + "\n# l = " + std::to_string(g->l) +
-                       "\n# Structure of remaining of the file:\n"
-                       "# [node name]\t[list of minimizers]\t[sequence of node]\t[abundance]\t[origin]\t[shift]\n";
-    ok = ok && w.write(line.data(), line.size());
-    // node index -> row (nodes are sorted by index)
-    std::string rc;
-    for (uint64_t q = 0; ok && q < g->n_seqlines; q++) {
-        uint32_t idx = g->q_index[q];
-        const uint32_t* it = std::lower_bound(g->node_index, g->node_index + g->n_nodes, idx);
+    mdbg_seq_writer* W = new mdbg_seq_writer();
+    W->g = g; W->f = f;
+    W->w = Lz4StoredWriter{f, lz4_frame != 0, {}};
+    W->ok = W->w.begin();
+    std::string hdr = "# k = " + std::to_string(g->k) + "\n# l = " + std::to_string(g->l) +
+                      "\n# Structure of remaining of the file:\n"
+                      "# [node name]\t[list of minimizers]\t[sequence of node]\t[abundance]\t[origin]\t[shift]\n";
+    W->ok = W->ok && W->w.write(hdr.data(), hdr.size());
+    *out = W;
+    return MDBG_OK;
+}
+
+// global index of the read the next line is cut from; UINT64_MAX when every line has been written
+uint64_t mdbg_seq_writer_next_read(const mdbg_seq_writer* W) {
+    return (W && W->q < W->g->n_seqlines) ? W->g->q_read[W->q] : UINT64_MAX;
+}
+
+// Writes every pending line cut from read `read_index` (bases of that read: read_bases[0 .. read_len)).
+// Reads must come in ascending order; reads no line needs may be skipped.
+int mdbg_seq_writer_read(mdbg_seq_writer* W, uint64_t read_index, const uint8_t* read_bases, uint64_t read_len) {
+    if (!W) return MDBG_ERR_BAD_ARG;
+    const mdbg_graph* g = W->g;
+    while (W->ok && W->q < g->n_seqlines && g->q_read[W->q] == read_index) {
+        const uint64_t q = W->q++;
+        if (g->q_end[q] > read_len || g->q_start[q] > g->q_end[q] || !read_bases) return MDBG_ERR_BAD_ARG;
+        const uint32_t idx = g->q_index[q];
+        const uint32_t* it = std::lower_bound(g->node_index, g->node_index + g->n_nodes, idx);   // nodes ascend in index
+        std::string& line = W->line;
         line = std::to_string(idx) + "\t[";
         if (it != g->node_index + g->n_nodes && *it == idx) {
             const uint64_t* t = g->tuple + (uint64_t)(it - g->node_index) * g->k;
             for (uint32_t j = 0; j < g->k; j++) { if (j) line += ", "; line += std::to_string(t[j]); }
         }
         line += "]\t";
-        const uint8_t* s = bases + read_off[g->q_read[q]] + g->q_start[q];
-        uint64_t len = g->q_end[q] - g->q_start[q];
-        if (g->q_reversed[q]) { revcomp_into(s, len, rc); line += rc; }
+        const uint8_t* s = read_bases + g->q_start[q];
+        const uint64_t len = g->q_end[q] - g->q_start[q];
+        if (g->q_reversed[q]) { revcomp_into(s, len, W->rc); line += W->rc; }
         else line.append((const char*)s, len);
         line += "\t*\t*\t(" + std::to_string(g->q_shift[2 * q]) + ", " + std::to_string(g->q_shift[2 * q + 1]) + ")\n";
-        ok = w.write(line.data(), line.size());
+        W->ok = W->w.write(line.data(), line.size());
     }
-    ok = ok && w.end();
-    ok = (fclose(f) == 0) && ok;
+    return W->ok ? MDBG_OK : MDBG_ERR_IO;
+}
+
+int mdbg_seq_writer_close(mdbg_seq_writer* W) {
+    if (!W) return MDBG_ERR_BAD_ARG;
+    bool ok = W->ok && W->q == W->g->n_seqlines;   // a line whose read never came is an error
+    ok = W->w.end() && ok;
+    ok = (fclose(W->f) == 0) && ok;
+    delete W;
     return ok ? MDBG_OK : MDBG_ERR_IO;
+}
+
+// The same in one call when the host still holds all reads (bases / read_off in global read order).
+int mdbg_write_sequences(const mdbg_graph* g, const uint8_t* bases, const uint64_t* read_off, const char* path,
+                         int lz4_frame) {
+    if (!g || !path || (g->n_seqlines && (!g->q_index || !bases || !read_off))) return MDBG_ERR_BAD_ARG;
+    mdbg_seq_writer* W = nullptr;
+    int rc = mdbg_seq_writer_open(g, path, lz4_frame, &W);
+    if (rc) return rc;
+    for (uint64_t r; rc == MDBG_OK && (r = mdbg_seq_writer_next_read(W)) != UINT64_MAX;)
+        rc = mdbg_seq_writer_read(W, r, bases + read_off[r], read_off[r + 1] - read_off[r]);
+    const int rc2 = mdbg_seq_writer_close(W);
+    return rc ? rc : rc2;
 }
 
 int mdbg_pack_bases_host(const uint8_t* bases, uint64_t n_bases, uint32_t* planes, uint8_t* bad_tiles, int threads) {

@@ -7,11 +7,11 @@
 //
 //   P1  stage the tile (cp.async 16-byte chunks -> padded rows, one row of 128 bytes per lane); the
 //       copy of tile n+1 is issued as soon as the rows of tile n are dead and lands under P4..P6;
-//   P2  ASCII -> two bit planes, 4 bases per multiply (ka_bitslice_math.h), alphabet check;
+//   P2  ASCII -> two bit planes, 8 bases per multiply (ka_bitslice_math.h), alphabet check;
 //   P3  run starts = plane word XOR itself shifted by one (32 bases per instruction), read starts
 //       forced; the planes are compacted by the run mask (parallel-suffix compress) and appended to
 //       the warp's HPC bit streams in shared memory -- the HPC string is materialised at 2 bits/base;
-//   P4  every lane filters windows of 32 HPC positions (stride 33-T) with filter_window<L,T>;
+//   P4  every lane filters windows of 64 HPC positions (stride 65-T) with filter_window64<L,T>;
 //   P5  the ~0.8 % survivors are hashed exactly from 4-base tables; raw positions come from a
 //       select in the run masks; windows that leave their read are dropped with a bitmap of read
 //       starts in HPC space;
@@ -125,25 +125,33 @@ BS_DEV void put_bits(uint32_t* arr, uint32_t o, uint32_t v) {
     if (v << s) bs_atomic_or_s(arr + w, v << s);
     if (s && (v >> (32u - s))) bs_atomic_or_s(arr + w + 1, v >> (32u - s));
 }
+// the same for both plane streams at once, branch-free (the streams have a spare word at the end)
+BS_DEV void put_bits2(uint32_t* arr_a, uint32_t* arr_b, uint32_t o, uint32_t va, uint32_t vb) {
+    const uint32_t w = o >> 5, s = o & 31u;
+    bs_atomic_or_s(arr_a + w, va << s);
+    bs_atomic_or_s(arr_a + w + 1, shr_clamp(va, 32u - s));
+    bs_atomic_or_s(arr_b + w, vb << s);
+    bs_atomic_or_s(arr_b + w + 1, shr_clamp(vb, 32u - s));
+}
 
 // 32 raw bytes (8 words at p, 16-byte aligned) -> plane words; alphabet flags accumulate in acc
 BS_DEV void gather32(const uint8_t* p, uint32_t& A, uint32_t& B, BadAcc& acc) {
     const uint4 v0 = *reinterpret_cast<const uint4*>(p);
     const uint4 v1 = *reinterpret_cast<const uint4*>(p + 16);
-    A = 0; B = 0;
-    plane_push(v1.w, A, B); plane_push(v1.z, A, B); plane_push(v1.y, A, B); plane_push(v1.x, A, B);
-    plane_push(v0.w, A, B); plane_push(v0.z, A, B); plane_push(v0.y, A, B); plane_push(v0.x, A, B);
+    uint32_t a0, a1, a2, a3, b0, b1, b2, b3;
+    plane_pair(v0.x, v0.y, a0, b0); plane_pair(v0.z, v0.w, a1, b1);
+    plane_pair(v1.x, v1.y, a2, b2); plane_pair(v1.z, v1.w, a3, b3);
+    A = top_bytes(a0, a1, a2, a3);
+    B = top_bytes(b0, b1, b2, b3);
     bad_accumulate(acc, v0.x); bad_accumulate(acc, v0.y); bad_accumulate(acc, v0.z); bad_accumulate(acc, v0.w);
     bad_accumulate(acc, v1.x); bad_accumulate(acc, v1.y); bad_accumulate(acc, v1.z); bad_accumulate(acc, v1.w);
 }
 
-// Queue the set bits of `cand` (HPC positions s + k).  Default: one shared-memory atomic per candidate;
-// MDBG_BS_CAND_BATCH: one per lane and call (the lane reserves all its slots at once).
+// Queue the set bits of `cand` (HPC positions s + k): one shared-memory atomic per lane and call (the lane
+// reserves all its slots at once).
 BS_DEV void push_candidates(WarpSmem& sm, uint32_t cand, const uint32_t s) {
-#if defined(MDBG_BS_CAND_BATCH)
     if (!cand) return;
     uint32_t qi = bs_atomic_add_s(&sm.qn, popc32(cand));
-#endif
     while (cand) {
 #if defined(__CUDA_ARCH__)
         const uint32_t k = (uint32_t)__ffs((int)cand) - 1u;
@@ -151,13 +159,8 @@ BS_DEV void push_candidates(WarpSmem& sm, uint32_t cand, const uint32_t s) {
         const uint32_t k = (uint32_t)__builtin_ctz(cand);
 #endif
         cand &= cand - 1u;
-#if !defined(MDBG_BS_CAND_BATCH)
-        const uint32_t qi = bs_atomic_add_s(&sm.qn, 1u);
-#endif
         if (qi < (uint32_t)QCAP) sm.u.q.queue[qi] = s + k;
-#if defined(MDBG_BS_CAND_BATCH)
         qi++;
-#endif
     }
 }
 
@@ -260,39 +263,36 @@ BS_DEV void process_tile(const KAArgs& A, WarpSmem& sm, const int lane, const ui
     // ---- P2 + P3: planes, alphabet, run starts, compaction (one raw word of 32 bases at a time) ----
     BadAcc bacc{0, 0, 0};
     uint32_t tot = 0, tail;
+    const bool has_starts = lbn > lb;                  // warp-uniform: most tiles hold no read start
     {
         const uint8_t* row = sm.raw + lane * RSTRIDE;
         const uint32_t prevb = lane ? (uint32_t)sm.raw[(lane - 1) * RSTRIDE + 127] : preb;
         const bool prev_ok = is_acgt(prevb);        // N / nothing before the tile: a run starts
-        uint32_t pa = (prevb >> 1) & 1u, pb = (prevb >> 2) & 1u;
+        // planes of the previous word: only their top bits matter (the base before this lane's first)
+        uint32_t qa = ((prevb >> 1) & 1u) << 31, qb = ((prevb >> 2) & 1u) << 31;
 #pragma unroll 1
         for (int n = 0; n < 4; n++) {
             const int idx = lane * 4 + n;
             uint32_t PA, PB;
             gather32(row + 32 * n, PA, PB, bacc);
-            uint32_t m = HPC ? ((PA ^ ((PA << 1) | pa)) | (PB ^ ((PB << 1) | pb))) : 0xFFFFFFFFu;
+            uint32_t m = HPC ? ((PA ^ fsl(qa, PA, 1)) | (PB ^ fsl(qb, PB, 1))) : 0xFFFFFFFFu;
             if (n == 0 && !prev_ok) m |= 1u;
-            m |= sm.ACC[idx];
-            sm.ACC[idx] = 0;
+            if (has_starts) { m |= sm.ACC[idx]; sm.ACC[idx] = 0; }
             if (vt < TILE) {           // last tile of the batch: nothing starts at or after byte vt
                 const int nv = vt - (lane * 128 + 32 * n);
                 m &= nv >= 32 ? 0xFFFFFFFFu : (nv > 0 ? low_mask((uint32_t)nv) : 0u);
             }
-            pa = PA >> 31; pb = PB >> 31;
-#if defined(MDBG_BS_PEXT_SKIP5)
+            qa = PA; qb = PB;
             if (HPC) {                 // the last round of the network only when some lane of the warp needs it
                 const PextState ps = pext_pair_rounds4(m, PA, PB);
                 if (bs_any(ps.mk != 0)) pext_pair_round5(ps, PA, PB);
             } else { PA &= m; PB &= m; }
-#else
-            if (HPC) pext_pair(m, PA, PB); else { PA &= m; PB &= m; }
-#endif
             sm.mraw[idx] = m;
             sm.u.t.ca[idx] = PA;
             sm.u.t.cb[idx] = PB;
             tot += popc32(m);
         }
-        tail = pa | (pb << 1);                       // code of this lane's last base
+        tail = (qa >> 31) | ((qb >> 31) << 1);       // code of this lane's last base
     }
     const bool tile_bad = bs_any(bad_of(bacc) != 0);
     const uint32_t tail31 = bs_shfl(tail, 31);
@@ -308,10 +308,9 @@ BS_DEV void process_tile(const KAArgs& A, WarpSmem& sm, const int lane, const ui
 #pragma unroll 1
         for (int n = 0; n < 4; n++) {
             const int idx = lane * 4 + n;
-            const uint32_t c = popc32(sm.mraw[idx]);
             sm.cpre[idx] = o;
-            if (c) { put_bits(sm.CA, o, sm.u.t.ca[idx]); put_bits(sm.CB, o, sm.u.t.cb[idx]); }
-            o += c;
+            put_bits2(sm.CA, sm.CB, o, sm.u.t.ca[idx], sm.u.t.cb[idx]);
+            o += popc32(sm.mraw[idx]);
         }
         if (lane == 31) sm.cpre[NW] = o;
     }
@@ -373,7 +372,6 @@ BS_DEV void process_tile(const KAArgs& A, WarpSmem& sm, const int lane, const ui
 
     // ---- P4: filter -------------------------------------------------------------------------
     if (!dirty) {
-#if defined(MDBG_BS_FILTER64)
         constexpr uint32_t STR = 65 - T;               // 64-position windows: the low half keeps all 32
         const uint32_t nwin = (Ctile + STR - 1) / STR;
         for (uint32_t idx = lane; idx < nwin; idx += 32) {
@@ -389,19 +387,6 @@ BS_DEV void process_tile(const KAArgs& A, WarpSmem& sm, const int lane, const ui
             push_candidates(sm, c_lo, s);
             push_candidates(sm, c_hi, s + 32u);
         }
-#else
-        constexpr uint32_t STR = 33 - T;
-        const uint32_t nwin = (Ctile + STR - 1) / STR;
-        for (uint32_t idx = lane; idx < nwin; idx += 32) {
-            const uint32_t s = idx * STR, w = s >> 5, sh = s & 31u;
-            const uint32_t x0 = sm.CA[w], x1 = sm.CA[w + 1], x2 = sm.CA[w + 2];
-            const uint32_t y0 = sm.CB[w], y1 = sm.CB[w + 1], y2 = sm.CB[w + 2];
-            uint32_t cand = filter_window<L, T>(fsr(x0, x1, sh), fsr(x1, x2, sh), fsr(y0, y1, sh), fsr(y1, y2, sh));
-            const uint32_t nv = Ctile - s;
-            cand &= low_mask(nv < STR ? nv : STR);
-            push_candidates(sm, cand, s);
-        }
-#endif
         bs_syncwarp();
         if (sm.qn > (uint32_t)QCAP) dirty = true;   // low-complexity sequence: exact path
     }

@@ -86,15 +86,33 @@ MDBG_HD uint32_t apply_tt(uint32_t tt, uint32_t acc, uint32_t a, uint32_t b) {
 }
 
 // ---- ASCII -> bit planes --------------------------------------------------------------------
-// Four bases per 32-bit word: the code bits sit at bit 1 (a) and bit 2 (b) of every byte.  One
-// multiply gathers the four bits of a plane into the top nibble (no carries: all partial products
-// land on distinct bits), a funnel shift appends the nibble.  Words are fed LAST FIRST so that the
-// first base ends up in bit 0.
-constexpr uint32_t GATHER_A = 0x08102040u;   // byte k bit 1 -> bit 28+k
-constexpr uint32_t GATHER_B = 0x04081020u;   // byte k bit 2 -> bit 28+k
-MDBG_HD void plane_push(uint32_t w, uint32_t& A, uint32_t& B) {
-    A = fsl((w & 0x02020202u) * GATHER_A, A, 4);
-    B = fsl((w & 0x04040404u) * GATHER_B, B, 4);
+// The code bits sit at bit 1 (a) and bit 2 (b) of every byte.  Eight bases per multiply: two words are
+// merged nibble-wise (bases 0..3 keep their low nibbles, bases 4..7 move theirs into the high nibbles:
+// one shift on the FMA pipe + one LOP3), so a plane's eight bits sit at bits 1 / 5 (2 / 6) of the four
+// bytes, and ONE multiply gathers them into the top byte in base order (all partial products land on
+// distinct bits: no carries).  Four such bytes are one plane word of 32 bases (three PRMT).
+constexpr uint32_t GATHER_A8 = 0x00810204u;  // bit 8j+1 -> 24+j, bit 8j+5 -> 28+j
+constexpr uint32_t GATHER_B8 = 0x00408102u;  // bit 8j+2 -> 24+j, bit 8j+6 -> 28+j
+MDBG_HD void plane_pair(uint32_t w0, uint32_t w1, uint32_t& pa, uint32_t& pb) {
+    const uint32_t n = (w0 & 0x0F0F0F0Fu) | ((w1 << 4) & 0xF0F0F0F0u);
+    pa = (n & 0x22222222u) * GATHER_A8;
+    pb = (n & 0x44444444u) * GATHER_B8;
+}
+// word whose byte i is the top byte of x_i
+MDBG_HD uint32_t top_bytes(uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3) {
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(__byte_perm(x0, x1, 0x0073), __byte_perm(x2, x3, 0x0073), 0x5410);
+#else
+    return (x0 >> 24) | ((x1 >> 24) << 8) | ((x2 >> 24) << 16) | (x3 & 0xFF000000u);
+#endif
+}
+// v >> n for n in [1, 32] (32 gives 0)
+MDBG_HD uint32_t shr_clamp(uint32_t v, uint32_t n) {
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_rc(v, 0u, n);
+#else
+    return n >= 32u ? 0u : (v >> n);
+#endif
 }
 
 // Alphabet check, word-parallel (same identities as ka_minimizers.cu): a byte is one of A C G T iff

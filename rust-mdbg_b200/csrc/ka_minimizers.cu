@@ -683,20 +683,21 @@ __global__ void __launch_bounds__(KA_THREADS, MDBG_KA_MIN_BLOCKS) ka_minimizers_
     }
 }
 
-// One warp per tile: move the tile's staged slice to its final, globally ordered position; then fix
-// up the per-read offsets (tile-relative rank -> global index).
+// Eight lanes per tile (a tile holds ~4096 * 2 * density minimizers: a dozen): move the tile's staged slice
+// to its final, globally ordered position; then fix up the per-read offsets (tile-relative rank -> global
+// index).
 __global__ void ka_finalize_kernel(const KAArgs A, const uint64_t* __restrict__ tile_excl) {
     const uint64_t gtid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    const uint64_t warp = gtid >> 5, lane = gtid & 31;
-    if (warp < A.n_tiles) {
-        const uint64_t cnt = A.tile_cnt[warp], src = A.tile_soff[warp], dst = A.out_base + tile_excl[warp];
-        for (uint64_t i = lane; i < cnt; i += 32) {
+    const uint64_t tile = gtid >> 3, sub = gtid & 7;
+    if (tile < A.n_tiles) {
+        const uint64_t cnt = A.tile_cnt[tile], src = A.tile_soff[tile], dst = A.out_base + tile_excl[tile];
+        for (uint64_t i = sub; i < cnt; i += 8) {
             if (src + i < A.stage_cap && dst + i < A.out_cap) {
                 A.out_hash[dst + i] = A.stage_hash[src + i];
                 A.out_pos[dst + i] = A.stage_pos[src + i];
             }
         }
-        if (warp + 1 == A.n_tiles && lane == 0) *A.total_out = A.out_base + tile_excl[warp] + cnt;
+        if (tile + 1 == A.n_tiles && sub == 0) *A.total_out = A.out_base + tile_excl[tile] + cnt;
     }
     if (gtid == 0 && A.dirty_out) *A.dirty_out = A.dirty_n ? *A.dirty_n : 0;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -735,7 +736,7 @@ cudaError_t ka_launch_list(const KAArgs& A, int hpc, int grid, cudaStream_t st, 
 }
 
 cudaError_t ka_finalize(const KAArgs& A, const uint64_t* tile_excl, cudaStream_t st, uint64_t* launches) {
-    uint64_t threads = A.n_tiles * 32;
+    uint64_t threads = A.n_tiles * 8;
     ka_finalize_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(A, tile_excl);
     if (launches) *launches += 1;
     return cudaGetLastError();

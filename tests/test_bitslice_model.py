@@ -15,11 +15,11 @@ ROOT = os.path.dirname(HERE)
 TILE = 4096
 
 
-@pytest.fixture(scope="module", params=["", "_opt"], ids=["default", "opt-variants"])
-def model(request):
-    """The kernel body as built by default, and with the opt-in variants of the Makefile (BS_OPT)."""
+@pytest.fixture(scope="module")
+def model():
+    """The kernel body compiled for the CPU (tests/model/)."""
     subprocess.check_call(["make", "-C", ROOT, "-s", "model"], stdout=subprocess.DEVNULL)
-    L = ctypes.CDLL(os.path.join(HERE, "model", "libka_bitslice_model%s.so" % request.param))
+    L = ctypes.CDLL(os.path.join(HERE, "model", "libka_bitslice_model.so"))
     vp, u64, u32 = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32
     L.bs_model_run.restype = ctypes.c_int
     L.bs_model_run.argtypes = [vp, vp, u64, u64, u32, u64, ctypes.c_int, u32, ctypes.c_int, u64, u64,
