@@ -238,10 +238,13 @@ def main():
     t0 = time.perf_counter()
     ka_ms, launches, stats = 0.0, 0, None
     stage = {"ka": 0.0, "kb": 0.0, "kc": 0.0, "kd": 0.0, "ke": 0.0}
+    kern_ms = [0.0] * 8
     for _ in range(steps):
         stats = step_device()
         tm = ctx.timings()
         ka_ms += tm["ms_ka_kernel"]
+        for i_, v_ in enumerate(tm["ms_kernels"]):
+            kern_ms[i_] += v_
         launches += tm["launches_push"] + tm["launches_finish"]
         for s_ in stage:
             stage[s_] += tm["ms_" + s_]
@@ -285,6 +288,21 @@ def main():
                 "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": ka_avg_ms,
                 "share_of_step": ka_avg_ms / (dev_ms / steps)}
+
+    # the other kernels of the step against the same HBM roofline (algorithmic bytes per SURVEY 8d; times from CUDA
+    # events around each kernel inside the library): they move few bytes per item, latency- not bandwidth-bound
+    Kc, Dc, Sc, kk_ = stats["n_kminmers"] / max(1, world), stats["n_distinct"] / max(1, world), stats["n_nodes"], wl["k"]
+    kernel_bytes = [("kb_records_kernel", Kc * (8 + 48)), ("kc_insert_kernel", Kc * (64 + 8 + 4)),
+                    ("kc_verify_kernel", Kc * 8 + max(0.0, Kc - Dc) * 2 * kk_ * 8), ("cub radix sort by slot (3 passes)", Kc * 8 * 2 * 3),
+                    ("ke_join_kernel<0>", Sc / max(1, world) * (2 * (kk_ - 1) * 8 * 2 + 26)), ("ka_finalize_kernel", M * 24 * 2),
+                    ("kd_nodes_kernel + kd_expand_kernel", Sc * (20 * 2 + kk_ * 8 * 2 + 14))]
+    kernel_rooflines = []
+    for i_, (name_, by_) in enumerate(kernel_bytes):
+        ms_ = kern_ms[i_] / steps
+        if ms_ > 0:
+            kernel_rooflines.append({"kernel": name_, "avg_ms": ms_, "algorithmic_bytes": int(by_),
+                                     "achieved_gbs": by_ / (ms_ * 1e-3) / 1e9, "frac": by_ / (ms_ * 1e-3) / 1e9 / peak,
+                                     "share_of_step": ms_ / (dev_ms / steps)})
 
     # ------------------------------------------------------------------ multi-k sweep (config 5)
     multik = None
@@ -452,7 +470,7 @@ def main():
                "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": config,
                "timing": "CUDA events on the launching stream around K steps, max over ranks",
                "wall_ms_per_step": wall_ms / steps, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-               "roofline": roofline, "cpu_baseline": cpu,
+               "roofline": roofline, "kernel_rooflines": kernel_rooflines, "cpu_baseline": cpu,
                "stage_ms_per_step": {k_: v_ / steps for k_, v_ in stage.items()},
                "counts": {k_: int(v_) for k_, v_ in stats.items()}}
         if multik is not None:

@@ -181,6 +181,9 @@ typedef struct {
     uint64_t upload_h2d_bytes;                 /* bytes of bases that crossed PCIe in the last mdbg_push_reads */
     float ms_exchange;                         /* N > 1: the record all-to-all of the last finish (inside ms_kb..ms_kc) */
     uint64_t exchange_bytes;                   /* N > 1: bytes this GPU sent over NVLink in the last finish           */
+    float ms_kernels[8];                       /* single kernels of the last push / finish (CUDA events around each):
+                                                  0 kb_records, 1 kc_insert, 2 kc_verify, 3 radix sort by slot,
+                                                  4 ke_join, 5 ka_finalize, 6 kd_nodes + kd_expand, 7 reserved          */
 } mdbg_timings;
 int mdbg_get_timings(mdbg_ctx* ctx, mdbg_timings* out);
 void* mdbg_stream(mdbg_ctx* ctx);              /* the cudaStream_t all kernels run on        */

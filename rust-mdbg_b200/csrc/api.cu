@@ -52,6 +52,21 @@ __global__ void widen_pos_kernel(const uint32_t* __restrict__ in, uint64_t* __re
     uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (i < n) out[i] = in[i];
 }
+// read_off of a device-resident batch: non-decreasing, ends at n_bases, no record of 4 Gbases or more
+// (positions inside a read are u32 on the device); flag bit 0 = order, bit 1 = a record too long
+__global__ void check_read_off_kernel(const uint64_t* __restrict__ off, uint64_t n_reads, uint64_t n_bases,
+                                      unsigned long long* flags) {
+    uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (r > n_reads) return;
+    unsigned long long f = 0;
+    if (r == n_reads) { if (off[r] != n_bases) f |= 1; }
+    else {
+        if (off[r + 1] < off[r]) f |= 1;
+        else if (off[r + 1] - off[r] >= 0xFFFFFFF0ull) f |= 2;
+    }
+    if (r == 0 && off[0] != 0) f |= 1;
+    if (f) atomicOr(flags, f);
+}
 __global__ void flush_kernel(uint4* p, uint64_t n, uint32_t v) {
     uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -101,6 +116,7 @@ int mdbg_ctx_create(const mdbg_params* p, mdbg_ctx** out) {
     if (e == cudaSuccess) e = cudaMalloc(&c->d_mail, MAIL_WORDS * sizeof(uint64_t));
     if (e == cudaSuccess) e = cudaMallocHost(&c->h_mail, MAIL_WORDS * sizeof(uint64_t));
     for (int i = 0; i < 24 && e == cudaSuccess; i++) e = cudaEventCreate(&c->ev[i]);
+    for (int i = 0; i < 16 && e == cudaSuccess; i++) e = cudaEventCreate(&c->evk[i]);
     if (e != cudaSuccess) {
         g_create_err = std::string("CUDA init failed: ") + cudaGetErrorString(e);
         delete c;
@@ -164,6 +180,7 @@ void mdbg_ctx_destroy(mdbg_ctx* c) {
     if (c->h_mail) cudaFreeHost(c->h_mail);
     mdbg_comm_release(c);
     for (int i = 0; i < 24; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (int i = 0; i < 16; i++) if (c->evk[i]) cudaEventDestroy(c->evk[i]);
     c->pool.trim();
     for (auto ev : c->copy_ev) cudaEventDestroy(ev);
     for (auto& pb : c->pinned_cache) cudaFreeHost(pb.second);
@@ -326,6 +343,7 @@ static int run_ka(mdbg_ctx* c, const uint8_t* d_bases, const uint64_t* d_read_of
         MDBG_CK(c, cudaEventRecord(c->ev[16], c->st));
         MDBG_CK(c, cub::DeviceScan::ExclusiveSum(scan_tmp.p, scan_bytes, tile_cnt.p, tile_excl.p, n_tiles, c->st));
         c->tm.launches_push += 2;
+        MDBG_CK(c, cudaEventRecord(c->evk[10], c->st));
         MDBG_CK(c, ka_finalize(A, tile_excl, c->st, &c->tm.launches_push));
         MDBG_CK(c, cudaEventRecord(c->ev[1], c->st));
         MDBG_CK(c, cudaMemcpyAsync(c->h_sc, c->d_sc, sizeof(Scalars), cudaMemcpyDeviceToHost, c->st));
@@ -334,6 +352,7 @@ static int run_ka(mdbg_ctx* c, const uint8_t* d_bases, const uint64_t* d_read_of
         cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
         c->tm.ms_ka = ms;
         cudaEventElapsedTime(&c->tm.ms_ka_kernel, c->ev[0], c->ev[16]);
+        cudaEventElapsedTime(&c->tm.ms_kernels[5], c->evk[10], c->ev[1]);
         c->tm.ka_ms_sum += ms;
         c->tm.ka_launches += 1;
         c->tm.ka_dense_tiles = c->h_sc->dense_tiles;
@@ -374,11 +393,20 @@ extern "C" {
 
 int mdbg_push_reads_device(mdbg_ctx* c, const uint8_t* d_bases, const uint64_t* d_read_off,
                            uint64_t n_reads, uint64_t n_bases) {
-    if (!c) return MDBG_ERR_BAD_ARG;
+    if (!c || !d_read_off || (n_bases && !d_bases)) { if (c) c->err = "null argument"; return MDBG_ERR_BAD_ARG; }
     MDBG_CK(c, cudaSetDevice(c->device));
     c->tm.launches_push = 0;
     c->tm.ms_h2d = 0;
     MDBG_CK(c, cudaEventRecord(c->ev[2], c->st));
+    {   // the checks mdbg_push_reads makes on the host, on the device (the flag comes back with K-A's own scalars)
+        MDBG_CK(c, cudaMemsetAsync(&c->d_sc->v[10], 0, 8, c->st));
+        check_read_off_kernel<<<(unsigned)((n_reads + 1 + 255) / 256), 256, 0, c->st>>>(d_read_off, n_reads, n_bases, &c->d_sc->v[10]);
+        MDBG_CK(c, cudaGetLastError());
+        MDBG_CK(c, cudaMemcpyAsync(&c->h_sc->v[10], &c->d_sc->v[10], 8, cudaMemcpyDeviceToHost, c->st));
+        MDBG_CK(c, cudaStreamSynchronize(c->st));
+        if (c->h_sc->v[10] & 1) { c->err = "read_off is not a non-decreasing offset array ending at n_bases"; return MDBG_ERR_BAD_ARG; }
+        if (c->h_sc->v[10] & 2) { c->err = "a single record of 4 Gbases or more is not supported"; return MDBG_ERR_RANGE; }
+    }
     int rc = run_ka(c, d_bases, d_read_off, n_reads, n_bases);
     if (rc) return rc;
     MDBG_CK(c, cudaEventRecord(c->ev[3], c->st));

@@ -1,6 +1,7 @@
 // comm.cu -- NCCL plumbing for the multi-GPU path (one process per GPU).  The unique id is
 // created on rank 0 by mdbg_nccl_unique_id and shipped by the host (torch.distributed
 // broadcast in bench.py / tests); the exchange itself is in graph.cu (build_device_graph).
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -13,6 +14,8 @@ using namespace mdbg;
 extern "C" void mdbg_comm_release(mdbg_ctx* c) {
     if (c && c->comm) {
         NcclApi& N = nccl();
+        if (N.ok && c->comm2) N.CommDestroy((ncclComm_t)c->comm2);
+        c->comm2 = nullptr;
         if (N.ok) N.CommDestroy((ncclComm_t)c->comm);
         c->comm = nullptr;
         c->rank = 0;
@@ -49,6 +52,14 @@ int mdbg_comm_init(mdbg_ctx* c, const uint8_t id[MDBG_NCCL_ID_BYTES], int rank, 
     }
     mdbg_comm_release(c);   // a second init replaces the first communicator
     c->comm = (void*)comm;
+    // second communicator over the same ranks: lets the arena all-gather overlap the record exchange (operations
+    // of ONE communicator run in issue order).  Opt-in (MDBG_COMM2=1): without it everything runs on `comm`, in order.
+    c->comm2 = nullptr;
+    const char* want2 = getenv("MDBG_COMM2");
+    if (N.CommSplit && world > 1 && want2 && want2[0] == '1') {
+        ncclComm_t c2 = nullptr;
+        if (N.CommSplit(comm, 0, rank, &c2, nullptr) == ncclSuccess) c->comm2 = (void*)c2;
+    }
     c->rank = rank;
     c->world = world;
     return MDBG_OK;

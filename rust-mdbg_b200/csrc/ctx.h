@@ -100,9 +100,11 @@ struct mdbg_ctx {
     uint64_t* h_mail = nullptr;      // ... and their pinned host mirror
     void* l2_flush = nullptr; size_t l2_flush_bytes = 0;
     cudaEvent_t ev[24]{};
+    cudaEvent_t evk[16]{};   // begin/end pairs around single kernels (mdbg_timings.ms_kernels)
     mdbg_timings tm{};
     // NCCL (multi-GPU)
     void* comm = nullptr; int rank = 0, world = 1;
+    void* comm2 = nullptr;   // a copy of the communicator for the arena all-gather, which runs on st_copy under K-B / K-C
     uint64_t read_base = 0; bool read_base_set = false;   // global index of this rank's first read
     // device-resident result of the last finish (kept until the next finish/reset)
     struct DeviceGraph* dg = nullptr;

@@ -252,10 +252,22 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
     // sighting needs from them travels inside its record)
     Tmp<uint64_t> g_hash;
     const uint64_t* arena = c->m_hash;
+    bool arena_pending = false;   // the all-gather runs on the copy stream (own communicator) under K-B / the exchange
+    struct PendingGuard {         // an error return must not release g_hash while the copy stream still fills it
+        bool& pending; cudaStream_t s;
+        ~PendingGuard() { if (pending) cudaStreamSynchronize(s); }
+    } pending_guard{arena_pending, c->st_copy};
     if (W > 1) {
         MDBG_CK(c, g_hash.get(c->pool, Mpitch * (uint64_t)W));
-        if (c->M) MDBG_CK(c, cudaMemcpyAsync(g_hash.p + Mpitch * rank, c->m_hash, c->M * 8, cudaMemcpyDeviceToDevice, st));
-        if (Mpitch) NCK(c, nccl().AllGather(g_hash.p + Mpitch * rank, g_hash.p, Mpitch, ncclUint64, (ncclComm_t)c->comm, st));
+        cudaStream_t sa = c->comm2 ? c->st_copy : st;
+        ncclComm_t ca = (ncclComm_t)(c->comm2 ? c->comm2 : c->comm);
+        if (c->comm2) {
+            MDBG_CK(c, cudaEventRecord(c->ev[19], st));
+            MDBG_CK(c, cudaStreamWaitEvent(sa, c->ev[19], 0));
+        }
+        if (c->M) MDBG_CK(c, cudaMemcpyAsync(g_hash.p + Mpitch * rank, c->m_hash, c->M * 8, cudaMemcpyDeviceToDevice, sa));
+        if (Mpitch) NCK(c, nccl().AllGather(g_hash.p + Mpitch * rank, g_hash.p, Mpitch, ncclUint64, ca, sa));
+        if (c->comm2) { MDBG_CK(c, cudaEventRecord(c->ev[20], sa)); arena_pending = true; }
         arena = g_hash.p;
         c->tm.exchange_bytes += Mpitch * 8 * (uint64_t)(W - 1);
     }
@@ -274,12 +286,14 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
     const uint64_t table_seed0 = 0x7461626c65000000ull;
     uint64_t fp_mask0 = ~0ull;
     if (c->p.debug_fp_bits > 0 && c->p.debug_fp_bits < 64) fp_mask0 = (1ull << c->p.debug_fp_bits) - 1;
+    MDBG_CK(c, cudaEventRecord(c->evk[0], st));
     if (K_local) {
         kb_records_kernel<<<nblk(K_local), 256, 0, st>>>(A, kmer_off, K_local, k, table_seed0, fp_mask0, rbase, kbase,
                                                          W > 1 ? Mpitch * rank : 0, (uint32_t)W, l_wloc, l_ord, l_info, l_fp,
                                                          W > 1 ? nullptr : iota.p, W > 1 ? l_owner.p : nullptr);
         LAUNCHED(c);
     }
+    MDBG_CK(c, cudaEventRecord(c->evk[1], st));
     cnt.reset(); kmer_off.reset();
     MDBG_CK(c, cudaEventRecord(c->ev[6], st));
 
@@ -361,15 +375,21 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
             MDBG_CK(c, cudaMemsetAsync(keys, 0xFF, cap * 8, st));
             MDBG_CK(c, cudaMemsetAsync(first, 0xFF, cap * 4, st));
             MDBG_CK(c, cudaMemsetAsync(&c->d_sc->v[1], 0, 8, st));
+            MDBG_CK(c, cudaEventRecord(c->evk[2], st));
             kc_insert_kernel<<<nblk(K * 4), 256, 0, st>>>(fp, K, keys, first, cap - 1, slot);
             LAUNCHED(c);
+            MDBG_CK(c, cudaEventRecord(c->evk[3], st));
+            if (arena_pending) { MDBG_CK(c, cudaStreamWaitEvent(st, c->ev[20], 0)); arena_pending = false; }   // tuples from here on
+            MDBG_CK(c, cudaEventRecord(c->evk[4], st));
             kc_verify_kernel<<<nblk(K), 256, 0, st>>>(T, K, slot, first, &c->d_sc->v[1]);
             LAUNCHED(c);
+            MDBG_CK(c, cudaEventRecord(c->evk[5], st));
             // K-D: stable sort by slot, segment heads (speculatively: the collision flag is read
             // together with the segment count, one host round trip for both)
             RC(R.cub([&](void* t, size_t& b) {
                 return cub::DeviceRadixSort::SortPairs(t, b, slot.p, sslot.p, iota.p, sj.p, (uint32_t)K, 0, cap_bits, st);
             }));
+            MDBG_CK(c, cudaEventRecord(c->evk[6], st));
             kd_heads_kernel<<<nblk(K), 256, 0, st>>>(sslot, K, head);
             LAUNCHED(c);
             RC(R.cub([&](void* t, size_t& b) {
@@ -381,6 +401,7 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
         }
         D = (uint32_t)(c->h_sc->v[2] & 0xFFFFFFFFu);
     }
+    if (arena_pending) { MDBG_CK(c, cudaStreamWaitEvent(st, c->ev[20], 0)); arena_pending = false; }
     MDBG_CK(c, cudaEventRecord(c->ev[7], st));   // ms_kc = table + sort by slot, ms_kd = reduce + nodes
     slot.reset(); first.reset(); iota.reset(); sslot.reset();
     MDBG_CK(c, first_ord.get(c->pool, D)); MDBG_CK(c, solid.get(c->pool, D)); MDBG_CK(c, nseq.get(c->pool, (uint64_t)D + 1));
@@ -443,6 +464,7 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
         MDBG_CK(c, G->seqlen.get(c->pool, Stot)); MDBG_CK(c, G->shift.get(c->pool, 2 * Stot));
         MDBG_CK(c, G->tuple.get(c->pool, Stot * k));
         if (W > 1 && Stot > 0) MDBG_CK(c, cudaMemsetAsync(nrec.p, 0, Stot * sizeof(NodeRec), st));
+        MDBG_CK(c, cudaEventRecord(c->evk[12], st));
         if (D > 0) {
             kd_nodes_kernel<<<nblk(D), 256, 0, st>>>(D, minab, K, seg_start, sj, first_ord, counted, solid, ord_bits_map, wscan,
                                                      r_wloc, r_ord, r_info, seg_index, nrec);
@@ -457,6 +479,7 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
             kd_expand_kernel<<<nblk(Stot * k), 256, 0, st>>>(nrec, Stot, k, arena, NO);
             LAUNCHED(c);
         }
+        MDBG_CK(c, cudaEventRecord(c->evk[13], st));
         first_ord.reset(); solid.reset();
     }
     // .sequences lines of this owner, in ordinal (= emission) order
@@ -520,9 +543,11 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
         uint32_t EP = 0, NR = 0;
         bool overflow = false;
         if (q_n > 0) {
+            MDBG_CK(c, cudaEventRecord(c->evk[8], st));
             ke_join_kernel<0><<<nblk((uint64_t)q_n * KE_LANES, 128), 128, 0, st>>>(NV, ekey, erev, skey, sval, inv, presimp, q_lo, q_n, cnt_q, nullptr,
                                                               cap_e, cap_r, &c->d_sc->v[6]);
             LAUNCHED(c);
+            MDBG_CK(c, cudaEventRecord(c->evk[9], st));
             RC(R.cub([&](void* t, size_t& b) { return cub::DeviceScan::ExclusiveSum(t, b, cnt_q.p, off_q.p, q_n + 1, st); }));
             MDBG_CK(c, cudaMemcpyAsync(&c->d_sc->v[5], off_q.p + q_n, 8, cudaMemcpyDeviceToDevice, st));
             RC(read_scalars(c));
@@ -611,6 +636,13 @@ int finish_timings(mdbg_ctx* c) {
     cudaEventElapsedTime(&c->tm.ms_ke, c->ev[8], c->ev[9]);
     cudaEventElapsedTime(&c->tm.ms_total_finish, c->ev[5], c->ev[9]);
     if (c->world > 1) cudaEventElapsedTime(&c->tm.ms_exchange, c->ev[10], c->ev[11]);
+    // single kernels (an event pair that was not recorded in this finish leaves 0)
+    static const int pairs[][3] = {{0, 0, 1}, {1, 2, 3}, {2, 4, 5}, {3, 5, 6}, {4, 8, 9}, {6, 12, 13}};
+    for (auto& p : pairs) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, c->evk[p[1]], c->evk[p[2]]) != cudaSuccess) { cudaGetLastError(); ms = 0; }
+        c->tm.ms_kernels[p[0]] = ms > 0 ? ms : 0;
+    }
     return MDBG_OK;
 }
 
@@ -787,6 +819,12 @@ int mdbg_window(mdbg_ctx* c, const uint64_t* hash, const uint64_t* pos, const ui
     cudaStream_t st = c->st;
     const uint32_t k = c->p.k, l = c->p.l;
     const uint64_t M = min_read_off[n_reads];
+    if (M > 0 && (!hash || !pos)) { c->err = "null hash / pos with minimizers present"; return MDBG_ERR_BAD_ARG; }
+    if (M >= 0xFFFFFFF0ull) { c->err = "more than 2^32 minimizers in one mdbg_window call"; return MDBG_ERR_RANGE; }
+    for (uint64_t r = 0; r < n_reads; r++)
+        if (min_read_off[r + 1] < min_read_off[r]) { c->err = "min_read_off is not non-decreasing"; return MDBG_ERR_BAD_ARG; }
+    for (uint64_t i = 0; i < M; i++)
+        if (pos[i] > 0xFFFFFFFFull) { c->err = "a minimizer position of 4 G or more (positions inside a read are u32)"; return MDBG_ERR_RANGE; }
     Runner R{c};
     Tmp<uint64_t> d_hash, d_off, cnt, kmer_off;
     Tmp<uint32_t> d_pos;

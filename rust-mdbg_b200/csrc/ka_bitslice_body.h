@@ -147,20 +147,25 @@ BS_DEV void gather32(const uint8_t* p, uint32_t& A, uint32_t& B, BadAcc& acc) {
     bad_accumulate(acc, v1.x); bad_accumulate(acc, v1.y); bad_accumulate(acc, v1.z); bad_accumulate(acc, v1.w);
 }
 
-// Queue the set bits of `cand` (HPC positions s + k): one shared-memory atomic per lane and call (the lane
-// reserves all its slots at once).
-BS_DEV void push_candidates(WarpSmem& sm, uint32_t cand, const uint32_t s) {
-    if (!cand) return;
-    uint32_t qi = bs_atomic_add_s(&sm.qn, popc32(cand));
-    while (cand) {
+// Queue the set bits of a 64-position candidate set (HPC positions s + k): ONE shared-memory atomic per lane
+// and window (the lane reserves all its slots at once).
+BS_DEV void push_candidates(WarpSmem& sm, uint32_t c_lo, uint32_t c_hi, const uint32_t s) {
+    if (!(c_lo | c_hi)) return;
+    uint32_t qi = bs_atomic_add_s(&sm.qn, popc32(c_lo) + popc32(c_hi));
+    uint32_t base = s;
+    for (int half = 0; half < 2; half++) {
+        uint32_t cand = half ? c_hi : c_lo;
+        while (cand) {
 #if defined(__CUDA_ARCH__)
-        const uint32_t k = (uint32_t)__ffs((int)cand) - 1u;
+            const uint32_t k = (uint32_t)__ffs((int)cand) - 1u;
 #else
-        const uint32_t k = (uint32_t)__builtin_ctz(cand);
+            const uint32_t k = (uint32_t)__builtin_ctz(cand);
 #endif
-        cand &= cand - 1u;
-        if (qi < (uint32_t)QCAP) sm.u.q.queue[qi] = s + k;
-        qi++;
+            cand &= cand - 1u;
+            if (qi < (uint32_t)QCAP) sm.u.q.queue[qi] = base + k;
+            qi++;
+        }
+        base += 32u;
     }
 }
 
@@ -384,8 +389,7 @@ BS_DEV void process_tile(const KAArgs& A, WarpSmem& sm, const int lane, const ui
             const uint32_t nv = Ctile - s;
             c_lo &= low_mask(nv);
             c_hi &= low_mask(nv > 32u ? (nv - 32u < STR - 32u ? nv - 32u : STR - 32u) : 0u);
-            push_candidates(sm, c_lo, s);
-            push_candidates(sm, c_hi, s + 32u);
+            push_candidates(sm, c_lo, c_hi, s);
         }
         bs_syncwarp();
         if (sm.qn > (uint32_t)QCAP) dirty = true;   // low-complexity sequence: exact path

@@ -13,6 +13,7 @@ struct NcclApi {
     ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t*, void*) = nullptr;   // optional (NCCL >= 2.18)
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
@@ -33,6 +34,7 @@ inline NcclApi& nccl() {
     MDBG_NCCL_SYM(GetUniqueId, "ncclGetUniqueId");
     MDBG_NCCL_SYM(CommInitRank, "ncclCommInitRank");
     MDBG_NCCL_SYM(CommDestroy, "ncclCommDestroy");
+    MDBG_NCCL_SYM(CommSplit, "ncclCommSplit");
     MDBG_NCCL_SYM(GetErrorString, "ncclGetErrorString");
     MDBG_NCCL_SYM(GroupStart, "ncclGroupStart");
     MDBG_NCCL_SYM(GroupEnd, "ncclGroupEnd");

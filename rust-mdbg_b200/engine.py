@@ -213,7 +213,7 @@ class Context:
     def timings(self):
         t = CTimings()
         self._ck(self.L.mdbg_get_timings(self.h, ctypes.byref(t)))
-        return {n: getattr(t, n) for n, _ in CTimings._fields_}
+        return {n: (list(getattr(t, n)) if n == "ms_kernels" else getattr(t, n)) for n, _ in CTimings._fields_}
 
     # ---- memory / sync ------------------------------------------------------------------------
     def device_malloc(self, nbytes):

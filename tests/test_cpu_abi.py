@@ -176,6 +176,57 @@ def _lz4_stored_frame_decode(raw):
     return bytes(out)
 
 
+def _liblz4_frame_decode(raw):
+    """LZ4 frame -> bytes with the SYSTEM liblz4 (LZ4F_decompress), not this repository's reader."""
+    lz4 = ctypes.CDLL("liblz4.so.1")
+    lz4.LZ4F_createDecompressionContext.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_uint]
+    lz4.LZ4F_createDecompressionContext.restype = ctypes.c_size_t
+    lz4.LZ4F_decompress.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_size_t), ctypes.c_void_p,
+                                    ctypes.POINTER(ctypes.c_size_t), ctypes.c_void_p]
+    lz4.LZ4F_decompress.restype = ctypes.c_size_t
+    lz4.LZ4F_isError.argtypes = [ctypes.c_size_t]
+    lz4.LZ4F_freeDecompressionContext.argtypes = [ctypes.c_void_p]
+    ctx = ctypes.c_void_p()
+    assert not lz4.LZ4F_isError(lz4.LZ4F_createDecompressionContext(ctypes.byref(ctx), 100))
+    src = ctypes.create_string_buffer(raw, len(raw))
+    dst = ctypes.create_string_buffer(1 << 20)
+    out, pos = bytearray(), 0
+    while pos < len(raw):
+        dn, sn = ctypes.c_size_t(len(dst)), ctypes.c_size_t(len(raw) - pos)
+        rc = lz4.LZ4F_decompress(ctx, dst, ctypes.byref(dn), ctypes.byref(src, pos), ctypes.byref(sn), None)
+        assert not lz4.LZ4F_isError(rc), "liblz4 rejects the frame"
+        out += dst.raw[:dn.value]
+        pos += sn.value
+        if rc == 0 and sn.value == 0 and dn.value == 0:
+            break
+    assert rc == 0, "frame not complete"
+    lz4.LZ4F_freeDecompressionContext(ctx)
+    return bytes(out)
+
+
+def _parse_sequences_like_reference(data):
+    """Line grammar as utils/parse_sequences_file.py:21-34 of the reference reads it."""
+    k = l = 0
+    node_minims, kmer_to_seq, minim_shift = {}, {}, {}
+    for line in data.decode().splitlines():
+        if line.startswith("#"):
+            if line.startswith("# k = "):
+                k = int(line.split()[-1])
+            if line.startswith("# l = "):
+                l = int(line.split()[-1])
+            continue
+        spl = line.split()
+        seq_id = spl[0]
+        minims = tuple(map(lambda x: int(x.strip("[").strip("]").replace(",", "")), spl[1:-5]))
+        assert spl[-4] == "*" and spl[-3] == "*"
+        seq = spl[-5]
+        shifts = tuple(map(lambda x: int(x.strip("(").strip(")").replace(",", "")), spl[-2:]))
+        node_minims[seq_id] = minims
+        kmer_to_seq[minims] = seq
+        minim_shift[seq_id] = shifts
+    return k, l, node_minims, kmer_to_seq, minim_shift
+
+
 def test_file_writers_on_host(mdbg, oracle, example_reads, tmp_path):
     """mdbg_write_gfa / mdbg_write_sequences are host code: feed them a graph (the oracle's, through
     the C struct) and compare with the oracle's own canonical text -- .gfa S/L grammar
@@ -215,6 +266,34 @@ def test_file_writers_on_host(mdbg, oracle, example_reads, tmp_path):
     body = sorted(x for x in plain.splitlines(True) if not x.startswith("#"))
     assert body == sorted(open(oseq).read().splitlines(True))
     assert _lz4_stored_frame_decode(open(seqz, "rb").read()).decode() == plain
+    # an independent consumer: the system's liblz4 (what lzzzz / python-lz4 wrap: to_basespace.rs:233,
+    # utils/parse_sequences_file.py:12) decodes the frame, then the reference's parser logic reads the lines
+    assert _liblz4_frame_decode(open(seqz, "rb").read()).decode() == plain
+    k, l, node_minims, kmer_to_seq, minim_shift = _parse_sequences_like_reference(_liblz4_frame_decode(open(seqz, "rb").read()))
+    assert (k, l) == (7, 10) and len(node_minims) == len(o.q_index)
+    for i in range(len(o.index)):
+        name = str(int(o.index[i]))
+        assert node_minims[name] == tuple(int(x) for x in o.tuple[i])
+    for q in range(len(o.q_index)):
+        name = str(int(o.q_index[q]))
+        raw = bytes(bases[int(off[int(o.q_read[q])]) + int(o.q_start[q]):int(off[int(o.q_read[q])]) + int(o.q_end[q])])
+        if o.q_rev[q]:
+            raw = raw[::-1].translate(bytes.maketrans(b"ACGT", b"TGCA"))
+        assert kmer_to_seq[node_minims[name]] == raw.decode()
+        assert minim_shift[name] == (int(o.q_shift[q][0]), int(o.q_shift[q][1]))
+    # the streaming writer (what the front end uses in its second pass over the input) gives the same file
+    W = F.vp()
+    seqs = str(tmp_path / "p.stream.sequences")
+    assert L.mdbg_seq_writer_open(ctypes.byref(cg), seqs.encode(), 1, ctypes.byref(W)) == 0
+    n_calls = 0
+    while True:
+        r = L.mdbg_seq_writer_next_read(W)
+        if r == 0xFFFFFFFFFFFFFFFF:
+            break
+        assert L.mdbg_seq_writer_read(W, r, bases.ctypes.data + int(off[r]), int(off[r + 1] - off[r])) == 0
+        n_calls += 1
+    assert L.mdbg_seq_writer_close(W) == 0 and n_calls > 0
+    assert open(seqs, "rb").read() == open(seqz, "rb").read()
 
 
 def test_bench_reference_arm_line():
