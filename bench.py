@@ -245,8 +245,10 @@ def main():
         ka_ms += tm["ms_ka_kernel"]
         for i_, v_ in enumerate(tm["ms_kernels"]):
             kern_ms[i_] += v_
+        stage["exchange"] = stage.get("exchange", 0.0) + tm["ms_exchange"]
+        stage["finish_total"] = stage.get("finish_total", 0.0) + tm["ms_total_finish"]
         launches += tm["launches_push"] + tm["launches_finish"]
-        for s_ in stage:
+        for s_ in ("ka", "kb", "kc", "kd", "ke"):
             stage[s_] += tm["ms_" + s_]
     ctx.sync()
     dev_ms = ctx.timer_stop()
@@ -472,6 +474,7 @@ def main():
                "wall_ms_per_step": wall_ms / steps, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                "roofline": roofline, "kernel_rooflines": kernel_rooflines, "cpu_baseline": cpu,
                "stage_ms_per_step": {k_: v_ / steps for k_, v_ in stage.items()},
+               "nvlink_bytes_sent_per_gpu_per_step": int(tm.get("exchange_bytes", 0)),
                "counts": {k_: int(v_) for k_, v_ in stats.items()}}
         if multik is not None:
             out["multik"] = multik

@@ -507,24 +507,37 @@ int mdbg_push_reads(mdbg_ctx* c, const uint8_t* bases, const uint64_t* read_off,
             if (cudaPointerGetAttributes(&pa, bases) != cudaSuccess) (void)cudaGetLastError();
             else if (pa.type == cudaMemoryTypeUnregistered) ascii_rate = std::min(link_rate, 12e9);
         }
-        double busy_until = 0, pack_s_per_byte = 1.0 / 40e9;
+        // The engine's backlog is OBSERVED, not modelled: bytes enqueued minus bytes of the chunks whose copy event
+        // has completed, divided by the rate the completed chunks have actually moved at (several ranks share the
+        // host's memory system and PCIe switches: the link gives half its nominal rate with 8 uploading ranks).
+        double pack_s_per_byte = 1.0 / 40e9, t_first = -1.0;
+        uint64_t cum_enq = 0, cum_done = 0;
+        size_t done_ptr = 0;
+        std::vector<uint64_t> enq(n_chunks, 0);
         auto now_s = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-        prepare = [&, n_words, CHW, hybrid, link_rate, ascii_rate, busy_until, pack_s_per_byte, now_s](size_t ci) mutable -> int {
+        prepare = [&, n_words, CHW, hybrid, link_rate, ascii_rate, pack_s_per_byte, t_first, cum_enq, cum_done, done_ptr, enq,
+                   now_s](size_t ci) mutable -> int {
             const uint64_t wa = (uint64_t)ci * CHW, wb = std::min(n_words, wa + CHW);
             // this chunk's slot of the staging ring, addressed as if the ring were the whole batch
             uint32_t* hp = reinterpret_cast<uint32_t*>(reinterpret_cast<uintptr_t>(c->h_planes) +
                                                        8 * ((ci % UPLOAD_SLOTS) * CHW) - 8 * wa);
             const uint64_t chunk_bytes = std::min<uint64_t>(B, wb * 32) - wa * 32;
             const double t_dec = now_s();
-            const double backlog = std::max(0.0, busy_until - t_dec);
+            while (done_ptr < ci && cudaEventQuery(c->copy_ev[done_ptr]) == cudaSuccess) cum_done += enq[done_ptr++];
+            (void)cudaGetLastError();   // cudaErrorNotReady is not an error
+            double rate = std::min(link_rate, ascii_rate);
+            if (t_first >= 0 && cum_done >= (32u << 20) && t_dec > t_first)
+                rate = std::min(rate, std::max(2e9, (double)cum_done / (t_dec - t_first)));
+            const double backlog = (double)(cum_enq - cum_done) / rate;
+            if (t_first < 0) t_first = t_dec;
             if (hybrid && backlog < pack_s_per_byte * (double)chunk_bytes) {   // the engine would run dry while we pack
-                busy_until = std::max(t_dec, busy_until) + (double)chunk_bytes / ascii_rate;
                 const uint64_t off = wa * 32, end = std::min<uint64_t>(B, wb * 32);
                 MDBG_CK(c, cudaMemcpyAsync(d_bases.p + off, bases + off, end - off, cudaMemcpyHostToDevice, c->st_copy));
                 MDBG_CK(c, cudaEventRecord(c->copy_ev[ci], c->st_copy));
                 if (wb == n_words) MDBG_CK(c, cudaEventRecord(c->ev[4], c->st_copy));
                 c->tm.upload_ascii_tiles += (uint32_t)((wb - wa + PACK_TILE_WORDS - 1) / PACK_TILE_WORDS);
                 c->tm.upload_h2d_bytes += end - off;
+                enq[ci] = end - off; cum_enq += end - off;
                 return MDBG_OK;        // run_ka makes the compute stream wait for copy_ev[ci]
             }
             if (ci >= UPLOAD_SLOTS) MDBG_CK(c, cudaEventSynchronize(c->copy_ev[ci - UPLOAD_SLOTS]));   // slot free again
@@ -532,9 +545,9 @@ int mdbg_push_reads(mdbg_ctx* c, const uint8_t* bases, const uint64_t* read_off,
             {
                 const double t_end = now_s(), per_byte = (t_end - t_dec) / (double)std::max<uint64_t>(1, chunk_bytes);
                 pack_s_per_byte = 0.5 * pack_s_per_byte + 0.5 * per_byte;
-                busy_until = std::max(t_end, busy_until) + (double)(wb - wa) * 8 / link_rate;
             }
             c->tm.upload_h2d_bytes += (wb - wa) * 8;
+            enq[ci] = (wb - wa) * 8; cum_enq += (wb - wa) * 8;
             MDBG_CK(c, cudaMemcpyAsync(d_planes.p + 2 * wa, hp + 2 * wa, (wb - wa) * 8, cudaMemcpyHostToDevice, c->st_copy));
             MDBG_CK(c, cudaEventRecord(c->copy_ev[ci], c->st_copy));
             if (wb == n_words) MDBG_CK(c, cudaEventRecord(c->ev[4], c->st_copy));

@@ -114,6 +114,7 @@ __global__ void kb_records_kernel(MinArena A, const uint64_t* __restrict__ kmer_
     bool rv = window_reversed(h, k);
     uint64_t f = fp_init(seed, k);
     for (uint32_t q = 0; q < k; q++) f = fp_mix(f, rv ? __ldg(h + k - 1 - q) : __ldg(h + q));
+    f = fp_fin(f);
     if (owner) owner[g] = (uint8_t)__umul64hi(f, (uint64_t)world);
     f &= fp_mask;
     if (f == KC_EMPTY) f = KC_EMPTY - 1;
@@ -169,6 +170,7 @@ __global__ void kc_fp_kernel(TupleSrc T, uint64_t K, uint64_t seed, uint64_t fp_
     T.row(j, t, step);
     uint64_t f = fp_init(seed, T.k);
     for (uint32_t q = 0; q < T.k; q++) f = fp_mix(f, __ldg(t + (int64_t)q * step));
+    f = fp_fin(f);
     f &= fp_mask;
     if (f == KC_EMPTY) f = KC_EMPTY - 1;
     fp[j] = f;
@@ -207,6 +209,7 @@ __global__ void rs_node_fp_kernel(const uint64_t* __restrict__ tuple, uint32_t S
     if (j >= S) return;
     uint64_t f = fp_init(seed, k);
     for (uint32_t q = 0; q < k; q++) f = fp_mix(f, __ldg(tuple + (uint64_t)j * k + q));
+    f = fp_fin(f);
     fp[j] = f;
     pos[j] = j;
 }
@@ -223,6 +226,7 @@ __global__ void rs_lookup_kernel(MinArena A, const uint64_t* __restrict__ kmer_o
     const bool rv = window_reversed(h, k);
     uint64_t f = fp_init(seed, k);
     for (uint32_t q = 0; q < k; q++) f = fp_mix(f, __ldg(rv ? h + (k - 1 - q) : h + q));
+    f = fp_fin(f);
     uint32_t lo = 0, hi = S;           // lower bound of f in sfp
     while (lo < hi) {
         const uint32_t mid = lo + ((hi - lo) >> 1);
@@ -485,6 +489,7 @@ __global__ void ke_entries_kernel(NodeView N, uint64_t seed, uint64_t* __restric
     }
     uint64_t f = fp_init(seed, k1);
     for (uint32_t j = 0; j < k1; j++) f = fp_mix(f, rv ? t[k1 - 1 - j] : t[j]);
+    f = fp_fin(f);
     ekey[e] = f >> 32;   // 32-bit bucket key (4 radix passes); equality is decided on the tuples
     eval[e] = e;
     erev[e] = rv ? 1 : 0;

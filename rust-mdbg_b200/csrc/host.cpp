@@ -52,7 +52,7 @@ void mdbg_shard_reads(uint64_t n, int world, int rank, uint64_t* lo, uint64_t* h
 uint64_t mdbg_tuple_fingerprint(const uint64_t* t, uint32_t k, uint64_t seed) {
     uint64_t h = mdbg::fp_init(seed, k);
     for (uint32_t i = 0; i < k; i++) h = mdbg::fp_mix(h, t[i]);
-    return h;
+    return mdbg::fp_fin(h);
 }
 // owner = top bits of the fingerprint, scaled to the world size (works for any world)
 uint32_t mdbg_owner_of_fingerprint(uint64_t fp, int world) {

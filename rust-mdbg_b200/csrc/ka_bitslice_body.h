@@ -48,6 +48,10 @@ constexpr int NW = 128;                // run-mask words of a tile
 constexpr int QCAP = 64;               // candidate queue (expected ~25 per tile at T = 8)
 constexpr int HALO_RUNS = 16;          // look-ahead kept by a top tile (>= l-1 for every instantiated l)
 constexpr uint32_t Q_DROP = 0xFFFFFFFFu;
+#ifndef MDBG_BS_UNROLL
+#define MDBG_BS_UNROLL 1               // words of a lane's row processed per iteration of the P2/P3 loop (A/B: 1, 2, 4)
+#endif
+constexpr int BS_UNROLL = MDBG_BS_UNROLL;
 
 struct Carry {                         // the first HPC bases of tile t+1, seen from tile t
     uint32_t a, b, rs;                 // planes and read-start bits, cnt valid positions
@@ -275,7 +279,7 @@ BS_DEV void process_tile(const KAArgs& A, WarpSmem& sm, const int lane, const ui
         const bool prev_ok = is_acgt(prevb);        // N / nothing before the tile: a run starts
         // planes of the previous word: only their top bits matter (the base before this lane's first)
         uint32_t qa = ((prevb >> 1) & 1u) << 31, qb = ((prevb >> 2) & 1u) << 31;
-#pragma unroll 1
+#pragma unroll BS_UNROLL
         for (int n = 0; n < 4; n++) {
             const int idx = lane * 4 + n;
             uint32_t PA, PB;

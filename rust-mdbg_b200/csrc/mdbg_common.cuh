@@ -66,15 +66,21 @@ inline uint64_t hash_bound(double density) {
     return (uint64_t)x;
 }
 
-// Fingerprint of a canonical tuple: order-sensitive 64-bit mix (murmur-style rounds).  Used
-// only to place a tuple (table slot, owner rank, sort key); identity is always decided by
-// comparing the tuples themselves.
+// Fingerprint of a canonical tuple: order-sensitive 64-bit hash, ONE multiply per element (the elements are
+// ntHash values, already well mixed) and a murmur-style finish.  Used only to place a tuple (table slot, owner
+// rank, sort key); identity is always decided by comparing the tuples themselves, and a collision only costs a
+// retry with another seed (the seed enters before the first multiply, so collisions do not persist across seeds).
 MDBG_HD uint64_t fp_mix(uint64_t h, uint64_t v) {
     h ^= v;
     h *= 0xff51afd7ed558ccdULL;
     h ^= h >> 32;
+    return h;
+}
+MDBG_HD uint64_t fp_fin(uint64_t h) {
     h *= 0xc4ceb9fe1a85ec53ULL;
     h ^= h >> 29;
+    h *= 0xff51afd7ed558ccdULL;
+    h ^= h >> 32;
     return h;
 }
 MDBG_HD uint64_t fp_init(uint64_t seed, uint32_t k) { return seed ^ (0x9e3779b97f4a7c15ULL * (k + 1)); }
