@@ -475,6 +475,8 @@ def main():
                "roofline": roofline, "kernel_rooflines": kernel_rooflines, "cpu_baseline": cpu,
                "stage_ms_per_step": {k_: v_ / steps for k_, v_ in stage.items()},
                "nvlink_bytes_sent_per_gpu_per_step": int(tm.get("exchange_bytes", 0)),
+               "record_exchange": (("kx_scatter_kernel: peer stores over NVLink (CUDA IPC inboxes)" if int(tm.get("exchange_p2p", 0))
+                                    else "grouped ncclSend/ncclRecv") if world > 1 else None),
                "counts": {k_: int(v_) for k_, v_ in stats.items()}}
         if multik is not None:
             out["multik"] = multik

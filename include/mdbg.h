@@ -181,6 +181,8 @@ typedef struct {
     uint64_t upload_h2d_bytes;                 /* bytes of bases that crossed PCIe in the last mdbg_push_reads */
     float ms_exchange;                         /* N > 1: the record all-to-all of the last finish (inside ms_kb..ms_kc) */
     uint64_t exchange_bytes;                   /* N > 1: bytes this GPU sent over NVLink in the last finish           */
+    uint32_t exchange_p2p;                     /* N > 1: 1 = the records went straight into the owners' inboxes over NVLink
+                                                  (kx_scatter_kernel over CUDA IPC mappings), 0 = ncclSend/ncclRecv      */
     float ms_kernels[8];                       /* single kernels of the last push / finish (CUDA events around each):
                                                   0 kb_records, 1 kc_insert, 2 kc_verify, 3 radix sort by slot,
                                                   4 ke_join, 5 ka_finalize, 6 kd_nodes + kd_expand, 7 reserved          */

@@ -11,7 +11,26 @@
 using namespace mdbg;
 
 // called by mdbg_ctx_destroy and before a re-init
+// unmap the peers' inboxes (an exporter must not free memory a peer still has mapped: growing the inboxes is
+// unmap everywhere -> barrier -> free, see ensure_inbox in graph.cu)
+void mdbg_inbox_unmap_peers(mdbg_ctx* c) {
+    for (int p = 0; p < MAX_WORLD; p++) {
+        if (c->peer_inbox[p] && c->peer_inbox[p] != c->inbox) cudaIpcCloseMemHandle(c->peer_inbox[p]);
+        c->peer_inbox[p] = nullptr;
+    }
+    (void)cudaGetLastError();
+}
+// ... and free the own one
+void mdbg_inbox_release(mdbg_ctx* c) {
+    mdbg_inbox_unmap_peers(c);
+    if (c->inbox) cudaFree(c->inbox);
+    c->inbox = nullptr;
+    c->inbox_cap = 0;
+    (void)cudaGetLastError();
+}
+
 extern "C" void mdbg_comm_release(mdbg_ctx* c) {
+    if (c) { cudaSetDevice(c->device); mdbg_inbox_release(c); c->p2p_state = 0; }
     if (c && c->comm) {
         NcclApi& N = nccl();
         if (N.ok && c->comm2) N.CommDestroy((ncclComm_t)c->comm2);
@@ -53,10 +72,10 @@ int mdbg_comm_init(mdbg_ctx* c, const uint8_t id[MDBG_NCCL_ID_BYTES], int rank, 
     mdbg_comm_release(c);   // a second init replaces the first communicator
     c->comm = (void*)comm;
     // second communicator over the same ranks: lets the arena all-gather overlap the record exchange (operations
-    // of ONE communicator run in issue order).  Opt-in (MDBG_COMM2=1): without it everything runs on `comm`, in order.
+    // of ONE communicator run in issue order).  MDBG_COMM2=0 turns it off: everything then runs on `comm`, in order.
     c->comm2 = nullptr;
     const char* want2 = getenv("MDBG_COMM2");
-    if (N.CommSplit && world > 1 && want2 && want2[0] == '1') {
+    if (N.CommSplit && world > 1 && !(want2 && want2[0] == '0')) {
         ncclComm_t c2 = nullptr;
         if (N.CommSplit(comm, 0, rank, &c2, nullptr) == ncclSuccess) c->comm2 = (void*)c2;
     }

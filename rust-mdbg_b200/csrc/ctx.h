@@ -105,6 +105,11 @@ struct mdbg_ctx {
     // NCCL (multi-GPU)
     void* comm = nullptr; int rank = 0, world = 1;
     void* comm2 = nullptr;   // a copy of the communicator for the arena all-gather, which runs on st_copy under K-B / K-C
+    // record inbox (N > 1): the peers' kx_scatter_kernel writes their records for this owner straight into this
+    // buffer over NVLink (CUDA IPC mappings of each other's inboxes); capacity in records, equal on every rank
+    void* inbox = nullptr; uint64_t inbox_cap = 0;
+    void* peer_inbox[mdbg::MAX_WORLD] = {};          // [p] = rank p's inbox as mapped into this process ([rank] = inbox)
+    int p2p_state = 0;                               // 0 untried, 1 mapped, -1 unavailable (NCCL send/recv instead)
     uint64_t read_base = 0; bool read_base_set = false;   // global index of this rank's first read
     // device-resident result of the last finish (kept until the next finish/reset)
     struct DeviceGraph* dg = nullptr;

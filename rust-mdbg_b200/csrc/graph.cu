@@ -47,6 +47,9 @@ struct DeviceGraph {
     Tmp<SeqRec> seq;                                           // this GPU's lines (ordinal order)
 };
 
+void mdbg_inbox_release(mdbg_ctx* c);   // comm.cu
+void mdbg_inbox_unmap_peers(mdbg_ctx* c);
+
 extern "C" void mdbg_graph_device_free(mdbg_ctx* c) {
     if (c && c->dg) { delete c->dg; c->dg = nullptr; }
 }
@@ -197,6 +200,69 @@ int alltoallv(mdbg_ctx* c, int narr, const void* const* send, void* const* recv,
     return MDBG_OK;
 }
 
+// Collective: make every rank's record inbox hold `cap_records` and map the peers' inboxes (CUDA IPC).  Every rank
+// calls it with the same value.  Sets c->p2p_state = 1 on success, -1 when any rank could not map a peer (then the
+// records travel with ncclSend/ncclRecv).
+int ensure_inbox(mdbg_ctx* c, uint64_t cap_records) {
+    if (c->p2p_state < 0) return MDBG_OK;
+    if (c->p2p_state == 1 && c->inbox_cap >= cap_records) return MDBG_OK;
+    const int W = c->world;
+    cudaStream_t st = c->st;
+    // nobody may still be writing into / reading from the old inboxes: the previous finish ended with a collective
+    // and a stream synchronisation on every rank, and this call follows an all-gather of this finish.  Growing:
+    // every rank unmaps its peers, a barrier, then every rank frees its own inbox.
+    if (c->inbox) {
+        mdbg_inbox_unmap_peers(c);
+        NCK(c, nccl().AllReduce(c->d_mail, c->d_mail, 1, ncclUint64, ncclSum, (ncclComm_t)c->comm, st));
+        MDBG_CK(c, cudaStreamSynchronize(st));
+    }
+    mdbg_inbox_release(c);
+    const uint64_t cap = cap_records + cap_records / 4 + 4096;
+    int ok = cudaMalloc(&c->inbox, InboxLayout::bytes(cap)) == cudaSuccess ? 1 : 0;
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof mine);
+    if (ok && cudaIpcGetMemHandle(&mine, c->inbox) != cudaSuccess) ok = 0;
+    (void)cudaGetLastError();
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    // handles (64 B) + ok flag (8 B) of every rank: 9 words each, through the mailbox
+    uint64_t h_words[9];
+    memcpy(h_words, &mine, 64);
+    h_words[8] = (uint64_t)ok;
+    uint64_t* d_in = c->d_mail + 64 + MAX_WORLD * MAX_WORLD;            // scratch behind the count matrix
+    uint64_t* d_all = d_in + 16;
+    MDBG_CK(c, cudaMemcpyAsync(d_in, h_words, 72, cudaMemcpyHostToDevice, st));
+    NCK(c, nccl().AllGather(d_in, d_all, 9, ncclUint64, (ncclComm_t)c->comm, st));
+    std::vector<uint64_t> all(9 * (size_t)W);
+    MDBG_CK(c, cudaMemcpyAsync(all.data(), d_all, all.size() * 8, cudaMemcpyDeviceToHost, st));
+    MDBG_CK(c, cudaStreamSynchronize(st));
+    bool all_ok = true;
+    for (int p = 0; p < W; p++) all_ok = all_ok && all[9 * p + 8] == 1;
+    int mapped = all_ok ? 1 : 0;
+    if (all_ok) {
+        for (int p = 0; p < W && mapped; p++) {
+            if (p == c->rank) { c->peer_inbox[p] = c->inbox; continue; }
+            cudaIpcMemHandle_t h;
+            memcpy(&h, &all[9 * p], 64);
+            if (cudaIpcOpenMemHandle(&c->peer_inbox[p], h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                (void)cudaGetLastError();
+                c->peer_inbox[p] = nullptr;
+                mapped = 0;
+            }
+        }
+    }
+    // every rank must take the same path: agree on the outcome
+    uint64_t flag = (uint64_t)mapped;
+    MDBG_CK(c, cudaMemcpyAsync(d_in, &flag, 8, cudaMemcpyHostToDevice, st));
+    NCK(c, nccl().AllGather(d_in, d_all, 1, ncclUint64, (ncclComm_t)c->comm, st));
+    MDBG_CK(c, cudaMemcpyAsync(all.data(), d_all, (size_t)W * 8, cudaMemcpyDeviceToHost, st));
+    MDBG_CK(c, cudaStreamSynchronize(st));
+    bool everyone = true;
+    for (int p = 0; p < W; p++) everyone = everyone && all[p] == 1;
+    if (everyone) { c->inbox_cap = cap; c->p2p_state = 1; }
+    else { mdbg_inbox_release(c); c->p2p_state = -1; }
+    return MDBG_OK;
+}
+
 // Everything from the resident minimizers to the device graph (installed in the context only on success).
 int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
     mdbg_graph_device_free(c);
@@ -302,14 +368,13 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
     Tmp<uint64_t> x_ord, x_fp;
     Tmp<RecInfo> x_info;
     Tmp<uint32_t> x_wloc;
-    const uint64_t* r_ord = l_ord; const uint64_t* r_fp_in = l_fp; const RecInfo* r_info = l_info; const uint32_t* r_wloc = l_wloc;
+    const uint64_t* r_ord = l_ord; const RecInfo* r_info = l_info; const uint32_t* r_wloc = l_wloc;
+    uint64_t* fp = l_fp.p;   // the owned records' table fingerprints (rewritten in place when a collision forces a new seed)
     if (W > 1) {
         Tmp<uint8_t> owner_s;
         Tmp<uint32_t> perm_in, perm;
         Tmp<uint64_t> s_ord, s_fp; Tmp<RecInfo> s_info; Tmp<uint32_t> s_wloc;
         MDBG_CK(c, owner_s.get(c->pool, K_local)); MDBG_CK(c, perm_in.get(c->pool, K_local)); MDBG_CK(c, perm.get(c->pool, K_local));
-        MDBG_CK(c, s_ord.get(c->pool, K_local)); MDBG_CK(c, s_fp.get(c->pool, K_local));
-        MDBG_CK(c, s_info.get(c->pool, K_local)); MDBG_CK(c, s_wloc.get(c->pool, K_local));
         if (K_local) {
             iota_kernel<<<nblk(K_local), 256, 0, st>>>(perm_in, (uint32_t)K_local);
             LAUNCHED(c);
@@ -323,31 +388,74 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
         uint64_t* d_cnt = c->d_mail + 64;   // [W][W]: row s = what rank s sends to each rank
         NCK(c, nccl().AllGather(c->d_mail, d_cnt, W, ncclUint64, (ncclComm_t)c->comm, st));
         MDBG_CK(c, cudaMemcpyAsync(c->h_mail, d_cnt, (size_t)W * W * 8, cudaMemcpyDeviceToHost, st));
-        if (K_local) {
-            kx_pack_kernel<<<nblk(K_local), 256, 0, st>>>(perm, K_local, l_fp, l_ord, l_wloc, l_info, s_fp, s_ord, s_wloc, s_info);
-            LAUNCHED(c);
-        }
         MDBG_CK(c, cudaStreamSynchronize(st));
-        uint64_t scnt[MAX_WORLD], rcnt[MAX_WORLD];
+        uint64_t scnt[MAX_WORLD], rcnt[MAX_WORLD], dst_off_of[MAX_WORLD];
         K = 0;
-        for (int p = 0; p < W; p++) { scnt[p] = c->h_mail[(size_t)rank * W + p]; rcnt[p] = c->h_mail[(size_t)p * W + rank]; K += rcnt[p]; }
+        for (int p = 0; p < W; p++) {
+            scnt[p] = c->h_mail[(size_t)rank * W + p]; rcnt[p] = c->h_mail[(size_t)p * W + rank]; K += rcnt[p];
+            dst_off_of[p] = 0;
+            for (int r = 0; r < rank; r++) dst_off_of[p] += c->h_mail[(size_t)r * W + p];   // the lower ranks' records come first
+        }
         if (K >= 0x7FFFFFF0ull) { c->err = "more than 2^31 k-min-mers owned by one GPU"; return MDBG_ERR_RANGE; }
-        MDBG_CK(c, x_ord.get(c->pool, K)); MDBG_CK(c, x_fp.get(c->pool, K)); MDBG_CK(c, x_info.get(c->pool, K));
-        MDBG_CK(c, x_wloc.get(c->pool, K)); MDBG_CK(c, iota.get(c->pool, K));
+        MDBG_CK(c, iota.get(c->pool, K));
+        // The records reach their owners either through the owners' inboxes, written over NVLink by kx_scatter_kernel
+        // (bucketing and exchange in one kernel; needs CUDA IPC between the ranks), or packed and sent with NCCL.
+        uint64_t kown_max = 0;
+        for (int p = 0; p < W; p++) {
+            uint64_t kp = 0;
+            for (int r = 0; r < W; r++) kp += c->h_mail[(size_t)r * W + p];
+            kown_max = std::max(kown_max, kp);
+        }
+        const char* p2p_env = getenv("MDBG_P2P");
+        if (p2p_env && p2p_env[0] == '0') c->p2p_state = -1;
+        // (the count matrix in h_mail is consumed above: ensure_inbox reuses the mailbox)
+        RC(ensure_inbox(c, kown_max));
         MDBG_CK(c, cudaEventRecord(c->ev[10], st));
-        const void* sv[4] = {s_fp.p, s_ord.p, s_wloc.p, s_info.p};
-        void* rv[4] = {x_fp.p, x_ord.p, x_wloc.p, x_info.p};
-        const size_t el[4] = {8, 8, 4, sizeof(RecInfo)};
-        RC(alltoallv(c, 4, sv, rv, el, scnt, rcnt));
-        MDBG_CK(c, cudaEventRecord(c->ev[11], st));
+        if (c->p2p_state == 1) {
+            ScatterPlan SP{};
+            uint64_t acc = 0;
+            for (int p = 0; p < W; p++) {
+                SP.box[p] = c->peer_inbox[p];
+                SP.bstart[p] = acc; acc += scnt[p];
+                SP.dst_off[p] = 0;
+            }
+            SP.bstart[W] = acc;
+            for (int p = 0; p < W; p++) SP.dst_off[p] = dst_off_of[p];
+            const InboxLayout IL{c->inbox_cap};
+            if (K_local) {
+                kx_scatter_kernel<<<nblk(K_local), 256, 0, st>>>(perm, owner_s, K_local, l_fp, l_ord, l_wloc, l_info, SP, IL,
+                                                                 SP.bstart[(rank + 1) % W]);
+                LAUNCHED(c);
+            }
+            // every rank's scatter must have landed before any owner reads its inbox: a collective after the kernel
+            // (stream order on every rank) is that barrier
+            NCK(c, nccl().AllReduce(c->d_mail, c->d_mail, 1, ncclUint64, ncclSum, (ncclComm_t)c->comm, st));
+            MDBG_CK(c, cudaEventRecord(c->ev[11], st));
+            r_ord = IL.ord(c->inbox); r_info = IL.info(c->inbox); r_wloc = IL.wloc(c->inbox);
+            fp = IL.fp(c->inbox);
+        } else {
+            MDBG_CK(c, x_ord.get(c->pool, K)); MDBG_CK(c, x_fp.get(c->pool, K)); MDBG_CK(c, x_info.get(c->pool, K));
+            MDBG_CK(c, x_wloc.get(c->pool, K));
+            MDBG_CK(c, s_ord.get(c->pool, K_local)); MDBG_CK(c, s_fp.get(c->pool, K_local));
+            MDBG_CK(c, s_info.get(c->pool, K_local)); MDBG_CK(c, s_wloc.get(c->pool, K_local));
+            if (K_local) {
+                kx_pack_kernel<<<nblk(K_local), 256, 0, st>>>(perm, K_local, l_fp, l_ord, l_wloc, l_info, s_fp, s_ord, s_wloc, s_info);
+                LAUNCHED(c);
+            }
+            const void* sv[4] = {s_fp.p, s_ord.p, s_wloc.p, s_info.p};
+            void* rv[4] = {x_fp.p, x_ord.p, x_wloc.p, x_info.p};
+            const size_t el[4] = {8, 8, 4, sizeof(RecInfo)};
+            RC(alltoallv(c, 4, sv, rv, el, scnt, rcnt));
+            MDBG_CK(c, cudaEventRecord(c->ev[11], st));
+            r_ord = x_ord; r_info = x_info; r_wloc = x_wloc;
+            fp = x_fp.p;
+        }
         c->tm.exchange_bytes += (K_local - scnt[rank]) * (8 + 8 + 4 + sizeof(RecInfo));
+        c->tm.exchange_p2p = c->p2p_state == 1 ? 1 : 0;
         if (K) { iota_kernel<<<nblk(K), 256, 0, st>>>(iota, (uint32_t)K); LAUNCHED(c); }
-        r_ord = x_ord; r_fp_in = x_fp; r_info = x_info; r_wloc = x_wloc;
         l_owner.reset();
-        // (the local arrays stay alive until the sends have run: freed with the other table scratch)
+        // (the local arrays stay alive until the sends / the scatter have run: freed with the other table scratch)
     }
-    uint64_t* fp = W > 1 ? x_fp.p : l_fp.p;   // rewritten in place when a collision forces a new seed
-    (void)r_fp_in;
     const TupleSrc T{arena, r_wloc, r_ord, k};
 
     // ---- K-C table + K-D sort by slot (retry with a new seed on a fingerprint collision) ---------

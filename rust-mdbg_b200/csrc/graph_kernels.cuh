@@ -72,6 +72,7 @@ struct RecInfo {
     uint32_t span;    // p[i+k-1] - p[i]   (seqlen = span + 2, end = p0 + span + l)
     uint64_t read;    // global read index
 };
+static_assert(sizeof(RecInfo) == 24, "RecInfo is moved as three u64 words");
 constexpr uint64_t ORD_REV = 1ull << 63;
 constexpr uint64_t ORD_MASK = ORD_REV - 1;
 
@@ -150,6 +151,66 @@ __global__ void kx_bounds_kernel(const uint8_t* __restrict__ sorted, uint64_t K,
     }
     cnt[w] = b[1] - b[0];
 }
+// Bucketing fused with the exchange: every record is written STRAIGHT into its owner's inbox over NVLink (the
+// inboxes of the peers are mapped into this process with CUDA IPC; `box[w]` is rank w's inbox as seen from here).
+// Record i of the owner-sorted order goes to slot dst_off[w] + (i - bstart[w]) of owner w: dst_off[w] = records
+// the lower ranks send to w, so an owner's inbox fills in rank order = ascending ordinal.  Consecutive threads
+// write consecutive remote addresses (coalesced 8/4-byte stores through the NVSwitch).
+struct InboxLayout {        // SoA inside one allocation of `cap` records
+    uint64_t cap;
+    __host__ __device__ uint64_t* fp(void* b) const { return (uint64_t*)b; }
+    __host__ __device__ uint64_t* ord(void* b) const { return (uint64_t*)b + cap; }
+    __host__ __device__ RecInfo* info(void* b) const { return (RecInfo*)((uint64_t*)b + 2 * cap); }
+    __host__ __device__ uint32_t* wloc(void* b) const { return (uint32_t*)((uint64_t*)b + 5 * cap); }
+    __host__ __device__ static uint64_t bytes(uint64_t cap) { return cap * 44 + 64; }
+};
+constexpr int KX_MAX_WORLD = 16;
+struct ScatterPlan {
+    void* box[KX_MAX_WORLD];
+    uint64_t bstart[KX_MAX_WORLD + 1];   // first record of bucket w in the owner-sorted order
+    uint64_t dst_off[KX_MAX_WORLD];
+};
+__device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) {
+    const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, src), hi = __shfl_sync(0xffffffffu, (uint32_t)(v >> 32), src);
+    return ((uint64_t)hi << 32) | lo;
+}
+__global__ void kx_scatter_kernel(const uint32_t* __restrict__ perm, const uint8_t* __restrict__ owner_s, uint64_t K,
+                                  const uint64_t* __restrict__ fp, const uint64_t* __restrict__ ord,
+                                  const uint32_t* __restrict__ wloc, const RecInfo* __restrict__ info,
+                                  const ScatterPlan P, const InboxLayout L, uint64_t rot) {
+    // Thread t takes record (t + rot) mod K: rank r starts with the bucket of rank r + 1, so that at any moment the
+    // GPUs of the job store to DIFFERENT owners (in plain bucket order everybody would write to owner 0 first, then
+    // to owner 1, ...: an incast that serialises the exchange on one NVLink ingress at a time).
+    const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31u;
+    const bool valid = t < K;
+    const uint64_t i = t + rot < K ? t + rot : t + rot - K;
+    uint64_t ibase = 0, v0 = 0, v1 = 0, v2 = 0;
+    if (valid) {
+        const uint32_t w = owner_s[i], j = __ldg(perm + i);
+        const uint64_t d = P.dst_off[w] + (i - P.bstart[w]);
+        void* b = P.box[w];
+        L.fp(b)[d] = fp[j];
+        L.ord(b)[d] = ord[j];
+        L.wloc(b)[d] = wloc[j];
+        const RecInfo ri = info[j];
+        v0 = (uint64_t)ri.p0 | ((uint64_t)ri.d01 << 32);
+        v1 = (uint64_t)ri.dlast | ((uint64_t)ri.span << 32);
+        v2 = ri.read;
+        ibase = (uint64_t)(uintptr_t)(L.info(b) + d);
+    }
+    // RecInfo is 24 bytes: stored per thread it would leave the SM as 8/16-byte pieces at stride 24 (three quarters of
+    // every NVLink packet empty).  The warp's 32 records are 96 words: lane t stores words t, t + 32, t + 64, so the
+    // records of one bucket leave as three contiguous 256-byte stores.
+#pragma unroll
+    for (int part = 0; part < 3; part++) {
+        const uint32_t q = part * 32u + lane, r = q / 3u, cidx = q - 3u * r;
+        const uint64_t a = shfl64(ibase, (int)r);
+        const uint64_t x0 = shfl64(v0, (int)r), x1 = shfl64(v1, (int)r), x2 = shfl64(v2, (int)r);
+        if (a) reinterpret_cast<uint64_t*>((uintptr_t)a)[cidx] = cidx == 0 ? x0 : (cidx == 1 ? x1 : x2);
+    }
+}
+
 // send buffers: the records in owner order (stable, so every bucket ascends in ordinal)
 __global__ void kx_pack_kernel(const uint32_t* __restrict__ perm, uint64_t K, const uint64_t* __restrict__ fp,
                                const uint64_t* __restrict__ ord, const uint32_t* __restrict__ wloc,

@@ -50,7 +50,7 @@ class CTimings(ctypes.Structure):
                 ("ms_ka_kernel", ctypes.c_float), ("ms_ka_start", ctypes.c_float),
                 ("ka_variant_used", u32), ("ka_dirty_tiles", u32), ("upload_packed", u32),
                 ("upload_ascii_tiles", u32), ("upload_h2d_bytes", u64), ("ms_exchange", ctypes.c_float),
-                ("exchange_bytes", u64), ("ms_kernels", ctypes.c_float * 8)]
+                ("exchange_bytes", u64), ("exchange_p2p", u32), ("ms_kernels", ctypes.c_float * 8)]
 
 
 class CSynth(ctypes.Structure):
