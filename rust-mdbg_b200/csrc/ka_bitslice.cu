@@ -60,10 +60,13 @@ void ka_bs_tables(void* host_out) {
 }
 
 // Tiles [A.tile_begin, A.tile_end) in groups of A.bs_group; dirty tiles are appended to A.dirty_list.
-cudaError_t ka_bs_launch(const KAArgs& A, int hpc, int grid, cudaStream_t st, uint64_t* launches) {
-    if (A.tile_end <= A.tile_begin) return cudaSuccess;
+cudaError_t ka_bs_launch(const KAArgs& A0, int hpc, int grid, cudaStream_t st, uint64_t* launches) {
+    if (A0.tile_end <= A0.tile_begin) return cudaSuccess;
+    KAArgs A = A0;
     const uint64_t S = A.bs_group ? A.bs_group : 1;
     const uint64_t groups = (A.tile_end - A.tile_begin + S - 1) / S;
+    if (groups > 0xFFFFFFFFull) return cudaErrorInvalidValue;
+    A.bs_ngroups = (uint32_t)groups;
     const uint64_t need = (groups + BS_WARPS - 1) / BS_WARPS;
     const unsigned g = (unsigned)(need < (uint64_t)grid ? need : (uint64_t)grid);
     cudaError_t e = cudaErrorInvalidValue;

@@ -50,6 +50,7 @@ struct KAArgs {
     unsigned int* dirty_n;
     unsigned long long* dirty_out;   // ka_finalize_kernel copies *dirty_n here (host mailbox)
     uint32_t bs_group;           // consecutive tiles claimed by a warp at a time
+    uint32_t bs_ngroups;         // groups of this launch = ceil((tile_end - tile_begin) / bs_group), set by ka_bs_launch
     const bs::T4Entry* bs_t4;    // 256 x 16 B: 4-base ntHash tables (ka_bs_tables), device memory
     uint32_t* dbg;               // optional: 8 words of per-tile state (tests / MDBG_BS_DEBUG_DUMP)
 };

@@ -83,6 +83,37 @@ bool cpu_has_avx2() {
     static const bool v = __builtin_cpu_supports("avx2") && !getenv("MDBG_PACK_NO_AVX2");
     return v;
 }
+// AVX-512BW: two words (64 bases) per load; the mask registers ARE the bit planes (vpmovb2m), the alphabet check
+// is one vpshufb + one compare-to-mask
+__attribute__((target("avx512f,avx512bw"))) void pack_full_words_avx512(const uint8_t* bases, uint64_t w_begin,
+                                                                        uint64_t w_end, uint32_t* planes,
+                                                                        uint8_t* bad_tiles) {
+    const __m512i lut = _mm512_broadcast_i32x4(_mm_setr_epi8('A', 'C', 'T', 'G', 'A', 'C', 'T', 'G', 'A', 'C', 'T', 'G',
+                                                             'A', 'C', 'T', 'G'));
+    const __m512i three = _mm512_set1_epi8(3);
+    uint64_t w = w_begin;
+    for (; w + 2 <= w_end; w += 2) {
+        const __m512i v = _mm512_loadu_si512(reinterpret_cast<const void*>(bases + w * 32));
+        const uint64_t a = (uint64_t)_mm512_movepi8_mask(_mm512_slli_epi16(v, 6));
+        const uint64_t b = (uint64_t)_mm512_movepi8_mask(_mm512_slli_epi16(v, 5));
+        const __m512i codes = _mm512_and_si512(_mm512_srli_epi16(v, 1), three);
+        const uint64_t ok = (uint64_t)_mm512_cmpeq_epi8_mask(_mm512_shuffle_epi8(lut, codes), v);
+        planes[2 * w] = (uint32_t)a;
+        planes[2 * w + 1] = (uint32_t)b;
+        planes[2 * w + 2] = (uint32_t)(a >> 32);
+        planes[2 * w + 3] = (uint32_t)(b >> 32);
+        if (ok != ~0ull && bad_tiles) {
+            if ((uint32_t)ok != 0xFFFFFFFFu) bad_tiles[w / PACK_TILE_WORDS] = 1;
+            if ((uint32_t)(ok >> 32) != 0xFFFFFFFFu) bad_tiles[(w + 1) / PACK_TILE_WORDS] = 1;
+        }
+    }
+    if (w < w_end) pack_full_words_avx2(bases, w, w_end, planes, bad_tiles);
+}
+bool cpu_has_avx512bw() {
+    static const bool v = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") &&
+                          !getenv("MDBG_PACK_NO_AVX512") && !getenv("MDBG_PACK_NO_AVX2");
+    return v;
+}
 #endif
 
 }  // namespace
@@ -92,7 +123,10 @@ void pack_words(const uint8_t* bases, uint64_t n_bases, uint64_t w_begin, uint64
 #if defined(MDBG_PACK_X86)
     if (cpu_has_avx2()) {              // whole words with AVX2, the ragged last word below
         const uint64_t full = std::min<uint64_t>(w_end, n_bases / 32);
-        if (w_begin < full) pack_full_words_avx2(bases, w_begin, full, planes, bad_tiles);
+        if (w_begin < full) {
+            if (cpu_has_avx512bw()) pack_full_words_avx512(bases, w_begin, full, planes, bad_tiles);
+            else pack_full_words_avx2(bases, w_begin, full, planes, bad_tiles);
+        }
         w_begin = std::max(w_begin, full);
     }
 #endif

@@ -125,6 +125,7 @@ int bs_model_run(const uint8_t* bases, const uint64_t* read_off, uint64_t R, uin
     A.tile_lb = tile_lb.data(); A.tile_counter = &tile_counter; A.n_tiles = n_tiles;
     A.tile_begin = tile_begin; A.tile_end = tile_end_or_0 ? tile_end_or_0 : n_tiles;
     A.dirty_list = dirty_list; A.dirty_n = &dn; A.bs_group = group; A.dbg = dbg;
+    { const uint64_t S = group ? group : 1; A.bs_ngroups = (uint32_t)((A.tile_end - A.tile_begin + S - 1) / S); }   // as ka_bs_launch does
     static bs::T4Entry t4[256];
     for (uint32_t i = 0; i < 256; i++) t4[i] = bs::t4_make(i);
     A.bs_t4 = t4;
