@@ -36,6 +36,11 @@ __device__ __forceinline__ uint64_t owner_read(const uint64_t* __restrict__ a, u
     return lo;
 }
 
+__device__ __forceinline__ uint64_t shfl64(uint64_t v, int src, uint32_t mask = 0xffffffffu) {
+    const uint32_t lo = __shfl_sync(mask, (uint32_t)v, src), hi = __shfl_sync(mask, (uint32_t)(v >> 32), src);
+    return ((uint64_t)hi << 32) | lo;
+}
+
 // ---- K-B ---------------------------------------------------------------------------------------
 // cnt[r] = m > k ? m-k+1 : 0  (strict, main.rs:756); cnt[R] = 0 so the exclusive scan ends with K.
 __global__ void kb_count_kernel(const uint64_t* __restrict__ m_off, uint64_t R, uint32_t k,
@@ -106,15 +111,43 @@ __global__ void kb_records_kernel(MinArena A, const uint64_t* __restrict__ kmer_
                                   RecInfo* __restrict__ info, uint64_t* __restrict__ fp,
                                   uint32_t* __restrict__ iota, uint8_t* __restrict__ owner) {
     uint64_t g = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    const uint32_t act = __ballot_sync(0xffffffffu, g < K);
     if (g >= K) return;
-    uint64_t r = owner_read(kmer_off, A.R, g);
-    uint64_t i = g - __ldg(kmer_off + r);
+    // The sightings of a warp are consecutive: nearly always they belong to the read of the warp's first one.  Lane 0
+    // of the warp does the binary search (19 dependent loads at config 3), the others take its answer when it fits
+    // their sighting too and search only otherwise (a read boundary inside the warp).
+    uint64_t r = 0, r_lo = 0, r_hi = 0;
+    {
+        const uint32_t lane = threadIdx.x & 31u;
+        const int leader = __ffs((int)act) - 1;
+        if ((int)lane == leader) {
+            r = owner_read(kmer_off, A.R, g);
+            r_lo = __ldg(kmer_off + r);
+            r_hi = __ldg(kmer_off + r + 1);
+        }
+        r = shfl64(r, leader, act); r_lo = shfl64(r_lo, leader, act); r_hi = shfl64(r_hi, leader, act);
+        if (g >= r_hi) {               // (g >= r_lo always: the leader holds the smallest g of the warp)
+            r = owner_read(kmer_off, A.R, g);
+            r_lo = __ldg(kmer_off + r);
+        }
+    }
+    uint64_t i = g - r_lo;
     uint64_t lo = __ldg(A.off + r) + i;
     const uint64_t* h = A.hash + lo;
     const uint32_t* p = A.pos + lo;
     bool rv = window_reversed(h, k);
     uint64_t f = fp_init(seed, k);
-    for (uint32_t q = 0; q < k; q++) f = fp_mix(f, rv ? __ldg(h + k - 1 - q) : __ldg(h + q));
+    {   // the loads do not depend on the mixing chain: four at a time
+        const int64_t st = rv ? -1 : 1;
+        const uint64_t* e = rv ? h + k - 1 : h;
+        uint32_t q = 0;
+        for (; q + 4 <= k; q += 4) {
+            const uint64_t e0 = __ldg(e + (int64_t)q * st), e1 = __ldg(e + (int64_t)(q + 1) * st);
+            const uint64_t e2 = __ldg(e + (int64_t)(q + 2) * st), e3 = __ldg(e + (int64_t)(q + 3) * st);
+            f = fp_mix(fp_mix(fp_mix(fp_mix(f, e0), e1), e2), e3);
+        }
+        for (; q < k; q++) f = fp_mix(f, __ldg(e + (int64_t)q * st));
+    }
     f = fp_fin(f);
     if (owner) owner[g] = (uint8_t)__umul64hi(f, (uint64_t)world);
     f &= fp_mask;
@@ -170,10 +203,6 @@ struct ScatterPlan {
     uint64_t bstart[KX_MAX_WORLD + 1];   // first record of bucket w in the owner-sorted order
     uint64_t dst_off[KX_MAX_WORLD];
 };
-__device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) {
-    const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, src), hi = __shfl_sync(0xffffffffu, (uint32_t)(v >> 32), src);
-    return ((uint64_t)hi << 32) | lo;
-}
 __global__ void kx_scatter_kernel(const uint32_t* __restrict__ perm, const uint8_t* __restrict__ owner_s, uint64_t K,
                                   const uint64_t* __restrict__ fp, const uint64_t* __restrict__ ord,
                                   const uint32_t* __restrict__ wloc, const RecInfo* __restrict__ info,
@@ -351,9 +380,19 @@ __global__ void kc_verify_kernel(TupleSrc T, uint64_t K, const uint32_t* __restr
     const uint64_t *a, *b; int sa, sb;
     T.row(j, a, sa);
     T.row(f, b, sb);
-    bool same = true;
-    for (uint32_t q = 0; q < T.k && same; q++) same = __ldg(a + (int64_t)q * sa) == __ldg(b + (int64_t)q * sb);
-    if (!same) atomicAdd(collisions, 1ull);
+    // four elements per step without a branch in between: eight loads in flight instead of two (the windows are
+    // equal in all but ~2^-40 of the cases, so leaving early buys nothing)
+    uint64_t diff = 0;
+    uint32_t q = 0;
+    for (; q + 4 <= T.k; q += 4) {
+        const uint64_t a0 = __ldg(a + (int64_t)q * sa), a1 = __ldg(a + (int64_t)(q + 1) * sa);
+        const uint64_t a2 = __ldg(a + (int64_t)(q + 2) * sa), a3 = __ldg(a + (int64_t)(q + 3) * sa);
+        const uint64_t b0 = __ldg(b + (int64_t)q * sb), b1 = __ldg(b + (int64_t)(q + 1) * sb);
+        const uint64_t b2 = __ldg(b + (int64_t)(q + 2) * sb), b3 = __ldg(b + (int64_t)(q + 3) * sb);
+        diff |= (a0 ^ b0) | (a1 ^ b1) | (a2 ^ b2) | (a3 ^ b3);
+    }
+    for (; q < T.k; q++) diff |= __ldg(a + (int64_t)q * sa) ^ __ldg(b + (int64_t)q * sb);
+    if (diff) atomicAdd(collisions, 1ull);
 }
 
 // ---- K-D ---------------------------------------------------------------------------------------

@@ -6,6 +6,7 @@
 // ka_minimizers_kernel (1 B read per base + 12 B written per minimizer).
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "ka_bitslice_body.h"
 
@@ -16,12 +17,26 @@ namespace {
 constexpr int BS_WARPS = KA_THREADS / 32;
 constexpr int BS_T = 8;                 // top bits tested by the filter: bound < 2^56
 
+// MDBG_BS_SMEM_PAD=<bytes>: extra dynamic shared memory per CTA (unused) -- lowers the number of resident CTAs per
+// SM for occupancy-sensitivity measurements; 0 in production.
+size_t smem_pad() {
+    static const size_t v = [] {
+        const char* e = getenv("MDBG_BS_SMEM_PAD");
+        long x = e ? atol(e) : 0;
+        return (size_t)((x > 0 && x <= 160 * 1024) ? x : 0);
+    }();
+    return v;
+}
+
 struct __align__(16) BsCta {
     bs::WarpSmem w[BS_WARPS];
 };
 
+#ifndef MDBG_BS_MINBLOCKS
+#define MDBG_BS_MINBLOCKS 6            // resident CTAs per SM (shared memory allows 6): up to 85 registers per thread
+#endif
 template <int L, bool HPC>
-__global__ void __launch_bounds__(KA_THREADS) ka_bitslice_kernel(const KAArgs A) {
+__global__ void __launch_bounds__(KA_THREADS, MDBG_BS_MINBLOCKS) ka_bitslice_kernel(const KAArgs A) {
     extern __shared__ __align__(16) unsigned char bs_smem_raw[];
     BsCta& cs = *reinterpret_cast<BsCta*>(bs_smem_raw);
     // warps are independent: no CTA-wide barrier anywhere
@@ -33,19 +48,20 @@ cudaError_t launch_one(const KAArgs& A, unsigned g, cudaStream_t st) {
     static bool attr_set = false;       // per instantiation; contexts of one process share the device code
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(ka_bitslice_kernel<L, HPC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)sizeof(BsCta));
+                                             (int)(sizeof(BsCta) + smem_pad()));
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    ka_bitslice_kernel<L, HPC><<<g, KA_THREADS, sizeof(BsCta), st>>>(A);
+    ka_bitslice_kernel<L, HPC><<<g, KA_THREADS, sizeof(BsCta) + smem_pad(), st>>>(A);
     return cudaGetLastError();
 }
 
 template <int L, bool HPC>
 int occupancy_one() {
     int n = 0;
-    cudaFuncSetAttribute(ka_bitslice_kernel<L, HPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BsCta));
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ka_bitslice_kernel<L, HPC>, KA_THREADS, sizeof(BsCta));
+    cudaFuncSetAttribute(ka_bitslice_kernel<L, HPC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)(sizeof(BsCta) + smem_pad()));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ka_bitslice_kernel<L, HPC>, KA_THREADS, sizeof(BsCta) + smem_pad());
     return n;
 }
 

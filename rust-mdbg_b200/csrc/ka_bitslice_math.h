@@ -150,6 +150,16 @@ MDBG_HD void pext_pair(uint32_t m, uint32_t& x, uint32_t& y) {
     }
 }
 
+// Prefix XOR of a word (bit i = parity of bits 0..i): XOR of the word shifted by 0..31.  Three shifts per level
+// ({0,1,2} x {0,3,6} x {0,9,18} x {0,27} covers 0..53): four 3-input LOP3 on the ALU pipe and seven shifts on the
+// FMA pipe (IMAD.SHL), one ALU instruction and one level of dependency fewer than the five shift-XOR doublings.
+MDBG_HD uint32_t prefix_xor(uint32_t v) {
+    v = v ^ (v << 1) ^ (v << 2);
+    v = v ^ (v << 3) ^ (v << 6);
+    v = v ^ (v << 9) ^ (v << 18);
+    return v ^ (v << 27);
+}
+
 // The same network in two parts: rounds 0..3 (moves by 1, 2, 4, 8), then round 4 (moves by 16), which does
 // nothing unless some base has 16 or more dropped bases below it -- `mk` says so (callers vote on it).
 struct PextState { uint32_t m, mk; };
@@ -159,11 +169,7 @@ MDBG_HD PextState pext_pair_rounds4(uint32_t m, uint32_t& x, uint32_t& y) {
     uint32_t mk = ~m << 1;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        uint32_t mp = mk ^ (mk << 1);
-        mp ^= mp << 2;
-        mp ^= mp << 4;
-        mp ^= mp << 8;
-        mp ^= mp << 16;
+        const uint32_t mp = prefix_xor(mk);
         const uint32_t mv = mp & m;
         m = (m ^ mv) | (mv >> (1 << i));
         uint32_t t = x & mv;
@@ -175,12 +181,7 @@ MDBG_HD PextState pext_pair_rounds4(uint32_t m, uint32_t& x, uint32_t& y) {
     return PextState{m, mk};
 }
 MDBG_HD void pext_pair_round5(const PextState& st, uint32_t& x, uint32_t& y) {
-    uint32_t mp = st.mk ^ (st.mk << 1);
-    mp ^= mp << 2;
-    mp ^= mp << 4;
-    mp ^= mp << 8;
-    mp ^= mp << 16;
-    const uint32_t mv = mp & st.m;
+    const uint32_t mv = prefix_xor(st.mk) & st.m;
     uint32_t t = x & mv;
     x = (x ^ t) | (t >> 16);
     t = y & mv;
