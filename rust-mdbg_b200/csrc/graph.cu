@@ -484,7 +484,7 @@ int build_device_graph(mdbg_ctx* c, bool want_seqlines) {
             MDBG_CK(c, cudaMemsetAsync(first, 0xFF, cap * 4, st));
             MDBG_CK(c, cudaMemsetAsync(&c->d_sc->v[1], 0, 8, st));
             MDBG_CK(c, cudaEventRecord(c->evk[2], st));
-            kc_insert_kernel<<<nblk(K * 4), 256, 0, st>>>(fp, K, keys, first, cap - 1, slot);
+            kc_insert_kernel<<<nblk((K + KC_U - 1) / KC_U * 4), 256, 0, st>>>(fp, K, keys, first, cap - 1, slot);
             LAUNCHED(c);
             MDBG_CK(c, cudaEventRecord(c->evk[3], st));
             if (arena_pending) { MDBG_CK(c, cudaStreamWaitEvent(st, c->ev[20], 0)); arena_pending = false; }   // tuples from here on

@@ -111,43 +111,15 @@ __global__ void kb_records_kernel(MinArena A, const uint64_t* __restrict__ kmer_
                                   RecInfo* __restrict__ info, uint64_t* __restrict__ fp,
                                   uint32_t* __restrict__ iota, uint8_t* __restrict__ owner) {
     uint64_t g = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    const uint32_t act = __ballot_sync(0xffffffffu, g < K);
     if (g >= K) return;
-    // The sightings of a warp are consecutive: nearly always they belong to the read of the warp's first one.  Lane 0
-    // of the warp does the binary search (19 dependent loads at config 3), the others take its answer when it fits
-    // their sighting too and search only otherwise (a read boundary inside the warp).
-    uint64_t r = 0, r_lo = 0, r_hi = 0;
-    {
-        const uint32_t lane = threadIdx.x & 31u;
-        const int leader = __ffs((int)act) - 1;
-        if ((int)lane == leader) {
-            r = owner_read(kmer_off, A.R, g);
-            r_lo = __ldg(kmer_off + r);
-            r_hi = __ldg(kmer_off + r + 1);
-        }
-        r = shfl64(r, leader, act); r_lo = shfl64(r_lo, leader, act); r_hi = shfl64(r_hi, leader, act);
-        if (g >= r_hi) {               // (g >= r_lo always: the leader holds the smallest g of the warp)
-            r = owner_read(kmer_off, A.R, g);
-            r_lo = __ldg(kmer_off + r);
-        }
-    }
-    uint64_t i = g - r_lo;
+    uint64_t r = owner_read(kmer_off, A.R, g);
+    uint64_t i = g - __ldg(kmer_off + r);
     uint64_t lo = __ldg(A.off + r) + i;
     const uint64_t* h = A.hash + lo;
     const uint32_t* p = A.pos + lo;
     bool rv = window_reversed(h, k);
     uint64_t f = fp_init(seed, k);
-    {   // the loads do not depend on the mixing chain: four at a time
-        const int64_t st = rv ? -1 : 1;
-        const uint64_t* e = rv ? h + k - 1 : h;
-        uint32_t q = 0;
-        for (; q + 4 <= k; q += 4) {
-            const uint64_t e0 = __ldg(e + (int64_t)q * st), e1 = __ldg(e + (int64_t)(q + 1) * st);
-            const uint64_t e2 = __ldg(e + (int64_t)(q + 2) * st), e3 = __ldg(e + (int64_t)(q + 3) * st);
-            f = fp_mix(fp_mix(fp_mix(fp_mix(f, e0), e1), e2), e3);
-        }
-        for (; q < k; q++) f = fp_mix(f, __ldg(e + (int64_t)q * st));
-    }
+    for (uint32_t q = 0; q < k; q++) f = fp_mix(f, rv ? __ldg(h + k - 1 - q) : __ldg(h + q));
     f = fp_fin(f);
     if (owner) owner[g] = (uint8_t)__umul64hi(f, (uint64_t)world);
     f &= fp_mask;
@@ -336,38 +308,75 @@ __global__ void rs_lookup_kernel(MinArena A, const uint64_t* __restrict__ kmer_o
 // Open-address table of 64-bit fingerprints.  Four lanes cooperate on one key: they read one
 // aligned 32-byte sector (4 slots) per probe, vote with ballot, and the lane holding the first
 // empty slot claims it with atomicCAS.  first[slot] = smallest ordinal that carries the key.
+// A group of four lanes takes KC_U consecutive keys and works on them in phases -- all first probes, then all
+// claims, then the few keys that need another look, one at a time -- so that KC_U sector reads and KC_U atomics
+// of a group are in flight together (one key at a time, a group waits for a DRAM round trip twice per key).
+constexpr int KC_U = 4;
 __global__ void kc_insert_kernel(const uint64_t* __restrict__ fp, uint64_t K, uint64_t* keys,
                                  uint32_t* first, uint64_t cap_mask, uint32_t* __restrict__ slot_out) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t sub = lane & 3, gbase = lane & ~3u;
-    uint64_t item = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 2;
-    bool active = item < K;
-    uint64_t key = active ? __ldg(fp + item) : 0;
-    uint64_t base = ((key * 0x9e3779b97f4a7c15ULL) >> 17) & cap_mask & ~3ull;
-    bool done = !active;
-    uint64_t slot = 0;
-    while (__any_sync(0xffffffffu, !done)) {
-        uint64_t cur = done ? 0 : *reinterpret_cast<volatile uint64_t*>(keys + base + sub);
-        uint32_t m_match = (__ballot_sync(0xffffffffu, !done && cur == key) >> gbase) & 0xFu;
-        uint32_t m_empty = (__ballot_sync(0xffffffffu, !done && cur == KC_EMPTY) >> gbase) & 0xFu;
-        uint32_t leader = m_empty ? (uint32_t)__ffs(m_empty) - 1 : 0;
-        uint64_t old = 0;
-        bool try_claim = !done && !m_match && m_empty;
-        if (try_claim && sub == leader)
-            old = atomicCAS(reinterpret_cast<unsigned long long*>(keys + base + leader), KC_EMPTY, key);
-        old = __shfl_sync(0xffffffffu, old, gbase + leader);
-        if (!done) {
-            if (m_match) { slot = base + (uint32_t)__ffs(m_match) - 1; done = true; }
-            else if (m_empty) {
-                if (old == KC_EMPTY || old == key) { slot = base + leader; done = true; }
+    const uint64_t item0 = ((blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 2) * KC_U;
+    uint64_t key[KC_U], base[KC_U], cur[KC_U], slot[KC_U];
+    bool done[KC_U];
+#pragma unroll
+    for (int u = 0; u < KC_U; u++) {
+        const bool active = item0 + u < K;
+        key[u] = active ? __ldg(fp + item0 + u) : 0;
+        base[u] = ((key[u] * 0x9e3779b97f4a7c15ULL) >> 17) & cap_mask & ~3ull;
+        done[u] = !active;
+        slot[u] = 0;
+    }
+#pragma unroll
+    for (int u = 0; u < KC_U; u++) cur[u] = done[u] ? 0 : *reinterpret_cast<volatile uint64_t*>(keys + base[u] + sub);
+    uint32_t m_match[KC_U], m_empty[KC_U], leader[KC_U];
+    uint64_t old[KC_U];
+#pragma unroll
+    for (int u = 0; u < KC_U; u++) {
+        m_match[u] = (__ballot_sync(0xffffffffu, !done[u] && cur[u] == key[u]) >> gbase) & 0xFu;
+        m_empty[u] = (__ballot_sync(0xffffffffu, !done[u] && cur[u] == KC_EMPTY) >> gbase) & 0xFu;
+        leader[u] = m_empty[u] ? (uint32_t)__ffs(m_empty[u]) - 1 : 0;
+        old[u] = 0;
+        if (!done[u] && !m_match[u] && m_empty[u] && sub == leader[u])
+            old[u] = atomicCAS(reinterpret_cast<unsigned long long*>(keys + base[u] + leader[u]), KC_EMPTY, key[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < KC_U; u++) {
+        old[u] = shfl64(old[u], (int)(gbase + leader[u]));
+        if (!done[u]) {
+            if (m_match[u]) { slot[u] = base[u] + (uint32_t)__ffs(m_match[u]) - 1; done[u] = true; }
+            else if (m_empty[u]) {
+                if (old[u] == KC_EMPTY || old[u] == key[u]) { slot[u] = base[u] + leader[u]; done[u] = true; }
                 // else: somebody else took that slot for another key; look at the window again
-            } else base = (base + 4) & cap_mask;
+            } else base[u] = (base[u] + 4) & cap_mask;
         }
     }
-    if (active && sub == 0) {
-        atomicMin(first + slot, (uint32_t)item);
-        slot_out[item] = (uint32_t)slot;
+    // what is left (a full window, a lost race): the same steps, one key at a time
+#pragma unroll
+    for (int u = 0; u < KC_U; u++) {
+        while (__any_sync(0xffffffffu, !done[u])) {
+            const uint64_t c = done[u] ? 0 : *reinterpret_cast<volatile uint64_t*>(keys + base[u] + sub);
+            const uint32_t mm = (__ballot_sync(0xffffffffu, !done[u] && c == key[u]) >> gbase) & 0xFu;
+            const uint32_t me = (__ballot_sync(0xffffffffu, !done[u] && c == KC_EMPTY) >> gbase) & 0xFu;
+            const uint32_t ld = me ? (uint32_t)__ffs(me) - 1 : 0;
+            uint64_t o = 0;
+            if (!done[u] && !mm && me && sub == ld)
+                o = atomicCAS(reinterpret_cast<unsigned long long*>(keys + base[u] + ld), KC_EMPTY, key[u]);
+            o = shfl64(o, (int)(gbase + ld));
+            if (!done[u]) {
+                if (mm) { slot[u] = base[u] + (uint32_t)__ffs(mm) - 1; done[u] = true; }
+                else if (me) {
+                    if (o == KC_EMPTY || o == key[u]) { slot[u] = base[u] + ld; done[u] = true; }
+                } else base[u] = (base[u] + 4) & cap_mask;
+            }
+        }
     }
+#pragma unroll
+    for (int u = 0; u < KC_U; u++)
+        if (item0 + u < K && sub == (uint32_t)u % 4u) {
+            atomicMin(first + slot[u], (uint32_t)(item0 + u));
+            slot_out[item0 + u] = (uint32_t)slot[u];
+        }
 }
 
 // exactness: every record must carry the same TUPLE as the first record of its slot

@@ -64,6 +64,32 @@ def test_pack_matches_numpy(L, n, threads):
     assert np.array_equal(bad[:nt], exp_bad)
 
 
+@pytest.mark.parametrize("env", [{}, {"MDBG_PACK_NO_AVX512": "1"}, {"MDBG_PACK_NO_AVX2": "1"}])
+def test_every_byte_value_is_classified(env):
+    """All 256 byte values, one per tile, at every position of a 64-byte group: only A, C, G, T leave a tile clean
+    (AVX-512, AVX2 and SSSE3/scalar code paths: the dispatch is cached per process, hence the subprocess)."""
+    code = r"""
+import sys, numpy as np
+sys.path.insert(0, @ROOT@)
+import rust_mdbg_b200
+L = rust_mdbg_b200.ffi.lib()
+for shift in (0, 1, 15, 16, 31, 32, 33, 63):
+    n = 256 * 4096
+    b = np.full(n, ord("A"), np.uint8)
+    b[1::2] = ord("G"); b[2::5] = ord("C"); b[3::7] = ord("T")
+    pos = np.arange(256) * 4096 + 1024 + shift
+    b[pos] = np.arange(256, dtype=np.uint8)
+    planes = np.zeros(2 * (n // 32) + 2, np.uint32); bad = np.zeros(257, np.uint8)
+    assert L.mdbg_pack_bases_host(b.ctypes.data, n, planes.ctypes.data, bad.ctypes.data, 2) == 0
+    exp = np.ones(256, np.uint8); exp[[ord(c) for c in "ACGT"]] = 0
+    assert np.array_equal(bad[:256], exp), (shift, np.nonzero(bad[:256] != exp)[0])
+    assert planes[2 * (pos[65] // 32)] >> (pos[65] % 32) & 1 == 0 and planes[2 * (pos[67] // 32)] >> (pos[67] % 32) & 1 == 1
+print("ok")
+""".replace("@ROOT@", repr(ROOT))
+    r = subprocess.run([os.sys.executable, "-c", code], capture_output=True, text=True, env={**os.environ, **env}, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), (r.stdout[-500:], r.stderr[-2000:])
+
+
 def test_expand_is_the_inverse(model):
     codes = "ACTG"
     for a in range(16):
