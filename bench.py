@@ -385,6 +385,45 @@ def main():
                # the graph built from the host buffers (packed / hybrid upload) against the device-resident one
                "counts_equal_device_resident": counts_equal,
                "stage_ms_per_step": {k_: v_ / steps for k_, v_ in e2e_parts.items()}}
+        # the same reads handed over as the caller's own 2-bit planes (mdbg_push_reads_packed): what the path does when
+        # the host keeps reads packed -- 0.25 B/base over PCIe, no packing inside the call.  Reported next to `e2e`
+        # (whose input is the reference's: ASCII), never instead of it.
+        if world == 1 and not args.no_extra:
+            n_words = (total + 31) // 32
+            hp = ctx.host_alloc_pinned(8 * n_words + 64)
+            rc = m.ffi.lib().mdbg_pack_bases_host(hb, total, hp, None, min(32, os.cpu_count() or 1))
+            assert rc == 0
+            pk_counts = {}
+            pk_parts = {"h2d": 0.0, "push": 0.0, "ka_done": 0.0, "finish": 0.0, "d2h": 0.0}
+
+            def step_packed():
+                ctx.reset()
+                ctx.push_reads_packed_ptr(hp, ho, reads_per_rank)
+                cg = ctx.finish_raw(want_seqlines=False)
+                tm = ctx.timings()
+                pk_parts["h2d"] += tm["ms_h2d"]; pk_parts["push"] += tm["ms_total_push"]; pk_parts["ka_done"] += tm["ms_ka"]
+                pk_parts["finish"] += tm["ms_total_finish"]; pk_parts["d2h"] += tm["ms_d2h"]
+                pk_counts.update(n_minimizers=int(cg.n_minimizers), n_kminmers=int(cg.n_kminmers),
+                                 n_distinct=int(cg.n_distinct), n_nodes=int(cg.n_nodes), n_edges=int(cg.n_edges))
+                ctx.graph_free(cg)
+
+            for _ in range(max(1, warmup)):
+                step_packed()
+            ctx.sync()
+            for k_ in pk_parts:
+                pk_parts[k_] = 0.0
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                step_packed()
+            ctx.sync()
+            pk_ms = (time.perf_counter() - t0) * 1e3
+            tm_pk = ctx.timings()
+            e2e["packed_input"] = {"value": bases_all * steps / (pk_ms * 1e-3) / 1e9, "unit": "Gbases/s",
+                                   "ms_per_step": pk_ms / steps, "stage_ms_per_step": {k_: v_ / steps for k_, v_ in pk_parts.items()},
+                                   "h2d_bytes_per_step": int(tm_pk["upload_h2d_bytes"]) + 8 * (reads_per_rank + 1),
+                                   "input": "the caller's 2-bit planes in pinned host memory (mdbg_push_reads_packed), 0.25 B/base",
+                                   "counts_equal_device_resident": all(int(stats[k_]) == v_ for k_, v_ in pk_counts.items())}
+            ctx.host_free_pinned(hp)
         ctx.host_free_pinned(hb); ctx.host_free_pinned(ho)
 
     # ------------------------------------------------------------------ N>1: the N-GPU graph == the 1-GPU graph

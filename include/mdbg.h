@@ -114,6 +114,13 @@ int mdbg_window(mdbg_ctx* ctx, const uint64_t* hash, const uint64_t* pos,
  * edge join + presimp; results under SERIAL-ORDER semantics.               */
 int mdbg_push_reads(mdbg_ctx* ctx, const uint8_t* bases, const uint64_t* read_off,
                     uint64_t n_reads);
+/* Same for a host that keeps its reads 2-bit packed (or packs while it parses: mdbg_pack_bases_host below):
+ * planes[2w], planes[2w+1] = bit planes of the 32 bases [32w, 32w+32) of the concatenated reads, read_off as
+ * above (in bases).  Only A, C, G, T can be said this way (a batch holding anything else goes through
+ * mdbg_push_reads); bases past read_off[n_reads] in the last word are ignored.  A quarter of the bytes cross
+ * PCIe and no host core packs inside the call; results are those of mdbg_push_reads on the same bases.     */
+int mdbg_push_reads_packed(mdbg_ctx* ctx, const uint32_t* planes, const uint64_t* read_off,
+                           uint64_t n_reads);
 /* Same with inputs already resident in this context's device memory (16-byte aligned). */
 int mdbg_push_reads_device(mdbg_ctx* ctx, const uint8_t* d_bases, const uint64_t* d_read_off,
                            uint64_t n_reads, uint64_t n_bases);

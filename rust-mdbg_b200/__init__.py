@@ -2,7 +2,7 @@
 ekimb/rust-mdbg behind the reference's Read / minimizers / KmerVec module surface.
 All compute is in libmdbg_b200.so (hand-written CUDA behind the C ABI of include/mdbg.h)."""
 from . import ffi, minimizers
-from .engine import Context, Graph, Params, Synth, nccl_unique_id
+from .engine import Context, Graph, Params, Synth, nccl_unique_id, pack_bases
 from .ffi import MdbgError
 from .kmer_vec import KmerVec
 from .read import Read

@@ -415,11 +415,10 @@ int mdbg_push_reads_device(mdbg_ctx* c, const uint8_t* d_bases, const uint64_t* 
     return MDBG_OK;
 }
 
-int mdbg_push_reads(mdbg_ctx* c, const uint8_t* bases, const uint64_t* read_off, uint64_t n_reads) {
-    if (!c || !read_off || (n_reads && !bases && read_off[n_reads] != 0)) {
-        if (c) c->err = "null argument";
-        return MDBG_ERR_BAD_ARG;
-    }
+// Host buffers -> device -> K-A.  Exactly one of `bases` (ASCII, 1 B/base) and `host_planes` (the caller's own 2-bit
+// planes, mdbg_push_reads_packed) describes the reads.
+static int push_host(mdbg_ctx* c, const uint8_t* bases, const uint32_t* host_planes, const uint64_t* read_off,
+                     uint64_t n_reads) {
     MDBG_CK(c, cudaSetDevice(c->device));
     uint64_t B = read_off[n_reads];
     for (uint64_t r = 0; r < n_reads; r++) {
@@ -433,13 +432,15 @@ int mdbg_push_reads(mdbg_ctx* c, const uint8_t* bases, const uint64_t* read_off,
     Tmp<uint8_t> d_bases;
     Tmp<uint64_t> d_off;
     Tmp<uint32_t> d_planes;
-    const bool packed = c->upload_packed && B > 0;
+    const bool packed = (c->upload_packed || host_planes) && B > 0;
     MDBG_CK(c, d_bases.get(c->pool, B + 64));
     MDBG_CK(c, d_off.get(c->pool, n_reads + 1));
     MDBG_CK(c, cudaEventRecord(c->ev[2], c->st));
-    // Upload in ~32 MB chunks cut at read starts on a second stream; K-A runs on the tiles whose
+    // Upload in 32-128 MB chunks cut at read starts on a second stream; K-A runs on the tiles whose
     // bytes have arrived, so the kernel hides behind the PCIe copy (pinned host memory).
-    uint64_t CH = 32ull << 20;
+    // (a chunk costs ~10 driver calls, a worker-pool round and one K-A launch: 32 MB for batches up to 2 GB, then
+    // B / 64 up to 128 MB -- measured at config 3: 97.5 / 101.6 / 103.3 / 91.8 Gbases/s end to end at 32 / 64 / 128 / 256 MB)
+    uint64_t CH = std::min<uint64_t>(128ull << 20, std::max<uint64_t>(32ull << 20, (B / 64) >> 20 << 20));
     if (const char* e = getenv("MDBG_UPLOAD_CHUNK_MB")) { long v = atol(e); if (v >= 1 && v <= 4096) CH = (uint64_t)v << 20; }
     std::vector<KaChunk> plan;
     const uint64_t n_tiles = std::max<uint64_t>(1, (B + KA_TILE - 1) / KA_TILE);
@@ -458,9 +459,12 @@ int mdbg_push_reads(mdbg_ctx* c, const uint8_t* bases, const uint64_t* read_off,
     std::vector<uint8_t> bad_tiles;
     // words per chunk of the packed / hybrid upload: a quarter of the ASCII chunk (8 MB of bases by default)
     uint64_t CHW = std::max<uint64_t>(2 * PACK_TILE_WORDS, (CH / 4 / 32) / PACK_TILE_WORDS * PACK_TILE_WORDS);
+    // the caller's own planes need no packing pipeline: chunks of CH bytes of planes (128 Mbases by default), so that
+    // a chunk's K-A launch fills the GPU and the host enqueues ~50 instead of ~900 chunks per 7 Gbases
+    if (host_planes) CHW = std::max<uint64_t>(2 * PACK_TILE_WORDS, (CH / 8) / PACK_TILE_WORDS * PACK_TILE_WORDS);
     std::function<int(size_t)> prepare;
     if (packed) {
-        if (!c->pack_pool) {
+        if (!host_planes && !c->pack_pool) {
             unsigned hw = std::max<unsigned>(1, std::thread::hardware_concurrency());
             if (const char* e = getenv("LOCAL_WORLD_SIZE")) { long v = atol(e); if (v >= 1 && v <= 64) hw = std::max<unsigned>(4, hw / (unsigned)v); }
             int nt = (int)std::min<unsigned>(32, hw);   // one process per GPU: share the host cores between the ranks
@@ -470,7 +474,7 @@ int mdbg_push_reads(mdbg_ctx* c, const uint8_t* bases, const uint64_t* read_off,
         // pinned staging: a ring of UPLOAD_SLOTS chunk-sized slots (a slot is reused once the copy that read
         // it has completed), not a second copy of the batch
         const uint64_t n_chunks = (n_words + CHW - 1) / CHW;
-        const size_t need = (size_t)std::min<uint64_t>(n_chunks, UPLOAD_SLOTS) * CHW * 8;
+        const size_t need = host_planes ? 0 : (size_t)std::min<uint64_t>(n_chunks, UPLOAD_SLOTS) * CHW * 8;
         if (c->h_planes_cap < need) {
             if (c->h_planes) cudaFreeHost(c->h_planes);
             c->h_planes = nullptr; c->h_planes_cap = 0;
@@ -498,11 +502,11 @@ int mdbg_push_reads(mdbg_ctx* c, const uint8_t* bases, const uint64_t* read_off,
         // has work for the time the cores need to pack the next chunks.  MDBG_UPLOAD=packed packs everything.
         // The decision is made on a host-side model of the engine's backlog: bytes queued so far at the link
         // rate (MDBG_PCIE_GBPS, default 50) against the measured packing time of a chunk.
-        const bool hybrid = c->upload_hybrid;
+        const bool hybrid = c->upload_hybrid && !host_planes;
         double link_rate = 50e9;
         if (const char* e = getenv("MDBG_PCIE_GBPS")) { double v = atof(e); if (v >= 1 && v <= 1000) link_rate = v * 1e9; }
         double ascii_rate = link_rate;   // pageable source: the driver stages ASCII chunks through its own pinned buffer
-        {
+        if (bases) {
             cudaPointerAttributes pa{};
             if (cudaPointerGetAttributes(&pa, bases) != cudaSuccess) (void)cudaGetLastError();
             else if (pa.type == cudaMemoryTypeUnregistered) ascii_rate = std::min(link_rate, 12e9);
@@ -518,6 +522,15 @@ int mdbg_push_reads(mdbg_ctx* c, const uint8_t* bases, const uint64_t* read_off,
         prepare = [&, n_words, CHW, hybrid, link_rate, ascii_rate, pack_s_per_byte, t_first, cum_enq, cum_done, done_ptr, enq,
                    now_s](size_t ci) mutable -> int {
             const uint64_t wa = (uint64_t)ci * CHW, wb = std::min(n_words, wa + CHW);
+            if (host_planes) {         // the caller packed already: the planes of the chunk go as they are
+                c->tm.upload_h2d_bytes += (wb - wa) * 8;
+                MDBG_CK(c, cudaMemcpyAsync(d_planes.p + 2 * wa, host_planes + 2 * wa, (wb - wa) * 8, cudaMemcpyHostToDevice, c->st_copy));
+                MDBG_CK(c, cudaEventRecord(c->copy_ev[ci], c->st_copy));
+                if (wb == n_words) MDBG_CK(c, cudaEventRecord(c->ev[4], c->st_copy));
+                MDBG_CK(c, cudaStreamWaitEvent(c->st, c->copy_ev[ci], 0));
+                MDBG_CK(c, expand_planes(d_planes.p, d_bases.p, wa, wb, c->num_sms, c->st, &c->tm.launches_push));
+                return MDBG_OK;
+            }
             // this chunk's slot of the staging ring, addressed as if the ring were the whole batch
             uint32_t* hp = reinterpret_cast<uint32_t*>(reinterpret_cast<uintptr_t>(c->h_planes) +
                                                        8 * ((ci % UPLOAD_SLOTS) * CHW) - 8 * wa);
@@ -594,7 +607,7 @@ int mdbg_push_reads(mdbg_ctx* c, const uint8_t* bases, const uint64_t* read_off,
     if (plan.empty()) plan.push_back(KaChunk{n_tiles, nullptr});
     if (!packed) MDBG_CK(c, cudaEventRecord(c->ev[4], c->st_copy));
     int rc = run_ka(c, d_bases, d_off, n_reads, B, &plan, packed ? &prepare : nullptr);
-    if (rc == MDBG_ERR_ALPHABET) {  // turn the batch offset into (read, offset) like SURVEY 5 asks
+    if (rc == MDBG_ERR_ALPHABET && bases) {  // turn the batch offset into (read, offset) like SURVEY 5 asks
         uint64_t pos = c->h_sc->err_pos;
         uint64_t r = std::upper_bound(read_off, read_off + n_reads + 1, pos) - read_off - 1;
         char buf[200];
@@ -610,6 +623,22 @@ int mdbg_push_reads(mdbg_ctx* c, const uint8_t* bases, const uint64_t* read_off,
     cudaEventElapsedTime(&c->tm.ms_total_push, c->ev[2], c->ev[3]);
     cudaEventElapsedTime(&c->tm.ms_ka_start, c->ev[2], c->ev[0]);
     return MDBG_OK;
+}
+
+int mdbg_push_reads(mdbg_ctx* c, const uint8_t* bases, const uint64_t* read_off, uint64_t n_reads) {
+    if (!c || !read_off || (n_reads && !bases && read_off[n_reads] != 0)) {
+        if (c) c->err = "null argument";
+        return MDBG_ERR_BAD_ARG;
+    }
+    return push_host(c, bases, nullptr, read_off, n_reads);
+}
+
+int mdbg_push_reads_packed(mdbg_ctx* c, const uint32_t* planes, const uint64_t* read_off, uint64_t n_reads) {
+    if (!c || !read_off || (n_reads && !planes && read_off[n_reads] != 0)) {
+        if (c) c->err = "null argument";
+        return MDBG_ERR_BAD_ARG;
+    }
+    return push_host(c, nullptr, planes, read_off, n_reads);
 }
 
 int mdbg_get_minimizers(mdbg_ctx* c, uint64_t* hash, uint64_t* pos, uint64_t* read_off, uint64_t cap,

@@ -147,6 +147,18 @@ class Context:
         self._ck(self.L.mdbg_push_reads(self.h, bases_ptr, read_off_ptr, n_reads))
         self.n_reads += n_reads
 
+    def push_reads_packed(self, planes, read_off):
+        """Reads the host already holds as 2-bit planes (pack_bases): a quarter of the PCIe bytes, no packing inside."""
+        pl = np.ascontiguousarray(planes, dtype=np.uint32)
+        ro = np.ascontiguousarray(read_off, dtype=np.uint64)
+        assert len(pl) >= 2 * ((int(ro[-1]) + 31) // 32)
+        self._ck(self.L.mdbg_push_reads_packed(self.h, ptr(pl), ptr(ro), len(ro) - 1))
+        self.n_reads += len(ro) - 1
+
+    def push_reads_packed_ptr(self, planes_ptr, read_off_ptr, n_reads):
+        self._ck(self.L.mdbg_push_reads_packed(self.h, planes_ptr, read_off_ptr, n_reads))
+        self.n_reads += n_reads
+
     def push_reads_device(self, d_bases, d_read_off, n_reads, n_bases):
         self._ck(self.L.mdbg_push_reads_device(self.h, d_bases, d_read_off, n_reads, n_bases))
         self.n_reads += n_reads
@@ -261,6 +273,20 @@ class Context:
 
     def set_read_base(self, first_read):
         self._ck(self.L.mdbg_comm_set_read_base(self.h, first_read))
+
+
+def pack_bases(bases, threads=8):
+    """2-bit planes of a buffer of bases (mdbg_pack_bases_host): (planes u32[2 * ceil(n / 32)], bad_tiles u8[ceil(n / 4096)]);
+    bad_tiles[t] = 1 when tile t holds a byte outside ACGT (such a batch cannot be pushed packed)."""
+    b = as_u8(bases)
+    n = len(b)
+    planes = np.zeros(2 * ((n + 31) // 32), np.uint32)
+    bad = np.zeros((n + 4095) // 4096 + 1, np.uint8)
+    if n:
+        rc = ffi.lib().mdbg_pack_bases_host(ptr(b), n, ptr(planes), ptr(bad), int(threads))
+        if rc != 0:
+            raise MdbgError(rc, "mdbg_pack_bases_host")
+    return planes, bad[:(n + 4095) // 4096]
 
 
 def nccl_unique_id():

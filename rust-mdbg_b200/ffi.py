@@ -77,6 +77,7 @@ SYMBOLS = {
     "mdbg_kminmer_cmp": (ctypes.c_int, [vp, vp, u32]),
     "mdbg_window": (ctypes.c_int, [vp, vp, vp, vp, u64, vp, vp, vp, vp, vp, u64, ctypes.POINTER(u64)]),
     "mdbg_push_reads": (ctypes.c_int, [vp, vp, vp, u64]),
+    "mdbg_push_reads_packed": (ctypes.c_int, [vp, vp, vp, u64]),
     "mdbg_push_reads_device": (ctypes.c_int, [vp, vp, vp, u64, u64]),
     "mdbg_reset": (ctypes.c_int, [vp]),
     "mdbg_finish": (ctypes.c_int, [vp, ctypes.c_int, GP]),

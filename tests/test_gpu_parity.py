@@ -410,3 +410,79 @@ def test_upload_modes_equal_oracle(mdbg, oracle, mode, gbps, monkeypatch):
     o = oracle.build_graph(bases, off, k, l, d, 2, 0.01)
     assert np.array_equal(h, o.m_hash) and np.array_equal(p, o.m_pos) and np.array_equal(mo, o.m_off)
     compare_graph(g, o, check_seqlines=False)
+
+
+@pytest.mark.parametrize("chunk_mb", ["1", None])
+def test_push_reads_packed_equals_oracle(mdbg, oracle, chunk_mb, monkeypatch):
+    """mdbg_push_reads_packed: the caller's own 2-bit planes (mdbg_pack_bases_host) instead of ASCII bases -- same
+    minimizers and graph as the oracle on the bases they encode; a quarter of the bytes cross PCIe.  Two pushes
+    (the second one starts in the middle of a plane word of the first batch's length), homopolymers across chunk
+    boundaries, tiny and empty reads, a batch whose length is no multiple of 32."""
+    if chunk_mb:
+        monkeypatch.setenv("MDBG_UPLOAD_CHUNK_MB", chunk_mb)
+    else:
+        monkeypatch.delenv("MDBG_UPLOAD_CHUNK_MB", raising=False)
+    rng = np.random.default_rng(78)
+    seqs = genome_reads(rng, 150000, 200, mean=9000, sd=3000, err=0.002)
+    seqs[40] = b"A" * 300000 + seqs[40]
+    seqs[100:100] = [b"", b"ACGT", b"T" * 9000, b"G"]
+    half = len(seqs) // 2
+    b0, o0 = pack_reads(seqs[:half])
+    b1, o1 = pack_reads(seqs[half:] + [b"ACGTTGCAAC" * 3 + b"A"])
+    assert len(b0) % 32 != 0 and len(b1) % 32 != 0
+    k, l, d = 8, 12, 0.003
+    with mdbg.Context(mdbg.Params(k=k, l=l, density=d, min_abundance=2, presimp=0.01)) as ctx:
+        for b, o in ((b0, o0), (b1, o1)):
+            planes, bad = mdbg.pack_bases(b, threads=4)
+            assert not bad.any()
+            ctx.push_reads_packed(planes, o)
+            tm = ctx.timings()
+            assert tm["upload_packed"] == 1 and tm["upload_ascii_tiles"] == 0
+            assert tm["upload_h2d_bytes"] == 8 * ((len(b) + 31) // 32)
+        h, p, mo = ctx.get_minimizers()
+        g = ctx.finish()
+    bases, off = pack_reads(seqs + [b"ACGTTGCAAC" * 3 + b"A"])
+    o = oracle.build_graph(bases, off, k, l, d, 2, 0.01)
+    assert np.array_equal(h, o.m_hash) and np.array_equal(p, o.m_pos) and np.array_equal(mo, o.m_off)
+    compare_graph(g, o, check_seqlines=False)
+
+
+def test_push_reads_packed_degenerate(mdbg):
+    with mdbg.Context(mdbg.Params(k=5, l=12, density=0.003)) as ctx:
+        ctx.push_reads_packed(np.zeros(0, np.uint32), np.zeros(1, np.uint64))            # no reads
+        ctx.push_reads_packed(np.zeros(0, np.uint32), np.zeros(4, np.uint64))            # three empty reads
+        planes, _ = mdbg.pack_bases(np.frombuffer(b"ACGTT", np.uint8))
+        ctx.push_reads_packed(planes, np.array([0, 5], np.uint64))                        # shorter than l
+        h, p, mo = ctx.get_minimizers()
+        assert len(h) == 0 and list(mo) == [0, 0, 0, 0, 0]
+        with pytest.raises(mdbg.MdbgError):
+            ctx.push_reads_packed(planes, np.array([0, 5, 3], np.uint64))                 # offsets must not decrease
+
+
+def test_push_argument_limits(mdbg):
+    """The documented limits of a push are refused before any byte is touched: offsets that decrease, a record of
+    4 Gbases or more (positions inside a read are u32 on the device) -- on the host entries and, checked by a kernel,
+    on the device-resident entry."""
+    small = np.frombuffer(b"ACGT" * 64, np.uint8).copy()
+    with mdbg.Context(mdbg.Params(k=5, l=12, density=0.003)) as ctx:
+        planes = mdbg.pack_bases(small)[0]
+        for ro in ([0, 200, 100], [0, 1 << 32], [0, 100, (1 << 32) + 200]):
+            o = np.array(ro, np.uint64)
+            for push in (lambda: ctx.push_reads(small, o),
+                         lambda: ctx.push_reads_packed_ptr(mdbg.ffi.ptr(planes), mdbg.ffi.ptr(o), len(ro) - 1)):
+                with pytest.raises(mdbg.MdbgError) as ei:
+                    push()
+                assert ei.value.code in (-3, -6)              # MDBG_ERR_BAD_ARG / MDBG_ERR_RANGE
+        d_b = ctx.device_malloc(4096); d_o = ctx.device_malloc(64)
+        ctx.h2d(d_b, small)
+        for ro, n_bases in (([0, 200, 100], 100), ([0, 128, 200], 256), ([0, 1 << 32], 1 << 32)):
+            ctx.h2d(d_o, np.array(ro, np.uint64))
+            with pytest.raises(mdbg.MdbgError) as ei:
+                ctx.push_reads_device(d_b, d_o, len(ro) - 1, n_bases)
+            assert ei.value.code in (-3, -6)
+        # the context is still usable
+        ctx.push_reads(small, np.array([0, 256], np.uint64))
+        h, p, mo = ctx.get_minimizers()
+        assert list(mo)[0] == 0 and len(mo) == 2
+        ctx.device_free(d_b); ctx.device_free(d_o)
+
