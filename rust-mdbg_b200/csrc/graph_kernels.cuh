@@ -635,28 +635,39 @@ constexpr uint32_t KE_LANES = 8;
 __device__ __forceinline__ uint32_t ke_compare(const uint64_t* __restrict__ t1, const uint64_t* __restrict__ t2,
                                                const uint64_t* __restrict__ qsub, bool qrev,
                                                const uint64_t* __restrict__ esub, bool er, uint32_t k,
-                                               uint32_t sub, uint32_t gmask) {
+                                               uint32_t sub, uint32_t gmask, bool own_entry) {
     const uint32_t k1 = k - 1;
     uint32_t ok = 31u;
+    // six streams walked with a stride of +-1 element: base pointers and directions are fixed before the loop
+    const uint64_t* qp = (qrev ? qsub + (k1 - 1) : qsub) + (qrev ? -(int64_t)sub : (int64_t)sub);
+    const uint64_t* ep = (er ? esub + (k1 - 1) : esub) + (er ? -(int64_t)sub : (int64_t)sub);
+    const int64_t qs = qrev ? -(int64_t)KE_LANES : (int64_t)KE_LANES, es = er ? -(int64_t)KE_LANES : (int64_t)KE_LANES;
+    const uint64_t* a1p = t1 + 1 + sub;
+    const uint64_t* a2p = t1 + k - 2 - sub;
+    const uint64_t* c1p = t2 + sub;
+    const uint64_t* c2p = t2 + k - 1 - sub;
     for (uint32_t base = 0; base < k1; base += KE_LANES) {   // same trip count for every lane of the group
         const uint32_t j = base + sub;
         if (j < k1) {
-            const uint64_t qa = __ldg(qrev ? qsub + (k1 - 1 - j) : qsub + j);
-            const uint64_t ea = __ldg(er ? esub + (k1 - 1 - j) : esub + j);
-            const uint64_t a1 = __ldg(t1 + 1 + j), a2 = __ldg(t1 + k - 2 - j);
-            const uint64_t c1 = __ldg(t2 + j), c2 = __ldg(t2 + k - 1 - j);
+            const uint64_t qa = __ldg(qp), ea = __ldg(ep);
+            const uint64_t a1 = __ldg(a1p), a2 = __ldg(a2p);
+            const uint64_t c1 = __ldg(c1p), c2 = __ldg(c2p);
             if (qa != ea) ok &= ~1u;
             if (a1 != c1) ok &= ~2u;
             if (a1 != c2) ok &= ~4u;
             if (a2 != c1) ok &= ~8u;
             if (a2 != c2) ok &= ~16u;
         }
+        qp += qs; ep += es; a1p += KE_LANES; a2p -= KE_LANES; c1p += KE_LANES; c2p -= KE_LANES;
         if (base == 0) {   // after the first 8 elements almost every foreign key is known: leave together
             uint32_t r = ok;
             r &= __shfl_xor_sync(gmask, r, 1);
             r &= __shfl_xor_sync(gmask, r, 2);
             r &= __shfl_xor_sync(gmask, r, 4);
             if ((r & 1u) == 0u) return 0u;
+            // the query's own entry (every bucket holds it): the key is equal by construction, and a node is joined to
+            // itself only if one of the four identities survives the first 8 elements (a periodic tuple)
+            if (own_entry && (r & 30u) == 0u) return 1u;
         }
     }
     ok &= __shfl_xor_sync(gmask, ok, 1);
@@ -683,7 +694,8 @@ __global__ void ke_join_kernel(NodeView N, const uint64_t* __restrict__ ekey, co
     uint32_t qe = 2 * n1 + (which == 0 ? 1 : 0);  // which 0: suffix entry, 1: prefix entry
     uint64_t kf = ekey[qe];
     // bucket [b0, b1) of equal fingerprints around the query's own entry in the sorted list
-    uint32_t b0 = inv[qe], b1 = b0 + 1;
+    const uint32_t own = inv[qe];
+    uint32_t b0 = own, b1 = b0 + 1;
     while (b0 > 0 && skey[b0 - 1] == kf) b0--;
     while (b1 < 2 * S && skey[b1] == kf) b1++;
     const uint64_t* t1 = N.tuple + (uint64_t)n1 * k;
@@ -706,7 +718,7 @@ __global__ void ke_join_kernel(NodeView N, const uint64_t* __restrict__ ekey, co
             uint32_t t;
             if (pass == 1 && e - b0 < 12) t = (uint32_t)(cache >> (5 * (e - b0))) & 31u;
             else {
-                t = ke_compare(t1, t2, qsub, qrev, t2 + (ent & 1), erev[ent] != 0, k, sub, gmask);
+                t = ke_compare(t1, t2, qsub, qrev, t2 + (ent & 1), erev[ent] != 0, k, sub, gmask, e == own);
                 if (pass == 0 && e - b0 < 12) cache |= (uint64_t)t << (5 * (e - b0));
             }
             if (!(t & 1u)) continue;   // another (k-1)-mer in the same fingerprint bucket

@@ -1,3 +1,5 @@
+#!/bin/bash
+# Eight-GPU runs behind profiles/r02_bench_n8_* (gpurun --gpus 8): multi_gpu_check, dmel50x shards, human52x_per8 + multi-k sweep
 mkdir -p gpurun_out/r2o
 T="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1"
 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29540 tests/multi_gpu_check.py > gpurun_out/r2o/mgpu8.log 2>&1; echo rc=$? >> gpurun_out/r2o/mgpu8.log
