@@ -514,14 +514,47 @@ static int push_host(mdbg_ctx* c, const uint8_t* bases, const uint32_t* host_pla
         // The engine's backlog is OBSERVED, not modelled: bytes enqueued minus bytes of the chunks whose copy event
         // has completed, divided by the rate the completed chunks have actually moved at (several ranks share the
         // host's memory system and PCIe switches: the link gives half its nominal rate with 8 uploading ranks).
-        double pack_s_per_byte = 1.0 / 40e9, t_first = -1.0;
-        uint64_t cum_enq = 0, cum_done = 0;
-        size_t done_ptr = 0;
-        std::vector<uint64_t> enq(n_chunks, 0);
+        // (the state of the upload lives on the heap: `prepare` is called by run_ka after this block has ended)
+        struct Up {
+            std::vector<uint8_t> mode;                     // per chunk: 0 undecided, 1 ASCII, 2 packed
+            std::vector<double> t_pack;                    // when the chunk's packing began
+            std::vector<uint64_t> enq;                     // bytes the chunk puts on the link
+            size_t n_enqueued = 0, done_ptr = 0;           // chunks whose copy event has been recorded in THIS push / seen complete
+            uint64_t cum_enq = 0, cum_done = 0;
+            double pack_s_per_byte = 1.0 / 40e9, t_first = -1.0;
+        };
+        auto up = std::make_shared<Up>();
+        up->mode.assign(n_chunks, 0); up->t_pack.assign(n_chunks, 0.0); up->enq.assign(n_chunks, 0);
         auto now_s = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-        prepare = [&, n_words, CHW, hybrid, link_rate, ascii_rate, pack_s_per_byte, t_first, cum_enq, cum_done, done_ptr, enq,
-                   now_s](size_t ci) mutable -> int {
-            const uint64_t wa = (uint64_t)ci * CHW, wb = std::min(n_words, wa + CHW);
+        // A chunk is decided (ASCII or packed) one chunk AHEAD: a packed chunk starts packing on the workers at once
+        // (PackPool::begin), the calling thread enqueues the copies and kernels of the previous chunk meanwhile and
+        // joins the packing afterwards (PackPool::finish) -- the ~10 driver calls per chunk no longer stop 16 cores.
+        auto chunk_words = [n_words, CHW](size_t ci, uint64_t& wa, uint64_t& wb) { wa = (uint64_t)ci * CHW; wb = std::min(n_words, wa + CHW); };
+        auto slot_of = [c, CHW](size_t ci, uint64_t wa) {   // the chunk's slot of the staging ring, addressed as if the ring were the whole batch
+            return reinterpret_cast<uint32_t*>(reinterpret_cast<uintptr_t>(c->h_planes) + 8 * ((ci % UPLOAD_SLOTS) * CHW) - 8 * wa);
+        };
+        auto decide = [&, up, hybrid, link_rate, ascii_rate, now_s, chunk_words, slot_of](size_t ci) -> int {
+            uint64_t wa, wb;
+            chunk_words(ci, wa, wb);
+            const uint64_t chunk_bytes = std::min<uint64_t>(B, wb * 32) - wa * 32;
+            const double t_dec = now_s();
+            while (up->done_ptr < up->n_enqueued && cudaEventQuery(c->copy_ev[up->done_ptr]) == cudaSuccess) up->cum_done += up->enq[up->done_ptr++];
+            (void)cudaGetLastError();   // cudaErrorNotReady is not an error
+            double rate = std::min(link_rate, ascii_rate);
+            if (up->t_first >= 0 && up->cum_done >= (32u << 20) && t_dec > up->t_first)
+                rate = std::min(rate, std::max(2e9, (double)up->cum_done / (t_dec - up->t_first)));
+            const double backlog = (double)(up->cum_enq - up->cum_done) / rate;
+            if (up->t_first < 0) up->t_first = t_dec;
+            if (hybrid && backlog < up->pack_s_per_byte * (double)chunk_bytes) { up->mode[ci] = 1; return MDBG_OK; }   // the engine would run dry while we pack
+            up->mode[ci] = 2;
+            if (ci >= UPLOAD_SLOTS) MDBG_CK(c, cudaEventSynchronize(c->copy_ev[ci - UPLOAD_SLOTS]));   // slot free again
+            up->t_pack[ci] = now_s();
+            pack_parallel_begin(*c->pack_pool, bases, B, wa, wb, slot_of(ci, wa), bad_tiles.data());
+            return MDBG_OK;
+        };
+        prepare = [&, up, decide, now_s, chunk_words, slot_of](size_t ci) -> int {
+            uint64_t wa, wb;
+            chunk_words(ci, wa, wb);
             if (host_planes) {         // the caller packed already: the planes of the chunk go as they are
                 c->tm.upload_h2d_bytes += (wb - wa) * 8;
                 MDBG_CK(c, cudaMemcpyAsync(d_planes.p + 2 * wa, host_planes + 2 * wa, (wb - wa) * 8, cudaMemcpyHostToDevice, c->st_copy));
@@ -531,39 +564,32 @@ static int push_host(mdbg_ctx* c, const uint8_t* bases, const uint32_t* host_pla
                 MDBG_CK(c, expand_planes(d_planes.p, d_bases.p, wa, wb, c->num_sms, c->st, &c->tm.launches_push));
                 return MDBG_OK;
             }
-            // this chunk's slot of the staging ring, addressed as if the ring were the whole batch
-            uint32_t* hp = reinterpret_cast<uint32_t*>(reinterpret_cast<uintptr_t>(c->h_planes) +
-                                                       8 * ((ci % UPLOAD_SLOTS) * CHW) - 8 * wa);
             const uint64_t chunk_bytes = std::min<uint64_t>(B, wb * 32) - wa * 32;
-            const double t_dec = now_s();
-            while (done_ptr < ci && cudaEventQuery(c->copy_ev[done_ptr]) == cudaSuccess) cum_done += enq[done_ptr++];
-            (void)cudaGetLastError();   // cudaErrorNotReady is not an error
-            double rate = std::min(link_rate, ascii_rate);
-            if (t_first >= 0 && cum_done >= (32u << 20) && t_dec > t_first)
-                rate = std::min(rate, std::max(2e9, (double)cum_done / (t_dec - t_first)));
-            const double backlog = (double)(cum_enq - cum_done) / rate;
-            if (t_first < 0) t_first = t_dec;
-            if (hybrid && backlog < pack_s_per_byte * (double)chunk_bytes) {   // the engine would run dry while we pack
+            if (up->mode[ci] == 0) { int rc = decide(ci); if (rc) return rc; }
+            if (up->mode[ci] == 2) {       // join the packing of this chunk and wait for the workers
+                c->pack_pool->finish();
+                const double per_byte = (now_s() - up->t_pack[ci]) / (double)std::max<uint64_t>(1, chunk_bytes);
+                up->pack_s_per_byte = 0.5 * up->pack_s_per_byte + 0.5 * per_byte;
+            }
+            up->enq[ci] = up->mode[ci] == 1 ? chunk_bytes : (wb - wa) * 8;
+            up->cum_enq += up->enq[ci];
+            if (ci + 1 < up->mode.size()) { int rc = decide(ci + 1); if (rc) return rc; }   // the next chunk packs while this one is enqueued
+            if (up->mode[ci] == 1) {
                 const uint64_t off = wa * 32, end = std::min<uint64_t>(B, wb * 32);
                 MDBG_CK(c, cudaMemcpyAsync(d_bases.p + off, bases + off, end - off, cudaMemcpyHostToDevice, c->st_copy));
                 MDBG_CK(c, cudaEventRecord(c->copy_ev[ci], c->st_copy));
                 if (wb == n_words) MDBG_CK(c, cudaEventRecord(c->ev[4], c->st_copy));
+                up->n_enqueued = ci + 1;
                 c->tm.upload_ascii_tiles += (uint32_t)((wb - wa + PACK_TILE_WORDS - 1) / PACK_TILE_WORDS);
                 c->tm.upload_h2d_bytes += end - off;
-                enq[ci] = end - off; cum_enq += end - off;
                 return MDBG_OK;        // run_ka makes the compute stream wait for copy_ev[ci]
             }
-            if (ci >= UPLOAD_SLOTS) MDBG_CK(c, cudaEventSynchronize(c->copy_ev[ci - UPLOAD_SLOTS]));   // slot free again
-            pack_parallel(*c->pack_pool, bases, B, wa, wb, hp, bad_tiles.data());
-            {
-                const double t_end = now_s(), per_byte = (t_end - t_dec) / (double)std::max<uint64_t>(1, chunk_bytes);
-                pack_s_per_byte = 0.5 * pack_s_per_byte + 0.5 * per_byte;
-            }
+            const uint32_t* hp = slot_of(ci, wa);
             c->tm.upload_h2d_bytes += (wb - wa) * 8;
-            enq[ci] = (wb - wa) * 8; cum_enq += (wb - wa) * 8;
             MDBG_CK(c, cudaMemcpyAsync(d_planes.p + 2 * wa, hp + 2 * wa, (wb - wa) * 8, cudaMemcpyHostToDevice, c->st_copy));
             MDBG_CK(c, cudaEventRecord(c->copy_ev[ci], c->st_copy));
             if (wb == n_words) MDBG_CK(c, cudaEventRecord(c->ev[4], c->st_copy));
+            up->n_enqueued = ci + 1;
             MDBG_CK(c, cudaStreamWaitEvent(c->st, c->copy_ev[ci], 0));
             MDBG_CK(c, expand_planes(d_planes.p, d_bases.p, wa, wb, c->num_sms, c->st, &c->tm.launches_push));
             // tiles with a byte outside ACGT travel as ASCII, over what the expansion wrote there
@@ -607,6 +633,7 @@ static int push_host(mdbg_ctx* c, const uint8_t* bases, const uint32_t* host_pla
     if (plan.empty()) plan.push_back(KaChunk{n_tiles, nullptr});
     if (!packed) MDBG_CK(c, cudaEventRecord(c->ev[4], c->st_copy));
     int rc = run_ka(c, d_bases, d_off, n_reads, B, &plan, packed ? &prepare : nullptr);
+    if (c->pack_pool) c->pack_pool->finish();   // (an error between a chunk's begin and its finish: nothing may outlive this call)
     if (rc == MDBG_ERR_ALPHABET && bases) {  // turn the batch offset into (read, offset) like SURVEY 5 asks
         uint64_t pos = c->h_sc->err_pos;
         uint64_t r = std::upper_bound(read_off, read_off + n_reads + 1, pos) - read_off - 1;

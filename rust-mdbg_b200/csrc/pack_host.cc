@@ -166,7 +166,9 @@ struct PackPool::Impl {
     std::vector<std::thread> workers;
     std::mutex mu;
     std::condition_variable cv_work, cv_done;
+    std::function<void(uint64_t)> fn_store;        // the burst's function (begin() keeps a copy)
     const std::function<void(uint64_t)>* fn = nullptr;
+    bool pending = false;                          // a burst was begun and not finished yet (caller's thread only)
     uint64_t n_items = 0;
     std::atomic<uint64_t> next{0};
     std::atomic<uint64_t> generation{0};
@@ -217,39 +219,71 @@ PackPool::~PackPool() {
 
 int PackPool::threads() const { return (int)impl_->workers.size() + 1; }
 
-void PackPool::parallel_for(uint64_t n_items, const std::function<void(uint64_t)>& fn) {
+void PackPool::begin(uint64_t n_items, std::function<void(uint64_t)> fn) {
+    finish();                          // one burst at a time
     if (n_items == 0) return;
-    if (impl_->workers.empty() || n_items == 1) {
-        for (uint64_t i = 0; i < n_items; i++) fn(i);
+    impl_->fn_store = std::move(fn);
+    impl_->pending = true;
+    if (impl_->workers.empty()) {      // no workers: everything happens in finish()
+        impl_->fn = &impl_->fn_store;
+        impl_->n_items = n_items;
+        impl_->next.store(0, std::memory_order_relaxed);
         return;
     }
     {
         std::lock_guard<std::mutex> lk(impl_->mu);   // a worker about to sleep sees the new generation
-        impl_->fn = &fn;
+        impl_->fn = &impl_->fn_store;
         impl_->n_items = n_items;
         impl_->next.store(0, std::memory_order_relaxed);
         impl_->active.store((int)impl_->workers.size(), std::memory_order_relaxed);
         impl_->generation.fetch_add(1, std::memory_order_release);
     }
     impl_->cv_work.notify_all();
+}
+
+void PackPool::finish() {
+    if (!impl_->pending) return;
     impl_->work();                     // the caller works too
-    int spins = 0;
-    while (impl_->active.load(std::memory_order_acquire) != 0) {
-        if (++spins < SPIN_LIMIT) { cpu_relax(); continue; }
-        std::unique_lock<std::mutex> lk(impl_->mu);
-        impl_->cv_done.wait(lk, [&] { return impl_->active.load() == 0; });
+    if (!impl_->workers.empty()) {
+        int spins = 0;
+        while (impl_->active.load(std::memory_order_acquire) != 0) {
+            if (++spins < SPIN_LIMIT) { cpu_relax(); continue; }
+            std::unique_lock<std::mutex> lk(impl_->mu);
+            impl_->cv_done.wait(lk, [&] { return impl_->active.load() == 0; });
+        }
     }
     impl_->fn = nullptr;
+    impl_->fn_store = nullptr;
+    impl_->pending = false;
+}
+
+void PackPool::parallel_for(uint64_t n_items, const std::function<void(uint64_t)>& fn) {
+    begin(n_items, fn);
+    finish();
+}
+
+static std::function<void(uint64_t)> pack_items(const uint8_t* bases, uint64_t n_bases, uint64_t w_begin, uint64_t w_end,
+                                                uint32_t* planes, uint8_t* bad_tiles, uint64_t& n_items) {
+    const uint64_t BLK = 16 * PACK_TILE_WORDS;     // 16 tiles (64 KiB of bases) per work item
+    const uint64_t first = w_begin / BLK, last = (w_end + BLK - 1) / BLK;
+    n_items = last - first;
+    return [=](uint64_t i) {
+        const uint64_t lo = std::max(w_begin, (first + i) * BLK), hi = std::min(w_end, (first + i + 1) * BLK);
+        if (lo < hi) pack_words(bases, n_bases, lo, hi, planes, bad_tiles);
+    };
+}
+
+void pack_parallel_begin(PackPool& pool, const uint8_t* bases, uint64_t n_bases, uint64_t w_begin, uint64_t w_end,
+                         uint32_t* planes, uint8_t* bad_tiles) {
+    uint64_t n = 0;
+    auto fn = pack_items(bases, n_bases, w_begin, w_end, planes, bad_tiles, n);
+    pool.begin(n, std::move(fn));
 }
 
 void pack_parallel(PackPool& pool, const uint8_t* bases, uint64_t n_bases, uint64_t w_begin, uint64_t w_end,
                    uint32_t* planes, uint8_t* bad_tiles) {
-    const uint64_t BLK = 16 * PACK_TILE_WORDS;     // 16 tiles (64 KiB of bases) per work item
-    const uint64_t first = w_begin / BLK, last = (w_end + BLK - 1) / BLK;
-    pool.parallel_for(last - first, [&](uint64_t i) {
-        const uint64_t lo = std::max(w_begin, (first + i) * BLK), hi = std::min(w_end, (first + i + 1) * BLK);
-        if (lo < hi) pack_words(bases, n_bases, lo, hi, planes, bad_tiles);
-    });
+    pack_parallel_begin(pool, bases, n_bases, w_begin, w_end, planes, bad_tiles);
+    pool.finish();
 }
 
 }  // namespace mdbg

@@ -22,6 +22,11 @@ public:
     PackPool& operator=(const PackPool&) = delete;
     int threads() const;
     void parallel_for(uint64_t n_items, const std::function<void(uint64_t)>& fn);   // fn(i) for i in [0, n_items)
+    // The same in two halves: begin() hands the items to the workers and returns, finish() lets the caller work
+    // on what is left and waits for the rest -- the caller is free in between (mdbg_push_reads enqueues the copies
+    // of the previous chunk there).  One burst at a time; finish() without a burst in flight does nothing.
+    void begin(uint64_t n_items, std::function<void(uint64_t)> fn);
+    void finish();
 private:
     struct Impl;
     Impl* impl_;
@@ -29,5 +34,8 @@ private:
 
 void pack_parallel(PackPool& pool, const uint8_t* bases, uint64_t n_bases, uint64_t w_begin, uint64_t w_end,
                    uint32_t* planes, uint8_t* bad_tiles);
+// begin()/finish() form of pack_parallel: the packing of words [w_begin, w_end) starts on the workers at once
+void pack_parallel_begin(PackPool& pool, const uint8_t* bases, uint64_t n_bases, uint64_t w_begin, uint64_t w_end,
+                         uint32_t* planes, uint8_t* bad_tiles);
 
 }  // namespace mdbg
