@@ -14,7 +14,7 @@ CLI := rust-mdbg_b200/rust-mdbg
 
 all: $(OUT) $(CLI) oracle model
 
-$(CLI): rust-mdbg_b200/cli/rust_mdbg_main.cpp include/mdbg.h $(OUT)
+$(CLI): rust-mdbg_b200/cli/rust_mdbg_main.cpp $(wildcard rust-mdbg_b200/cli/*.hpp) include/mdbg.h $(OUT)
 	g++ -O2 -std=c++17 -Wall -o $@ $< -Lrust-mdbg_b200 -lmdbg_b200 -lz -Wl,-rpath,'$$ORIGIN'
 
 $(CSRC)/%.o: $(CSRC)/%.cu $(HDR)

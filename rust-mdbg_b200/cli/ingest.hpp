@@ -17,10 +17,13 @@
 #include <unistd.h>
 #include <zlib.h>
 
+#include "gz_inflate.hpp"
+
 #include <algorithm>
 #include <atomic>
 #include <condition_variable>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -131,9 +134,18 @@ public:
         size_ = (size_t)sb.st_size;
         unsigned char magic[2] = {0, 0};
         if (size_ >= 2 && pread(fd_, magic, 2, 0) == 2 && magic[0] == 0x1f && magic[1] == 0x8b) {
-            gz_ = gzdopen(dup(fd_), "rb");
-            if (!gz_) return false;
-            gzbuffer(gz_, 1 << 20);
+            // the compressed file is mapped and decoded by gz_inflate.hpp (MDBG_GZ_ZLIB=1: zlib's gzread instead)
+            gz_on_ = true; gz_err_.clear();
+            if (!getenv("MDBG_GZ_ZLIB")) {
+                gzmap_ = (const uint8_t*)mmap(nullptr, size_, PROT_READ, MAP_PRIVATE, fd_, 0);
+                if (gzmap_ == MAP_FAILED) { gzmap_ = nullptr; return false; }
+                madvise((void*)gzmap_, size_, MADV_SEQUENTIAL);
+                zfast_.reset(gzmap_, size_);
+            } else {
+                gz_ = gzdopen(dup(fd_), "rb");
+                if (!gz_) return false;
+                gzbuffer(gz_, 1 << 20);
+            }
             blk_[0].resize(GZ_BLOCK + GZ_SLACK); blk_[1].resize(GZ_BLOCK + GZ_SLACK);
             gz_eof_ = false; carry_.clear();
             inflater_ = std::thread([this] { inflate_loop(); });
@@ -156,6 +168,8 @@ public:
         stop_ = false; ready_[0] = ready_[1] = false; blk_len_[0] = blk_len_[1] = 0; take_ = 0; put_ = 0;
         gz_eof_ = false; gz_eof_done_ = false; carry_.clear();
         if (gz_) { gzclose(gz_); gz_ = nullptr; }
+        if (gzmap_) { munmap((void*)gzmap_, size_); gzmap_ = nullptr; }
+        gz_on_ = false;
         if (map_) { munmap((void*)map_, size_); map_ = nullptr; }
         if (fd_ >= 0) { ::close(fd_); fd_ = -1; }
     }
@@ -164,11 +178,14 @@ public:
     // text; false when the file is exhausted and nothing was added.  A record larger than the buffer fails.
     bool next_batch(Batch& b, size_t target, std::string& err) {
         b.fill = 0; b.off.assign(1, 0); b.ids.clear();
-        if (gz_) {
+        if (gz_on_) {
             for (;;) {
                 std::unique_lock<std::mutex> lk(mu_);
                 cv_.wait(lk, [this] { return ready_[take_] || gz_eof_done_; });
-                if (!ready_[take_]) return false;
+                if (!ready_[take_]) {
+                    if (!gz_err_.empty()) err = gz_err_;     // a damaged stream is an error, not a short file
+                    return false;
+                }
                 const char* text = blk_[take_].data();
                 const size_t len = blk_len_[take_];
                 lk.unlock();
@@ -231,6 +248,17 @@ private:
 
     // inflate thread: fills blk_[put_] with whole records (the tail of a block that ends inside a record is
     // carried to the next one)
+    // next decompressed bytes; <= 0 at the end of the stream or on a damaged one (gz_err_ says which)
+    long gz_read(char* dst, size_t cap) {
+        if (gzmap_) {
+            const size_t got = zfast_.read(reinterpret_cast<uint8_t*>(dst), cap);
+            if (got == 0 && !zfast_.error().empty()) gz_err_ = zfast_.error();
+            return (long)got;
+        }
+        const int got = gzread(gz_, dst, (unsigned)std::min<size_t>(cap, 1u << 30));
+        if (got < 0) { int en = 0; const char* m = gzerror(gz_, &en); gz_err_ = std::string("gzip: ") + (m ? m : "read error"); }
+        return got;
+    }
     void inflate_loop() {
         for (;;) {
             {
@@ -243,7 +271,7 @@ private:
             if (n) memcpy(B.data(), carry_.data(), n);
             carry_.clear();
             while (!gz_eof_ && n < GZ_BLOCK) {
-                int got = gzread(gz_, B.data() + n, (unsigned)std::min<size_t>(GZ_BLOCK - n, 1u << 30));
+                const long got = gz_read(B.data() + n, GZ_BLOCK - n);
                 if (got <= 0) { gz_eof_ = true; break; }
                 n += (size_t)got;
             }
@@ -251,7 +279,7 @@ private:
             if (!gz_eof_) {   // cut at the last record start; a single record longer than a block keeps growing
                 const char* cutp = last_record_start(B.data(), B.data() + n);
                 while (cutp == B.data() && !gz_eof_ && n < B.size()) {
-                    int got = gzread(gz_, B.data() + n, (unsigned)std::min<size_t>(B.size() - n, 16u << 20));
+                    const long got = gz_read(B.data() + n, std::min<size_t>(B.size() - n, 16u << 20));
                     if (got <= 0) { gz_eof_ = true; break; }
                     n += (size_t)got;
                     cutp = gz_eof_ ? B.data() + n : last_record_start(B.data(), B.data() + n);
@@ -294,7 +322,11 @@ private:
     int fd_ = -1;
     size_t size_ = 0, pos_ = 0;
     const char* map_ = nullptr;
-    gzFile gz_ = nullptr;
+    gzFile gz_ = nullptr;            // MDBG_GZ_ZLIB=1 only
+    bool gz_on_ = false;             // the file is gzip: blocks come from the inflate thread
+    const uint8_t* gzmap_ = nullptr; // the compressed file, mapped
+    GzInflate zfast_;
+    std::string gz_err_;
     // gz pipeline
     std::thread inflater_;
     std::mutex mu_;

@@ -103,3 +103,32 @@ def test_degenerate_files(exe, tmp_path):
     assert len(got) == 657
     assert [int(x[1]) for x in got] == [int(off[i + 1] - off[i]) for i in range(657)]
     assert got[0][2] == "%016x" % fnv(bytes(bases[int(off[0]):int(off[1])]))
+
+
+def test_gzip_reader_paths_agree_and_damage_is_an_error(exe, tmp_path):
+    """The front end's own gzip decoder (cli/gz_inflate.hpp) and zlib's gzread (MDBG_GZ_ZLIB=1) deliver the same
+    records for single- and multi-member files; a damaged or truncated .gz is an error, not a shorter read set."""
+    rng = np.random.default_rng(21)
+    recs = make_records(rng, 900, mean=4000)
+    text = b"".join(b">" + i.encode() + b"\n" + s + b"\n" for i, s in recs)
+    exp = expected(recs)
+    one = str(tmp_path / "one.fa.gz")
+    open(one, "wb").write(gzip.compress(text, 6))
+    cut = [0]
+    while cut[-1] < len(text):                                   # members cut at arbitrary bytes (bgzip does that too)
+        cut.append(min(len(text), cut[-1] + int(rng.integers(1, 90000))))
+    many = str(tmp_path / "many.fa.gz")
+    open(many, "wb").write(b"".join(gzip.compress(text[a:b], int(rng.integers(1, 10))) for a, b in zip(cut, cut[1:])))
+    for path in (one, many):
+        for env in ({}, {"MDBG_GZ_ZLIB": "1"}):
+            out = subprocess.run([exe, path, "fasta", "5", str(1 << 20)], capture_output=True, text=True, check=True,
+                                 env={**os.environ, **env}).stdout
+            assert [tuple(x.split("\t")) for x in out.splitlines()] == exp
+    good = open(one, "rb").read()
+    flipped = bytearray(good); flipped[len(good) // 2] ^= 0x10
+    for name, blob in (("truncated", good[:len(good) * 2 // 3]), ("flipped", bytes(flipped)), ("no_trailer", good[:-8])):
+        bad = str(tmp_path / (name + ".fa.gz"))
+        open(bad, "wb").write(blob)
+        r = subprocess.run([exe, bad, "fasta", "3", str(1 << 20)], capture_output=True, text=True)
+        assert r.returncode == 1 and "gzip" in r.stderr, (name, r.returncode, r.stderr[-200:])
+
