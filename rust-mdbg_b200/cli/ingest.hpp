@@ -141,6 +141,10 @@ public:
                 if (gzmap_ == MAP_FAILED) { gzmap_ = nullptr; return false; }
                 madvise((void*)gzmap_, size_, MADV_SEQUENTIAL);
                 zfast_.reset(gzmap_, size_);
+                // block gzip (bgzip / BGZF: members of <= 64 KiB that carry their own compressed size): members are
+                // independent, so a block's worth of them is inflated by all threads at once
+                gzpos_ = 0;
+                bgzf_ = bgzf_member(0, nullptr, nullptr) && !getenv("MDBG_GZ_SERIAL");
             } else {
                 gz_ = gzdopen(dup(fd_), "rb");
                 if (!gz_) return false;
@@ -214,6 +218,7 @@ public:
 
 private:
     static constexpr size_t GZ_BLOCK = 64u << 20, GZ_SLACK = 64u << 20;
+    static constexpr long GZ_FULL = -2;    // gz_read: nothing read because the buffer has no room for the next unit
 
     bool parse_text(const char* text, size_t len, Batch& b, std::string& err) {
         if (len > b.cap) { err = "a block of reads longer than the staging buffer"; return false; }
@@ -249,7 +254,73 @@ private:
     // inflate thread: fills blk_[put_] with whole records (the tail of a block that ends inside a record is
     // carried to the next one)
     // next decompressed bytes; <= 0 at the end of the stream or on a damaged one (gz_err_ says which)
+    // BGZF member at byte `at` of the mapped file: its total size and uncompressed size (SAM spec 4.1: gzip member whose
+    // extra field holds the subfield 'B' 'C' 2 0 BSIZE-1, ISIZE in its last four bytes)
+    bool bgzf_member(size_t at, size_t* msize, size_t* isize) const {
+        if (size_ < at + 28) return false;
+        const uint8_t* h = gzmap_ + at;
+        if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) return false;
+        const size_t xlen = h[10] | (h[11] << 8);
+        if (size_ < at + 12 + xlen) return false;
+        for (size_t x = 0; x + 4 <= xlen;) {
+            const uint8_t* f = h + 12 + x;
+            const size_t slen = f[2] | (f[3] << 8);
+            if (f[0] == 'B' && f[1] == 'C' && slen == 2 && x + 6 <= xlen) {
+                const size_t total = (size_t)(f[4] | (f[5] << 8)) + 1;
+                if (total < 12 + xlen + 8 || at + total > size_) return false;
+                if (msize) *msize = total;
+                const uint8_t* t = h + total - 4;
+                if (isize) *isize = t[0] | (t[1] << 8) | (t[2] << 16) | ((size_t)t[3] << 24);
+                return true;
+            }
+            x += 4 + slen;
+        }
+        return false;
+    }
+    // as many whole BGZF members as fit `cap`, inflated by all threads; 0 when the next member is not BGZF any more
+    // (the serial decoder takes over from there) or the file has ended
+    size_t bgzf_read(char* dst, size_t cap) {
+        struct M { size_t at, msize, isize, out; };
+        std::vector<M> ms;
+        size_t out = 0, at = gzpos_;
+        while (at < size_) {
+            size_t msz, isz;
+            if (!bgzf_member(at, &msz, &isz)) break;
+            if (isz > (1u << 16) || out + isz > cap) break;          // (BGZF caps a member at 64 KiB; a fuller block next time)
+            ms.push_back(M{at, msz, isz, out});
+            out += isz; at += msz;
+        }
+        if (ms.empty()) return 0;
+        const int T = (int)std::min<size_t>((size_t)nthreads_, std::max<size_t>(1, ms.size() / 8));
+        if ((int)zpool_.size() < T) zpool_.resize(T);
+        std::vector<std::string> errs(T);
+        run_parallel(T, [&](int t) {
+            GzInflate& z = zpool_[t];
+            const size_t a = ms.size() * t / T, b = ms.size() * (t + 1) / T;
+            for (size_t i = a; i < b && errs[t].empty(); i++) {
+                z.reset(gzmap_ + ms[i].at, ms[i].msize);
+                const size_t got = z.read(reinterpret_cast<uint8_t*>(dst) + ms[i].out, ms[i].isize);
+                uint8_t extra;
+                if (!z.error().empty()) errs[t] = z.error();
+                else if (got != ms[i].isize || z.read(&extra, 1) != 0 || !z.error().empty()) errs[t] = "gzip: a BGZF member does not hold what its header says";
+            }
+        });
+        for (const std::string& e : errs) if (!e.empty()) { gz_err_ = e; return 0; }
+        gzpos_ = at;
+        return out;
+    }
     long gz_read(char* dst, size_t cap) {
+        if (gzmap_ && bgzf_) {
+            const size_t got = bgzf_read(dst, cap);
+            if (got || !gz_err_.empty()) return (long)got;
+            if (gzpos_ >= size_) return 0;
+            // not BGZF from here on (or a member too large for what is left of the block): the serial decoder goes on.
+            // A block with room for less than one member must not switch: ask again with a fresh block.
+            size_t msz, isz;
+            if (bgzf_member(gzpos_, &msz, &isz) && isz <= (1u << 16) && cap < (1u << 16)) return GZ_FULL;
+            bgzf_ = false;
+            zfast_.reset(gzmap_ + gzpos_, size_ - gzpos_);
+        }
         if (gzmap_) {
             const size_t got = zfast_.read(reinterpret_cast<uint8_t*>(dst), cap);
             if (got == 0 && !zfast_.error().empty()) gz_err_ = zfast_.error();
@@ -266,12 +337,13 @@ private:
                 cv_.wait(lk, [this] { return stop_ || !ready_[put_]; });
                 if (stop_) return;
             }
-            std::vector<char>& B = blk_[put_];
+            RawBuf& B = blk_[put_];
             size_t n = carry_.size();
             if (n) memcpy(B.data(), carry_.data(), n);
             carry_.clear();
             while (!gz_eof_ && n < GZ_BLOCK) {
                 const long got = gz_read(B.data() + n, GZ_BLOCK - n);
+                if (got == GZ_FULL) break;                       // block gzip: no room for one more member
                 if (got <= 0) { gz_eof_ = true; break; }
                 n += (size_t)got;
             }
@@ -280,6 +352,7 @@ private:
                 const char* cutp = last_record_start(B.data(), B.data() + n);
                 while (cutp == B.data() && !gz_eof_ && n < B.size()) {
                     const long got = gz_read(B.data() + n, std::min<size_t>(B.size() - n, 16u << 20));
+                    if (got == GZ_FULL) break;
                     if (got <= 0) { gz_eof_ = true; break; }
                     n += (size_t)got;
                     cutp = gz_eof_ ? B.data() + n : last_record_start(B.data(), B.data() + n);
@@ -326,12 +399,22 @@ private:
     bool gz_on_ = false;             // the file is gzip: blocks come from the inflate thread
     const uint8_t* gzmap_ = nullptr; // the compressed file, mapped
     GzInflate zfast_;
+    std::vector<GzInflate> zpool_;   // one decoder per thread for block gzip
+    bool bgzf_ = false;
+    size_t gzpos_ = 0;               // block gzip: next member's offset in the file
     std::string gz_err_;
     // gz pipeline
     std::thread inflater_;
     std::mutex mu_;
     std::condition_variable cv_;
-    std::vector<char> blk_[2];
+    struct RawBuf {                  // a block of text, NOT zero-filled (2 x 128 MB of page touching at open otherwise)
+        char* p = nullptr; size_t n = 0;
+        ~RawBuf() { free(p); }
+        void resize(size_t m) { if (m != n) { free(p); p = (char*)malloc(m); n = p ? m : 0; } }
+        char* data() { return p; }
+        size_t size() const { return n; }
+    };
+    RawBuf blk_[2];
     size_t blk_len_[2] = {0, 0};
     bool ready_[2] = {false, false};
     int take_ = 0, put_ = 0;

@@ -132,3 +132,44 @@ def test_gzip_reader_paths_agree_and_damage_is_an_error(exe, tmp_path):
         r = subprocess.run([exe, bad, "fasta", "3", str(1 << 20)], capture_output=True, text=True)
         assert r.returncode == 1 and "gzip" in r.stderr, (name, r.returncode, r.stderr[-200:])
 
+
+def bgzf_member(chunk, level=6):
+    import struct
+    import zlib
+    c = zlib.compressobj(level, zlib.DEFLATED, -15)
+    d = c.compress(chunk) + c.flush()
+    bsize = 12 + 6 + len(d) + 8
+    return (b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + struct.pack("<H", bsize - 1) + d +
+            struct.pack("<II", zlib.crc32(chunk) & 0xFFFFFFFF, len(chunk)))
+
+
+def test_block_gzip_is_inflated_in_parallel(exe, tmp_path):
+    """bgzip / BGZF files (independent members that carry their compressed size): a block's worth of members is
+    inflated by all threads at once; same records as the serial decoder (MDBG_GZ_SERIAL=1) and as zlib; a file that
+    stops being BGZF half way (plain gzip members appended) goes on through the serial decoder; a damaged member is
+    an error."""
+    rng = np.random.default_rng(22)
+    recs = make_records(rng, 1500, mean=5000)
+    text = b"".join(b">" + i.encode() + b"\n" + s + b"\n" for i, s in recs)
+    exp = expected(recs)
+    members = [bgzf_member(text[a:a + 65280], int(rng.integers(1, 10))) for a in range(0, len(text), 65280)]
+    pure = str(tmp_path / "pure.fa.gz")
+    open(pure, "wb").write(b"".join(members) + bgzf_member(b""))            # with the BGZF end-of-file marker
+    half = len(members) // 2
+    cut = sum(len(m) for m in members[:half])
+    tail_text = text[half * 65280:]
+    mixed = str(tmp_path / "mixed.fa.gz")
+    open(mixed, "wb").write(b"".join(members[:half]) + gzip.compress(tail_text[:100000], 6) + gzip.compress(tail_text[100000:], 1))
+    for path in (pure, mixed):
+        for env in ({}, {"MDBG_GZ_SERIAL": "1"}, {"MDBG_GZ_ZLIB": "1"}):
+            for threads, target in ((1, 1 << 30), (6, 1 << 20), (16, 200000)):
+                out = subprocess.run([exe, path, "fasta", str(threads), str(target)], capture_output=True, text=True, check=True,
+                                     env={**os.environ, **env}).stdout
+                assert [tuple(x.split("\t")) for x in out.splitlines()] == exp, (path, env, threads)
+    blob = bytearray(open(pure, "rb").read())
+    blob[cut + 40] ^= 0x04                                                 # inside the deflate data of a member in the middle
+    bad = str(tmp_path / "bad.fa.gz")
+    open(bad, "wb").write(bytes(blob))
+    r = subprocess.run([exe, bad, "fasta", "4", str(1 << 20)], capture_output=True, text=True)
+    assert r.returncode == 1 and "gzip" in r.stderr, (r.returncode, r.stderr[-200:])
+
