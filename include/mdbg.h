@@ -257,6 +257,11 @@ int mdbg_write_sequences(const mdbg_graph* g, const uint8_t* bases, const uint64
  * hands over each read the writer asks for and never holds the whole read set.  *g must outlive the writer. */
 typedef struct mdbg_seq_writer mdbg_seq_writer;
 int      mdbg_seq_writer_open(const mdbg_graph* g, const char* path, int lz4_frame, mdbg_seq_writer** out);
+/* One of n_parts writers sharing the lines of *g (the reference writes one {P}.{tid}.sequences per worker thread,
+ * main.rs:614-630, and its readers glob them): part p owns the runs of 32 lines with run % n_parts == p; every part
+ * writes the header.  Each part is driven like a whole writer (from its own thread if wished). */
+int      mdbg_seq_writer_open_part(const mdbg_graph* g, const char* path, int lz4_frame, uint32_t part, uint32_t n_parts,
+                                   mdbg_seq_writer** out);
 uint64_t mdbg_seq_writer_next_read(const mdbg_seq_writer* w);      /* UINT64_MAX: every line is written */
 int      mdbg_seq_writer_read(mdbg_seq_writer* w, uint64_t read_index, const uint8_t* read_bases, uint64_t read_len);
 int      mdbg_seq_writer_close(mdbg_seq_writer* w);                /* MDBG_ERR_IO if a needed read never came */

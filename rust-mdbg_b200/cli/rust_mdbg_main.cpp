@@ -221,7 +221,36 @@ int main(int argc, char** argv) {
     const double t_graph = now_s();
     if (mdbg_write_gfa(&g, (prefix + ".gfa").c_str()) != MDBG_OK) die("Couldn't create " + prefix + ".gfa");
     const double t_gfa = now_s();
-    if (!no_basespace) {   // second pass over the input: cut the .sequences lines (main.rs:696-707) without holding the reads
+    // A large node set is written by several writers at once, one {prefix}.{t}.sequences per writer like the reference's
+    // one file per worker thread (main.rs:614-630; to_basespace globs them): every batch of the second pass is walked by
+    // all writers in parallel, each cutting the lines it owns.  Small outputs keep the single {prefix}.0.sequences.
+    const int n_seq_writers = (g.n_seqlines >= 20000 && n_threads > 1) ? (int)std::min<long>(n_threads, 8) : 1;
+    if (!no_basespace && n_seq_writers > 1) {
+        std::vector<mdbg_seq_writer*> sw(n_seq_writers, nullptr);
+        std::vector<std::string> sp(n_seq_writers);
+        for (int t = 0; t < n_seq_writers; t++) {
+            sp[t] = prefix + "." + std::to_string(t) + ".sequences";
+            if (mdbg_seq_writer_open_part(&g, sp[t].c_str(), 1, (uint32_t)t, (uint32_t)n_seq_writers, &sw[t]) != MDBG_OK)
+                die("Couldn't create file: " + sp[t]);
+        }
+        std::vector<std::string> werr(n_seq_writers);
+        for_each_batch(reads, fasta, false, n_threads, pin, CAP, BATCH, [&](ingest::Batch& b, unsigned long long first) {
+            std::vector<std::thread> th;
+            for (int t = 0; t < n_seq_writers; t++)
+                th.emplace_back([&, t] {
+                    for (uint64_t r; werr[t].empty() && (r = mdbg_seq_writer_next_read(sw[t])) != UINT64_MAX && r < first + b.n_reads();) {
+                        if (r < first) { werr[t] = "internal: .sequences lines out of read order"; break; }
+                        const uint64_t i = r - first;
+                        if (mdbg_seq_writer_read(sw[t], r, b.bases + b.off[i], b.off[i + 1] - b.off[i]) != MDBG_OK)
+                            werr[t] = "Couldn't write file: " + sp[t];
+                    }
+                });
+            for (auto& x : th) x.join();
+            for (const std::string& e : werr) if (!e.empty()) die(e);
+        });
+        for (int t = 0; t < n_seq_writers; t++)
+            if (mdbg_seq_writer_close(sw[t]) != MDBG_OK) die("Couldn't write file: " + sp[t]);
+    } else if (!no_basespace) {   // second pass over the input: cut the .sequences lines (main.rs:696-707) without holding the reads
         mdbg_seq_writer* sw = nullptr;
         const std::string sp = prefix + ".0.sequences";
         if (mdbg_seq_writer_open(&g, sp.c_str(), 1, &sw) != MDBG_OK) die("Couldn't create file: " + sp);

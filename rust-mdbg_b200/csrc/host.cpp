@@ -180,10 +180,21 @@ struct mdbg_seq_writer {
     uint64_t q = 0;
     bool ok = true;
     std::string line, rc;
+    // one of n_parts writers that share the lines of a graph (the reference writes one file per worker thread,
+    // main.rs:614-630; its readers glob them): this one owns the runs of SEQ_RUN lines with run % n_parts == part
+    uint32_t part = 0, n_parts = 1;
+    static constexpr uint64_t SEQ_RUN = 32;
+    bool owns(uint64_t qq) const { return n_parts <= 1 || (qq / SEQ_RUN) % n_parts == part; }
+    void skip_foreign() { while (q < g->n_seqlines && !owns(q)) q++; }
 };
 
 int mdbg_seq_writer_open(const mdbg_graph* g, const char* path, int lz4_frame, mdbg_seq_writer** out) {
-    if (!g || !path || !out || (g->n_seqlines && !g->q_index)) return MDBG_ERR_BAD_ARG;
+    return mdbg_seq_writer_open_part(g, path, lz4_frame, 0, 1, out);
+}
+
+int mdbg_seq_writer_open_part(const mdbg_graph* g, const char* path, int lz4_frame, uint32_t part, uint32_t n_parts,
+                              mdbg_seq_writer** out) {
+    if (!g || !path || !out || (g->n_seqlines && !g->q_index) || n_parts == 0 || part >= n_parts) return MDBG_ERR_BAD_ARG;
     *out = nullptr;
     FILE* f = fopen(path, "wb");
     if (!f) return MDBG_ERR_IO;
@@ -195,6 +206,8 @@ int mdbg_seq_writer_open(const mdbg_graph* g, const char* path, int lz4_frame, m
                       "\n# Structure of remaining of the file:\n"
                       "# [node name]\t[list of minimizers]\t[sequence of node]\t[abundance]\t[origin]\t[shift]\n";
     W->ok = W->ok && W->w.write(hdr.data(), hdr.size());
+    W->part = part; W->n_parts = n_parts;
+    W->skip_foreign();
     *out = W;
     return MDBG_OK;
 }
@@ -211,6 +224,7 @@ int mdbg_seq_writer_read(mdbg_seq_writer* W, uint64_t read_index, const uint8_t*
     const mdbg_graph* g = W->g;
     while (W->ok && W->q < g->n_seqlines && g->q_read[W->q] == read_index) {
         const uint64_t q = W->q++;
+        if (!W->owns(q)) continue;                 // another part's line of the same read
         if (g->q_end[q] > read_len || g->q_start[q] > g->q_end[q] || !read_bases) return MDBG_ERR_BAD_ARG;
         const uint32_t idx = g->q_index[q];
         const uint32_t* it = std::lower_bound(g->node_index, g->node_index + g->n_nodes, idx);   // nodes ascend in index
@@ -228,6 +242,7 @@ int mdbg_seq_writer_read(mdbg_seq_writer* W, uint64_t read_index, const uint8_t*
         line += "\t*\t*\t(" + std::to_string(g->q_shift[2 * q]) + ", " + std::to_string(g->q_shift[2 * q + 1]) + ")\n";
         W->ok = W->w.write(line.data(), line.size());
     }
+    W->skip_foreign();
     return W->ok ? MDBG_OK : MDBG_ERR_IO;
 }
 

@@ -109,6 +109,7 @@ SYMBOLS = {
     "mdbg_write_gfa": (ctypes.c_int, [GP, ctypes.c_char_p]),
     "mdbg_write_sequences": (ctypes.c_int, [GP, vp, vp, ctypes.c_char_p, ctypes.c_int]),
     "mdbg_seq_writer_open": (ctypes.c_int, [GP, ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(vp)]),
+    "mdbg_seq_writer_open_part": (ctypes.c_int, [GP, ctypes.c_char_p, ctypes.c_int, u32, u32, ctypes.POINTER(vp)]),
     "mdbg_seq_writer_next_read": (u64, [vp]),
     "mdbg_seq_writer_read": (ctypes.c_int, [vp, u64, vp, u64]),
     "mdbg_seq_writer_close": (ctypes.c_int, [vp]),

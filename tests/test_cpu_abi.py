@@ -294,6 +294,30 @@ def test_file_writers_on_host(mdbg, oracle, example_reads, tmp_path):
         n_calls += 1
     assert L.mdbg_seq_writer_close(W) == 0 and n_calls > 0
     assert open(seqs, "rb").read() == open(seqz, "rb").read()
+    # several writers sharing the lines (one file per part, like the reference's one file per worker thread): every
+    # file carries the header, together they hold exactly the lines of the single file
+    all_lines = sorted(x for x in plain.splitlines(True) if not x.startswith("#"))
+    for n_parts in (1, 2, 3, 7):
+        got = []
+        for part in range(n_parts):
+            W = F.vp()
+            pth = str(tmp_path / ("p.%d_of_%d.sequences" % (part, n_parts)))
+            assert L.mdbg_seq_writer_open_part(ctypes.byref(cg), pth.encode(), 0, part, n_parts, ctypes.byref(W)) == 0
+            last = -1
+            while True:
+                r = L.mdbg_seq_writer_next_read(W)
+                if r == 0xFFFFFFFFFFFFFFFF:
+                    break
+                assert r > last or last == -1
+                last = r
+                assert L.mdbg_seq_writer_read(W, r, bases.ctypes.data + int(off[r]), int(off[r + 1] - off[r])) == 0
+            assert L.mdbg_seq_writer_close(W) == 0
+            txt = open(pth).read()
+            assert txt.startswith("# k = 7\n# l = 10\n")
+            got += [x for x in txt.splitlines(True) if not x.startswith("#")]
+        assert sorted(got) == all_lines and len(got) == len(all_lines)
+    W = F.vp()
+    assert L.mdbg_seq_writer_open_part(ctypes.byref(cg), str(tmp_path / "bad").encode(), 0, 3, 3, ctypes.byref(W)) != 0
 
 
 def test_bench_reference_arm_line():
