@@ -122,7 +122,21 @@ private:
         if (kraft < (1u << 15) && !(allow_incomplete && (used == 0 || (used == 1 && count[1] == 1)))) return false;
         uint32_t next[16];
         { uint32_t c = 0; for (int l = 1; l < 16; l++) { c = (c + (uint32_t)count[l - 1]) << 1; next[l] = c; } }
-        // sub-table sizes: per primary prefix, the longest code that starts with it
+        // sub-table sizes: per primary prefix, the longest code that starts with it (only when some code is longer
+        // than the primary index: rare on sequence text, so the common case touches nothing but the table itself)
+        bool any_long = false;
+        for (int l = pbits + 1; l < 16; l++) any_long = any_long || count[l] != 0;
+        if (!any_long) {
+            tab.assign((size_t)1 << pbits, 0);
+            for (int s = 0; s < n; s++) {
+                const int l = lens[s];
+                if (!l) continue;
+                const uint32_t r = rev(next[l]++, l);
+                const uint32_t e = entry_of(s) | (uint32_t)l;
+                for (uint32_t i = r; i < (1u << pbits); i += 1u << l) tab[i] = e;
+            }
+            return true;
+        }
         std::vector<uint8_t> submax((size_t)1 << pbits, 0);
         {
             uint32_t nx[16];
