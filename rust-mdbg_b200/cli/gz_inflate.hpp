@@ -23,6 +23,7 @@
 
 #include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace ingest {
@@ -37,6 +38,19 @@ public:
         obuf_.resize(WIN + ROUND + SLACK);
         opos_ = WIN; pend_begin_ = pend_end_ = WIN; hist_valid_ = 0;
         crc_ = 0; member_out_ = 0; stored_left_ = 0; member_start_ = WIN; crc_from_ = WIN;
+    }
+    // Goes on in the MIDDLE of a member: at bit `bit` of in[0, n) a block starts, window[0, wn) is the text before it
+    // (at most 32 KiB matter), crc / member_out are the member's CRC-32 and length so far.
+    void resume(const uint8_t* in, size_t n, uint64_t bit, const uint8_t* window, size_t wn, uint32_t crc, uint64_t member_out) {
+        reset(in, n);
+        ip_ = in + (size_t)(bit >> 3);
+        refill();
+        if (bitcnt_ >= (int)(bit & 7)) drop((int)(bit & 7));
+        if (wn > WIN) { window += wn - WIN; wn = WIN; }
+        if (wn) memcpy(obuf_.data() + WIN - wn, window, wn);
+        hist_valid_ = wn;
+        state_ = ST_BLOCK_HEADER;
+        crc_ = crc; member_out_ = member_out;
     }
     bool eof() const { return eof_ && pend_begin_ == pend_end_; }
     const std::string& error() const { return err_; }
@@ -58,7 +72,7 @@ public:
         return done;
     }
 
-private:
+protected:                                   // (GzSpan below decodes spans of a stream with the same tables and bit reader)
     static constexpr size_t WIN = 32768, ROUND = 1u << 20, SLACK = 258 + 16;
     static constexpr int LBITS = 11, DBITS = 8;                      // primary table bits
     enum { ST_HEADER, ST_BLOCK_HEADER, ST_STORED, ST_CODES, ST_TRAILER };
@@ -328,6 +342,9 @@ private:
         return (uint32_t)_mm_extract_epi32(_mm_xor_si128(x1, x0), 1);
     }
 #endif
+public:
+    static uint32_t crc32_of(const uint8_t* buf, size_t len) { return crc32_fast(0, buf, len); }
+protected:
     static uint32_t crc32_fast(uint32_t crc, const uint8_t* buf, size_t len) {
 #if defined(__x86_64__)
         static const bool have = __builtin_cpu_supports("pclmul") && __builtin_cpu_supports("sse4.1");
@@ -453,6 +470,324 @@ private:
         pend_begin_ = WIN;
         pend_end_ = ok ? opos_ : WIN;              // nothing of a failed round is handed out
         return ok && pend_end_ > pend_begin_;
+    }
+};
+
+
+// ---- one gzip stream, many threads ---------------------------------------------------------------------------------
+// A deflate stream has no index, but its blocks can be FOUND: a thread that starts in the middle of the file tries bit
+// offsets until a dynamic block header parses and the data behind it decodes (Kerbiriou & Chikhi, "Parallel decompression
+// of gzip-compressed files and random access to DNA sequences", 2019; rapidgzip).  What it cannot know is the 32 KiB of
+// text before its start, so it decodes into 16-bit symbols: a value >= 256 stands for "byte (value - 256) of the unknown
+// window" and is copied by matches like any literal.  When the span before it is done its last 32 KiB are known and the
+// markers are replaced.  Spans must join exactly (the span before ends on the bit the next one started at), else the later
+// span is thrown away and decoded again from the true position -- correctness never rests on the block finder, and the
+// member's CRC-32 (combined from the spans' CRCs) and length are verified at its end.
+
+class GzSpan : public GzInflate {
+public:
+    static constexpr uint16_t UNKNOWN = 0xFFFF;    // before the start of the data: a match that reaches it is invalid
+    std::vector<uint16_t> sym;                     // [0, WIN): image of the window before the span, then the span's text
+    uint64_t end_bit = 0;                          // where decoding stopped: a block boundary (or the end of the final block)
+    bool hit_final = false;
+    size_t used = 0;                               // symbols of `sym` in use (the vector itself is kept larger between blocks)
+
+    // Decodes blocks from bit `start_bit` of in[0, n) until the first block boundary at or after `stop_bit` or the end
+    // of the final block.  window[0, wn): the text before the span if known, else markers.  False on any error.
+    bool run(const uint8_t* in, size_t n, uint64_t start_bit, uint64_t stop_bit, const uint8_t* window, size_t wn,
+             bool window_known, size_t max_out) {
+        in_ = in; iend_ = in + n; err_.clear();
+        seek_bit(start_bit);
+        hit_final = false;
+        bool imaged = false;                       // (the block finder calls this for one bit offset in eight: the 64 KiB
+        for (;;) {                                 //  image is written only once a header has parsed)
+            const uint64_t at = bit_pos();
+            if (at >= stop_bit && imaged) { end_bit = at; sym.resize(used); return true; }
+            if (!block_header()) return false;
+            if (!imaged) {
+                if (sym.size() < WIN + (1u << 16)) sym.resize(WIN + (1u << 16));
+                used = WIN;
+                if (window_known) {
+                    if (wn > WIN) { window += wn - WIN; wn = WIN; }
+                    for (size_t j = 0; j < WIN - wn; j++) sym[j] = UNKNOWN;
+                    for (size_t j = 0; j < wn; j++) sym[WIN - wn + j] = window[j];
+                } else {
+                    for (size_t j = 0; j < WIN; j++) sym[j] = (uint16_t)(256 + j);
+                }
+                imaged = true;
+            }
+            if (state_ == ST_STORED) {
+                if ((size_t)(iend_ - ip_) < stored_left_) return fail("truncated stored block");
+                const size_t o = used;
+                if (sym.size() < o + stored_left_) sym.resize(std::max(sym.size() * 2, o + stored_left_));
+                for (uint32_t j = 0; j < stored_left_; j++) sym[o + j] = ip_[j];
+                used = o + stored_left_;
+                ip_ += stored_left_;
+                stored_left_ = 0;
+            } else if (!codes16(max_out)) {
+                return false;
+            }
+            if (final_block_) { hit_final = true; end_bit = bit_pos(); sym.resize(used); return true; }
+        }
+    }
+    // quick look: do the three header bits at `bit` say "not final, dynamic"?
+    static bool plausible(const uint8_t* in, size_t n, uint64_t bit) {
+        const size_t by = (size_t)(bit >> 3);
+        if (by + 2 > n) return false;
+        const uint32_t v = ((uint32_t)in[by] | ((uint32_t)in[by + 1] << 8)) >> (bit & 7);
+        return (v & 7u) == 4u;
+    }
+    size_t n_out() const { return used - WIN; }
+
+private:
+    uint64_t bit_pos() const { return 8ull * (uint64_t)(ip_ - in_) - (uint64_t)bitcnt_; }
+    void seek_bit(uint64_t bit) {
+        ip_ = in_ + (size_t)(bit >> 3);
+        bitbuf_ = 0; bitcnt_ = 0;
+        refill();
+        if (bitcnt_ >= (int)(bit & 7)) drop((int)(bit & 7));
+    }
+    // the symbol loop of GzInflate::codes with 16-bit output and no round limit (one block)
+    bool codes16(size_t max_out) {
+        const uint32_t* const dt = dtab_.data();
+        size_t op = used;
+        refill();
+        uint32_t e = litlen_entry_at_bits();
+        for (;;) {
+            if (op + 600 > sym.size()) {
+                if (op > max_out + WIN) { used = op; return fail("span grows beyond its bound"); }
+                sym.resize(sym.size() * 2);
+            }
+            uint16_t* const ob = sym.data();
+            if (!e) { used = op; return fail("invalid literal/length code in the stream"); }
+            if ((int)(e & 31) > bitcnt_) { used = op; return fail("truncated stream"); }
+            if ((e & T_MASK) == T_LIT) {
+                drop(e & 31);
+                ob[op++] = (uint16_t)(e >> 16);
+                for (int rep = 0; rep < 2; rep++) {
+                    const uint32_t e2 = ltab_[peek(LBITS)];
+                    if ((e2 & T_MASK) != T_LIT || !e2 || (int)(e2 & 31) > bitcnt_) break;
+                    drop(e2 & 31);
+                    ob[op++] = (uint16_t)(e2 >> 16);
+                }
+                refill();
+                e = litlen_entry_at_bits();
+                continue;
+            }
+            drop(e & 31);
+            if ((e & T_MASK) == T_EOB) { used = op; return true; }
+            const int lx = (int)((e >> 5) & 31);
+            uint32_t len = (e >> 16);
+            if (len == 0xFFFFu) { used = op; return fail("invalid length symbol"); }
+            len += peek(lx);
+            drop(lx);
+            uint32_t d = dt[peek(DBITS)];
+            if ((d & T_MASK) == T_SUB) { const int pb = (int)(d & 31), sb = (int)((d >> 5) & 31); d = dt[(d >> 16) + ((uint32_t)(bitbuf_ >> pb) & ((1u << sb) - 1))]; if (d) d += (uint32_t)pb; }
+            if (!d || (d >> 16) == 0xFFFFu) { used = op; return fail("invalid distance code in the stream"); }
+            const int dx = (int)((d >> 5) & 31);
+            if ((int)(d & 31) + dx > bitcnt_) { used = op; return fail("truncated stream"); }
+            drop(d & 31);
+            const size_t dist = (size_t)(d >> 16) + peek(dx);
+            drop(dx);
+            if (dist > op) { used = op; return fail("distance reaches before the window"); }
+            refill();
+            e = litlen_entry_at_bits();
+            const uint16_t* src = ob + op - dist;
+            uint16_t* dst = ob + op;
+            if (src[0] == UNKNOWN) { used = op; return fail("distance reaches before the start of the data"); }
+            op += len;
+            if (dist >= 8) {                       // sixteen bytes = eight symbols at a time (the slack absorbs the overrun)
+                uint16_t* const end = dst + len;
+                do { uint64_t w0, w1; memcpy(&w0, src, 8); memcpy(&w1, src + 4, 8); memcpy(dst, &w0, 8); memcpy(dst + 4, &w1, 8); src += 8; dst += 8; } while (dst < end);
+            } else if (dist >= 4) {
+                uint16_t* const end = dst + len;
+                do { uint64_t w; memcpy(&w, src, 8); memcpy(dst, &w, 8); src += 4; dst += 4; } while (dst < end);
+            } else {
+                for (uint32_t i = 0; i < len; i++) dst[i] = src[i];
+            }
+        }
+    }
+};
+
+// Drives spans over one gzip member: text comes out in order through read().  Anything it is not made for (a second
+// member, a span that outgrows its bound, a file that is too small to be worth it) goes to the serial decoder.
+class GzParallel {
+public:
+    void reset(const uint8_t* in, size_t n, int threads, size_t span_bytes) {
+        in_ = in; n_ = n; T_ = std::max(1, threads); span_ = std::max<size_t>(span_bytes, 1u << 16);
+        err_.clear(); text_.clear(); tpos_ = 0; done_ = false; serial_ = false; started_ = false;
+        window_.clear(); crc_ = 0; total_ = 0; next_bit_ = 0;
+        spans_.resize((size_t)T_);
+    }
+    const std::string& error() const { return err_; }
+    size_t read(uint8_t* out, size_t cap) {
+        size_t got = 0;
+        while (got < cap) {
+            if (tpos_ < text_.size()) {            // what the last batch produced
+                const size_t m = std::min(cap - got, text_.size() - tpos_);
+                memcpy(out + got, text_.data() + tpos_, m);
+                tpos_ += m; got += m;
+                continue;
+            }
+            if (serial_) {
+                const size_t g = z_.read(out + got, cap - got);
+                if (g == 0) { if (!z_.error().empty()) err_ = z_.error(); break; }
+                got += g;
+                continue;
+            }
+            if (done_ || !err_.empty()) break;
+            if (!batch() && !serial_) break;
+        }
+        return got;
+    }
+
+private:
+    const uint8_t* in_ = nullptr;
+    size_t n_ = 0, span_ = 0;
+    int T_ = 1;
+    std::string err_;
+    std::vector<uint8_t> text_;                    // resolved text of the last batch
+    size_t tpos_ = 0;
+    bool done_ = false, serial_ = false, started_ = false;
+    std::vector<uint8_t> window_;                  // last <= 32 KiB of text before next_bit_
+    uint32_t crc_ = 0;
+    uint64_t total_ = 0, next_bit_ = 0;            // member so far: CRC, length; where its next block starts
+    std::vector<GzSpan> spans_;
+    GzInflate z_;
+
+    bool fail(const std::string& m) { err_ = m; return false; }
+    // the rest of the file through the serial decoder, as a fresh stream from byte `at`
+    void go_serial(size_t at) { z_.reset(in_ + at, n_ - at); serial_ = true; }
+
+    template <class F>
+    static void parallel(int T, F&& f) {
+        std::vector<std::thread> th;
+        for (int t = 1; t < T; t++) th.emplace_back([&f, t] { f(t); });
+        f(0);
+        for (auto& x : th) x.join();
+    }
+
+    bool batch() {
+        if (!started_) {                           // the member header: the serial decoder's parser knows it
+            struct H : GzInflate { bool parse(const uint8_t* in, size_t n, size_t& deflate_at, std::string& e) { reset(in, n); if (!member_header()) { e = err_; return false; } if (eof_) { deflate_at = n; return true; } deflate_at = (size_t)(ip_ - in_); return true; } } h;
+            size_t at = 0;
+            if (!h.parse(in_, n_, at, err_)) return false;
+            if (at >= n_) { done_ = true; return false; }
+            next_bit_ = 8ull * at;
+            started_ = true;
+        }
+        const uint64_t nbits = 8ull * n_;
+        // span t nominally covers compressed bytes [base + t span_, base + (t + 1) span_)
+        const size_t base = (size_t)(next_bit_ >> 3);
+        std::vector<uint64_t> start((size_t)T_, 0);
+        std::vector<char> ok((size_t)T_, 0);
+        const size_t max_out = span_ * 64;         // a span that expands more than this is not sequence text: serial decoder
+        parallel(T_, [&](int t) {
+            GzSpan& S = spans_[(size_t)t];
+            const uint64_t nominal = 8ull * (base + (size_t)t * span_), stop = std::min<uint64_t>(nbits, 8ull * (base + (size_t)(t + 1) * span_));
+            if (t == 0) {
+                start[0] = next_bit_;
+                ok[0] = S.run(in_, n_, next_bit_, stop, window_.data(), window_.size(), true, max_out) ? 1 : 0;
+                return;
+            }
+            if (nominal + 64 >= nbits) return;
+            for (uint64_t b = nominal; b < stop; b++) {          // the first offset from which everything decodes
+                if (!GzSpan::plausible(in_, n_, b)) continue;
+                if (S.run(in_, n_, b, stop, nullptr, 0, false, max_out)) { start[(size_t)t] = b; ok[(size_t)t] = 1; return; }
+            }
+        });
+        if (!ok[0]) {
+            // span 0 starts at a true block boundary with its true window: its failure is the stream's (or the bound's)
+            const std::string& e = spans_[0].error();
+            if (e.find("beyond its bound") == std::string::npos) return fail(e.empty() ? "gzip: damaged stream" : e);
+            // text that expands more than 64x is not what the marker scheme is for: the serial decoder takes the
+            // member over where it stands
+            z_.resume(in_, n_, next_bit_, window_.data(), window_.size(), crc_, total_);
+            serial_ = true;
+            text_.clear(); tpos_ = 0;
+            return true;
+        }
+        // join the spans: span t is kept only if the text before it ended exactly where it started
+        int used = 1;
+        uint64_t end = spans_[0].end_bit;
+        bool final = spans_[0].hit_final;
+        while (!final && used < T_ && ok[(size_t)used] && start[(size_t)used] == end) {
+            end = spans_[(size_t)used].end_bit;
+            final = spans_[(size_t)used].hit_final;
+            used++;
+        }
+        // windows in order (each needs the resolved tail of the span before it), then every span's text in parallel
+        std::vector<std::vector<uint8_t>> win((size_t)used + 1);
+        win[0] = window_;
+        std::vector<size_t> off((size_t)used + 1, 0);
+        for (int t = 0; t < used; t++) off[(size_t)t + 1] = off[(size_t)t] + spans_[(size_t)t].n_out();
+        for (int t = 0; t < used; t++) {
+            const GzSpan& S = spans_[(size_t)t];
+            const std::vector<uint8_t>& w = win[(size_t)t];
+            const size_t have = S.used;            // window image + text
+            const size_t take = std::min<size_t>(32768, S.n_out() + w.size());
+            std::vector<uint8_t>& nw = win[(size_t)t + 1];
+            nw.resize(take);
+            for (size_t j = 0; j < take; j++) {
+                const uint16_t v = S.sym[have - take + j];
+                if (v < 256) nw[j] = (uint8_t)v;
+                else {
+                    const size_t k = (size_t)v - 256;            // byte k of the 32 KiB image before the span
+                    if (v == GzSpan::UNKNOWN || k + w.size() < 32768) return fail("gzip: distance reaches before the start of the data");
+                    nw[j] = w[k - (32768 - w.size())];
+                }
+            }
+        }
+        text_.resize(off[(size_t)used]);
+        tpos_ = 0;
+        std::vector<uint32_t> crcs((size_t)used, 0);
+        std::vector<char> bad((size_t)used, 0);
+        parallel(used, [&](int t) {
+            const GzSpan& S = spans_[(size_t)t];
+            const std::vector<uint8_t>& w = win[(size_t)t];
+            uint8_t* dst = text_.data() + off[(size_t)t];
+            const uint16_t* src = S.sym.data() + 32768;
+            const size_t m = S.n_out(), wpad = 32768 - w.size();
+            size_t j = 0;
+            while (j < m) {
+                // eight symbols at once while none of them is a marker (all of them, a window's reach into the span)
+                while (j + 8 <= m) {
+                    uint64_t a, b;
+                    memcpy(&a, src + j, 8); memcpy(&b, src + j + 4, 8);
+                    if ((a | b) & 0xFF00FF00FF00FF00ull) break;
+                    const uint64_t lo = (a & 0xFF) | ((a >> 8) & 0xFF00) | ((a >> 16) & 0xFF0000) | ((a >> 24) & 0xFF000000ull);
+                    const uint64_t hi = (b & 0xFF) | ((b >> 8) & 0xFF00) | ((b >> 16) & 0xFF0000) | ((b >> 24) & 0xFF000000ull);
+                    const uint64_t o = lo | (hi << 32);
+                    memcpy(dst + j, &o, 8);
+                    j += 8;
+                }
+                if (j >= m) break;
+                const uint16_t v = src[j];
+                if (v < 256) dst[j] = (uint8_t)v;
+                else if (v == GzSpan::UNKNOWN || (size_t)v - 256 < wpad) { bad[(size_t)t] = 1; dst[j] = 0; }
+                else dst[j] = w[(size_t)v - 256 - wpad];
+                j++;
+            }
+            crcs[(size_t)t] = GzInflate::crc32_of(dst, m);
+        });
+        for (int t = 0; t < used; t++) {
+            if (bad[(size_t)t]) return fail("gzip: distance reaches before the start of the data");
+            crc_ = (uint32_t)crc32_combine(crc_, crcs[(size_t)t], (z_off_t)spans_[(size_t)t].n_out());
+            total_ += spans_[(size_t)t].n_out();
+        }
+        window_ = win[(size_t)used];
+        next_bit_ = end;
+        if (final) {                               // trailer, then whatever follows goes to the serial decoder
+            const size_t tr = (size_t)((end + 7) >> 3);
+            if (n_ - tr < 8) return fail("gzip: truncated trailer");
+            const uint32_t crc = in_[tr] | (in_[tr + 1] << 8) | (in_[tr + 2] << 16) | ((uint32_t)in_[tr + 3] << 24);
+            const uint32_t isz = in_[tr + 4] | (in_[tr + 5] << 8) | (in_[tr + 6] << 16) | ((uint32_t)in_[tr + 7] << 24);
+            if (crc != crc_) return fail("gzip: CRC-32 mismatch");
+            if (isz != (uint32_t)total_) return fail("gzip: length mismatch");
+            go_serial(tr + 8);                     // further members, zero padding or the end of the file
+            if (text_.empty()) return true;        // (read() goes on with the serial decoder)
+        }
+        return true;
     }
 };
 

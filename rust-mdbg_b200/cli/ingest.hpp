@@ -145,6 +145,13 @@ public:
                 // independent, so a block's worth of them is inflated by all threads at once
                 gzpos_ = 0;
                 bgzf_ = bgzf_member(0, nullptr, nullptr) && !getenv("MDBG_GZ_SERIAL");
+                // one plain gzip stream of some size: spans of it are inflated by all threads (GzParallel); below
+                // three threads or a few MB the serial decoder is as fast
+                size_t par_min = 16u << 20, span = 2u << 20;
+                if (const char* e = getenv("MDBG_GZ_PAR_MIN")) par_min = (size_t)atoll(e);
+                if (const char* e = getenv("MDBG_GZ_SPAN")) span = (size_t)std::max<long long>(1 << 16, atoll(e));
+                gzpar_ = !bgzf_ && nthreads_ >= 3 && size_ >= par_min && !getenv("MDBG_GZ_SERIAL");
+                if (gzpar_) zpar_.reset(gzmap_, size_, nthreads_, span);
             } else {
                 gz_ = gzdopen(dup(fd_), "rb");
                 if (!gz_) return false;
@@ -173,7 +180,7 @@ public:
         gz_eof_ = false; gz_eof_done_ = false; carry_.clear();
         if (gz_) { gzclose(gz_); gz_ = nullptr; }
         if (gzmap_) { munmap((void*)gzmap_, size_); gzmap_ = nullptr; }
-        gz_on_ = false;
+        gz_on_ = false; gzpar_ = false; bgzf_ = false;
         if (map_) { munmap((void*)map_, size_); map_ = nullptr; }
         if (fd_ >= 0) { ::close(fd_); fd_ = -1; }
     }
@@ -321,6 +328,11 @@ private:
             bgzf_ = false;
             zfast_.reset(gzmap_ + gzpos_, size_ - gzpos_);
         }
+        if (gzmap_ && gzpar_) {
+            const size_t got = zpar_.read(reinterpret_cast<uint8_t*>(dst), cap);
+            if (got == 0 && !zpar_.error().empty()) gz_err_ = zpar_.error();
+            return (long)got;
+        }
         if (gzmap_) {
             const size_t got = zfast_.read(reinterpret_cast<uint8_t*>(dst), cap);
             if (got == 0 && !zfast_.error().empty()) gz_err_ = zfast_.error();
@@ -400,7 +412,8 @@ private:
     const uint8_t* gzmap_ = nullptr; // the compressed file, mapped
     GzInflate zfast_;
     std::vector<GzInflate> zpool_;   // one decoder per thread for block gzip
-    bool bgzf_ = false;
+    bool bgzf_ = false, gzpar_ = false;
+    GzParallel zpar_;                // one plain gzip stream inflated by all threads
     size_t gzpos_ = 0;               // block gzip: next member's offset in the file
     std::string gz_err_;
     // gz pipeline

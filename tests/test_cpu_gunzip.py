@@ -18,12 +18,17 @@ EXE = os.path.join(HERE, "model", "gunzip_check")
 
 @pytest.fixture(scope="module")
 def exe():
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-o", EXE, os.path.join(HERE, "model", "gunzip_check.cpp"), "-lz"])
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-pthread", "-o", EXE, os.path.join(HERE, "model", "gunzip_check.cpp"), "-lz"])
     return EXE
 
 
-def gunzip(exe, path, chunk=None):
-    r = subprocess.run([exe, path] + (["--raw", str(chunk)] if chunk else []), capture_output=True, timeout=300)
+def gunzip(exe, path, chunk=None, par=None):
+    args = [exe, path]
+    if chunk or par:
+        args += ["--raw", str(chunk or (1 << 20))]
+    if par:
+        args += [str(par[0]), str(par[1])]          # the parallel single-stream decoder: threads, span bytes
+    r = subprocess.run(args, capture_output=True, timeout=300)
     return r.returncode, r.stdout, r.stderr.decode()
 
 
@@ -190,7 +195,7 @@ def test_damaged_streams_under_sanitizers(tmp_path):
     """The decoder built with AddressSanitizer + UBSan on truncated, bit-flipped and random streams: every one is either
     decoded or refused with a message -- no out-of-bounds access, no undefined shift, no crash."""
     san = str(tmp_path / "gunzip_san")
-    r = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined",
+    r = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-pthread", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined",
                         "-o", san, os.path.join(HERE, "model", "gunzip_check.cpp"), "-lz"], capture_output=True, text=True)
     if r.returncode != 0:
         pytest.skip("no sanitizer runtime in this image: " + r.stderr[-200:])
@@ -204,11 +209,85 @@ def test_damaged_streams_under_sanitizers(tmp_path):
     for pos in range(10, len(small)):
         b = bytearray(small); b[pos] ^= 1 << (pos % 8); cases.append(bytes(b))
     p = str(tmp_path / "f.gz")
-    for blob in cases:
+    for n, blob in enumerate(cases):
         open(p, "wb").write(blob)
-        r = subprocess.run([san, p, "--hash"], capture_output=True, text=True, timeout=60)
-        assert r.returncode in (0, 1), (r.returncode, r.stderr[-500:])
-        assert "runtime error" not in r.stderr and "AddressSanitizer" not in r.stderr, r.stderr[-800:]
-        if r.returncode == 1:
-            assert r.stderr.startswith("gzip:") or "stopped" in r.stderr, r.stderr[-300:]
+        for extra in ([], ["1048576", "4", "65536"]) if n % 3 == 0 else ([],):      # every third one through GzParallel too
+            r = subprocess.run([san, p, "--hash"] + extra, capture_output=True, text=True, timeout=60)
+            assert r.returncode in (0, 1), (r.returncode, r.stderr[-500:])
+            assert "runtime error" not in r.stderr and "AddressSanitizer" not in r.stderr, r.stderr[-800:]
+            if r.returncode == 1:
+                assert r.stderr.startswith("gzip:") or "stopped" in r.stderr, r.stderr[-300:]
+
+
+PAR = [(1, 1 << 16), (3, 1 << 16), (8, 70000), (5, 1 << 20), (16, 200000)]
+
+
+@pytest.mark.parametrize("level", [1, 6, 9])
+def test_parallel_single_stream(exe, tmp_path, level):
+    """GzParallel: spans of ONE gzip stream decoded by several threads from block starts they find themselves, unknown
+    windows as 16-bit markers resolved afterwards, spans joined only where they meet exactly: same bytes as zlib for every
+    thread count and span size (tiny spans: a join every few blocks)."""
+    rng = np.random.default_rng(30 + level)
+    text = fasta(rng, 400, 12000)
+    p = str(tmp_path / "x.gz")
+    open(p, "wb").write(gzip.compress(text, level))
+    for par in PAR:
+        rc, out, err = gunzip(exe, p, par=par)
+        assert rc == 0, (par, err)
+        assert out == text, (par, len(out), len(text))
+
+
+def test_parallel_odd_streams(exe, tmp_path):
+    """What the block finder does not look for or the marker scheme is not made for must still come out right: stored and
+    fixed-Huffman blocks, incompressible and extremely compressible stretches (the serial decoder takes over mid-member),
+    several members, an empty member first, tiny files, binary data with long codes."""
+    rng = np.random.default_rng(40)
+    dna_text = fasta(rng, 150, 15000)
+    noise = bytes(rng.integers(0, 256, 600000, dtype=np.uint8))
+    p8 = np.array([2.0 ** -(i // 8) for i in range(256)]); p8 /= p8.sum()
+    skew = bytes(rng.choice(256, 500000, p=p8).astype(np.uint8))
+    cases = {
+        "stored": gzip.compress(dna_text, 0),
+        "fixed": member(dna_text, 6, zlib.Z_FIXED),
+        "huffman_only": member(dna_text, 6, zlib.Z_HUFFMAN_ONLY),
+        "rle": member(dna_text + b"A" * 3000000 + dna_text, 6, zlib.Z_RLE),
+        "mixed": gzip.compress(dna_text + noise + dna_text[:200000] + b"ACGT" * 2000000 + dna_text[-300000:] + skew, 6),
+        "very_compressible": gzip.compress(b"A" * 50000000 + dna_text, 6),
+        "members": member(dna_text[:700000], 6) + member(b"", 6) + member(dna_text[700000:], 1) + member(noise, 6),
+        "empty_first": member(b"", 6) + gzip.compress(dna_text, 6),
+        "tiny": gzip.compress(b"ACGT\n", 6),
+        "empty": gzip.compress(b"", 6),
+        "padded": gzip.compress(dna_text, 6) + b"\0" * 100,
+    }
+    for name, blob in cases.items():
+        p = str(tmp_path / (name + ".gz"))
+        open(p, "wb").write(blob)
+        ref = dna_text if name == "padded" else gzip.decompress(blob)
+        for par in ((4, 1 << 16), (7, 300000), (2, 4 << 20)):
+            rc, out, err = gunzip(exe, p, par=par)
+            assert rc == 0, (name, par, err)
+            assert out == ref, (name, par, len(out), len(ref))
+
+
+def test_parallel_damaged_streams_are_refused(exe, tmp_path):
+    rng = np.random.default_rng(41)
+    text = fasta(rng, 200, 12000)
+    good = gzip.compress(text, 6)
+    bad = {"truncated": good[:len(good) // 2], "no_trailer": good[:-8], "crc": good[:-8] + bytes([good[-8] ^ 1]) + good[-7:],
+           "isize": good[:-1] + bytes([good[-1] ^ 0x40]), "garbage_after": good + b"garbage"}
+    for k, pos in enumerate(rng.integers(12, len(good) - 10, 60)):
+        b = bytearray(good); b[int(pos)] ^= 1 << int(rng.integers(0, 8)); bad["flip%d" % k] = bytes(b)
+    for name, blob in bad.items():
+        p = str(tmp_path / (name + ".gz"))
+        open(p, "wb").write(blob)
+        try:
+            ref = gzip.decompress(blob)
+        except Exception:
+            ref = None
+        for par in ((4, 1 << 16), (3, 500000)):
+            rc, out, err = gunzip(exe, p, par=par)
+            if ref is None:
+                assert rc == 1 and "gzip" in err, (name, par, rc, err)
+            else:
+                assert rc == 0 and out == ref, (name, par)
 

@@ -173,3 +173,29 @@ def test_block_gzip_is_inflated_in_parallel(exe, tmp_path):
     r = subprocess.run([exe, bad, "fasta", "4", str(1 << 20)], capture_output=True, text=True)
     assert r.returncode == 1 and "gzip" in r.stderr, (r.returncode, r.stderr[-200:])
 
+
+def test_plain_gzip_is_inflated_in_parallel(exe, tmp_path):
+    """One gzip stream above the size threshold (lowered here) goes through GzParallel: same records as the serial
+    decoder and as zlib for FASTA and FASTQ, small spans, many threads; damage is an error."""
+    rng = np.random.default_rng(23)
+    recs = make_records(rng, 1200, mean=6000)
+    fa = b"".join(b">" + i.encode() + b"\n" + s + b"\n" for i, s in recs)
+    fq = b"".join(b"@" + i.encode() + b"\n" + s + b"\n+\n" + bytes(rng.integers(33, 74, len(s), dtype=np.uint8)) + b"\n" for i, s in recs)
+    exp = expected(recs)
+    par = {"MDBG_GZ_PAR_MIN": "0", "MDBG_GZ_SPAN": "65536"}
+    for name, text, fmt in (("x.fa.gz", fa, "fasta"), ("x.fq.gz", fq, "fastq")):
+        p = str(tmp_path / name)
+        open(p, "wb").write(gzip.compress(text, 6))
+        for env in (par, {**par, "MDBG_GZ_SPAN": "1000000"}, {"MDBG_GZ_SERIAL": "1"}, {"MDBG_GZ_ZLIB": "1"}):
+            for threads, target in ((3, 1 << 30), (8, 1 << 20), (16, 300000)):
+                out = subprocess.run([exe, p, fmt, str(threads), str(target)], capture_output=True, text=True, check=True,
+                                     env={**os.environ, **env}).stdout
+                assert [tuple(x.split("\t")) for x in out.splitlines()] == exp, (name, env, threads)
+    good = open(str(tmp_path / "x.fa.gz"), "rb").read()
+    flipped = bytearray(good); flipped[len(good) // 3] ^= 0x20
+    for name, blob in (("truncated", good[:len(good) // 2]), ("flipped", bytes(flipped))):
+        bad = str(tmp_path / (name + ".fa.gz"))
+        open(bad, "wb").write(blob)
+        r = subprocess.run([exe, bad, "fasta", "6", str(1 << 20)], capture_output=True, text=True, env={**os.environ, **par})
+        assert r.returncode == 1 and "gzip" in r.stderr, (name, r.returncode, r.stderr[-200:])
+
