@@ -681,7 +681,8 @@ private:
         const size_t base = (size_t)(next_bit_ >> 3);
         std::vector<uint64_t> start((size_t)T_, 0);
         std::vector<char> ok((size_t)T_, 0);
-        const size_t max_out = span_ * 64;         // a span that expands more than this is not sequence text: serial decoder
+        const size_t max_out = span_ * 24;         // a span that expands more than this is not sequence text (3.5-5x): serial
+                                                   // decoder; also bounds the memory of a batch (2 B per symbol and span)
         parallel(T_, [&](int t) {
             GzSpan& S = spans_[(size_t)t];
             const uint64_t nominal = 8ull * (base + (size_t)t * span_), stop = std::min<uint64_t>(nbits, 8ull * (base + (size_t)(t + 1) * span_));
@@ -700,7 +701,7 @@ private:
             // span 0 starts at a true block boundary with its true window: its failure is the stream's (or the bound's)
             const std::string& e = spans_[0].error();
             if (e.find("beyond its bound") == std::string::npos) return fail(e.empty() ? "gzip: damaged stream" : e);
-            // text that expands more than 64x is not what the marker scheme is for: the serial decoder takes the
+            // text that expands more than 24x is not what the marker scheme is for: the serial decoder takes the
             // member over where it stands
             z_.resume(in_, n_, next_bit_, window_.data(), window_.size(), crc_, total_);
             serial_ = true;
